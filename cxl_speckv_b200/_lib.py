@@ -1,0 +1,80 @@
+"""ctypes binding of libcxlspeckv.so (include/speckv.h + include/speckv_ext.h)."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+PKG = os.path.dirname(os.path.abspath(__file__))
+
+SPECKV_OK, SPECKV_ERR_GENERAL, SPECKV_ERR_DRIVER, SPECKV_ERR_NOMEM, SPECKV_ERR_INVAL = 0, -1, -2, -3, -4
+COMP_FP16, COMP_INT8, COMP_INT8_DELTA_RLE = 0, 1, 2
+DTYPE_F16, DTYPE_BF16, DTYPE_F32 = 0, 1, 2
+
+_STATUS = {0: "SPECKV_OK", -1: "SPECKV_ERR_GENERAL", -2: "SPECKV_ERR_DRIVER", -3: "SPECKV_ERR_NOMEM",
+           -4: "SPECKV_ERR_INVAL"}
+
+
+class SpeckvError(RuntimeError):
+    def __init__(self, what: str, status: int):
+        super().__init__(f"{what} failed: {_STATUS.get(status, status)}")
+        self.status = status
+
+
+class Stats(C.Structure):
+    _fields_ = [("total_compressions", C.c_uint64), ("total_decompressions", C.c_uint64),
+                ("total_translations", C.c_uint64), ("bytes_in_compress", C.c_uint64),
+                ("bytes_out_decompress", C.c_uint64)]
+
+
+def lib_path() -> str:
+    return os.environ.get("SPECKV_LIB", os.path.join(PKG, "libcxlspeckv.so"))
+
+
+_LIB = None
+
+
+def lib() -> C.CDLL:
+    """Loads libcxlspeckv.so.  Raises if it has not been built: there is no fallback path."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = lib_path()
+    if not os.path.exists(path):
+        raise ImportError(f"{path} not found: build it with `python -m cxl_speckv_b200.build` "
+                          "(nvcc, sm_100a). The CUDA library is the product; there is no CPU fallback.")
+    L = C.CDLL(path)
+    vp, sz, u32p, f32p, u64p = C.c_void_p, C.c_size_t, C.POINTER(C.c_uint32), C.POINTER(C.c_float), C.POINTER(C.c_uint64)
+    # frozen ABI (speckv.h)
+    L.speckv_init.argtypes = [C.c_char_p]; L.speckv_init.restype = C.c_int
+    L.speckv_finalize.argtypes = []; L.speckv_finalize.restype = None
+    L.speckv_alloc.argtypes = [sz, vp, C.POINTER(C.c_uint64)]; L.speckv_alloc.restype = C.c_int
+    L.speckv_free.argtypes = [C.c_uint64]; L.speckv_free.restype = C.c_int
+    L.speckv_access.argtypes = [C.c_uint64, C.c_uint64, sz, C.POINTER(vp)]; L.speckv_access.restype = C.c_int
+    L.speckv_prefetch.argtypes = [C.c_uint32, C.c_uint16, C.c_uint32, C.c_uint32, C.POINTER(C.c_int32), C.c_uint32]
+    L.speckv_prefetch.restype = C.c_int
+    L.speckv_set_prefetch_depth.argtypes = [C.c_uint32]; L.speckv_set_prefetch_depth.restype = C.c_int
+    L.speckv_set_compression_scheme.argtypes = [C.c_int]; L.speckv_set_compression_scheme.restype = C.c_int
+    # additive ABI (speckv_ext.h)
+    L.speckv_ext_device_count.argtypes = []; L.speckv_ext_device_count.restype = C.c_int
+    L.speckv_ext_version.argtypes = []; L.speckv_ext_version.restype = C.c_char_p
+    L.speckv_ext_slot_bytes.argtypes = [sz, C.c_int]; L.speckv_ext_slot_bytes.restype = sz
+    L.speckv_ext_compress.argtypes = [vp, C.c_int, sz, sz, vp, sz, vp, vp, C.c_int, vp]
+    L.speckv_ext_compress.restype = C.c_int
+    L.speckv_ext_decompress.argtypes = [vp, sz, vp, vp, sz, sz, C.c_int, vp, vp, C.c_int, vp]
+    L.speckv_ext_decompress.restype = C.c_int
+    L.speckv_ext_compress_host.argtypes = [vp, C.c_int, sz, sz, vp, sz, vp, vp, C.c_int]
+    L.speckv_ext_compress_host.restype = C.c_int
+    L.speckv_ext_decompress_host.argtypes = [vp, sz, vp, vp, sz, sz, C.c_int, vp, vp, C.c_int]
+    L.speckv_ext_decompress_host.restype = C.c_int
+    L.speckv_ext_host_alloc.argtypes = [sz]; L.speckv_ext_host_alloc.restype = vp
+    L.speckv_ext_host_free.argtypes = [vp]; L.speckv_ext_host_free.restype = None
+    L.speckv_ext_translate.argtypes = [vp, vp, sz, vp]; L.speckv_ext_translate.restype = C.c_int
+    L.speckv_ext_get_stats.argtypes = [C.POINTER(Stats)]; L.speckv_ext_get_stats.restype = None
+    L.speckv_ext_reset_stats.argtypes = []; L.speckv_ext_reset_stats.restype = None
+    _LIB = L
+    return L
+
+
+def check(status: int, what: str) -> None:
+    if status != SPECKV_OK:
+        raise SpeckvError(what, status)

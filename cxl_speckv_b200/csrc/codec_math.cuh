@@ -1,0 +1,99 @@
+// codec_math.cuh -- bit-exact arithmetic of the KV block codec on sm_100a.
+//
+// Mirrors, operation for operation, what the reference computes on x86-64
+// (src/fpga_engine/cache_engine.cpp):
+//   scale  s = max|x| / 127.0f, or 1.0f if the max is 0             (:172-184)
+//   code   q = int8( (int32) roundf( (x / s) * 127.0f ) )           (:186-196)
+//            = low byte of the truncating float->int32 conversion; NaN and
+//              out-of-range give 0x80000000 -> 0 (cvttss2si), so codes WRAP
+//   value  y = ((float) q / 127.0f) * s                             (:275-284)
+// Every float op is an explicit round-to-nearest intrinsic so nvcc can neither
+// contract nor reassociate it; denormals are kept (no -ftz, no fast-math).
+#pragma once
+
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+
+namespace speckv {
+
+enum : int { DT_F16 = 0, DT_BF16 = 1, DT_F32 = 2 };
+
+// ---- widening / narrowing at the fp16 / bf16 boundary ------------------------
+template <typename T> __device__ __forceinline__ float widen(T v);
+template <> __device__ __forceinline__ float widen<__half>(__half v) { return __half2float(v); }
+template <> __device__ __forceinline__ float widen<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+template <> __device__ __forceinline__ float widen<float>(float v) { return v; }
+
+template <typename T> __device__ __forceinline__ T narrow(float v);
+template <> __device__ __forceinline__ __half narrow<__half>(float v) { return __float2half_rn(v); }
+template <> __device__ __forceinline__ __nv_bfloat16 narrow<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+template <> __device__ __forceinline__ float narrow<float>(float v) { return v; }
+
+// ---- scale --------------------------------------------------------------------
+// `abs_val > max_val` (cache_engine.cpp:176-179) never admits a NaN; fmaxf
+// returns the non-NaN operand, so with m starting at 0 it is the same function.
+__device__ __forceinline__ float absmax_step(float m, float x) { return fmaxf(m, fabsf(x)); }
+__device__ __forceinline__ float scale_from_max(float m) { return (m > 0.0f) ? __fdiv_rn(m, 127.0f) : 1.0f; }
+
+// ---- rounding + the wrapping cast ------------------------------------------------
+// std::round (half away from zero) then static_cast<int8_t>:
+//   roundf(t) == sign(t) * floor(|t| + 0.5); the add is done round-toward-zero
+//   so that 0.49999997f + 0.5f does not round up to 1.0f.
+// kRangeCheck is needed only when |t| may reach 2^31 or be +-inf (x86 yields
+// the "integer indefinite" 0x80000000 there, whose low byte is 0; cvt.rzi
+// would saturate instead).  NaN converts to 0 on both machines.
+template <bool kRangeCheck>
+__device__ __forceinline__ uint32_t round_wrap_u8(float t) {
+    float a = __fadd_rz(fabsf(t), 0.5f);
+    int k = __float2int_rz(a);
+    if (kRangeCheck) {
+        if (!(a < 2147483648.0f)) k = 0;
+    }
+    k = (t < 0.0f) ? -k : k;
+    return (uint32_t)k & 0xffu;
+}
+
+// ---- quantiser --------------------------------------------------------------------
+// Exact form: two IEEE operations as written in the reference.
+__device__ __forceinline__ uint32_t quantize_exact(float x, float s) {
+    float y = __fdiv_rn(x, s);
+    return round_wrap_u8<true>(__fmul_rn(y, 127.0f));
+}
+
+// Fast form: with r = RN(1/s) (computed once per group with __frcp_rn) one
+// residual correction reproduces RN(x/s):
+//     y0 = RN(x*r);  e = RN(x - y0*s) (exact, FMA);  y = RN(y0 + e*r)
+// oracle/verify_fastdiv.c proves by exhaustion that the resulting CODE equals
+// the reference's for every (x, max) pair of fp16 values, and for every pair of
+// bf16 values with max >= 2^-60; groups outside that domain (and fp32 input)
+// take quantize_exact.  |t| <= 16130 here, so no range check is needed.
+__device__ __forceinline__ uint32_t quantize_fast(float x, float s, float r) {
+    float y0 = __fmul_rn(x, r);
+    float e = __fmaf_rn(-y0, s, x);
+    float y = __fmaf_rn(e, r, y0);
+    return round_wrap_u8<false>(__fmul_rn(y, 127.0f));
+}
+
+// Is the fast form valid for a group whose max-abs is m (element type T)?
+template <typename T> __device__ __forceinline__ bool fast_quant_ok(float m);
+template <> __device__ __forceinline__ bool fast_quant_ok<__half>(float m) { return m > 0.0f && m < __int_as_float(0x7f800000); }
+template <> __device__ __forceinline__ bool fast_quant_ok<__nv_bfloat16>(float m) {
+    return m >= 8.673617379884035e-19f /* 2^-60 */ && m < __int_as_float(0x7f800000);
+}
+template <> __device__ __forceinline__ bool fast_quant_ok<float>(float) { return false; }
+
+// ---- dequantiser -------------------------------------------------------------------
+// (float) q / 127.0f * s with q the signed code.  q/127 is an IEEE division by a
+// constant; oracle/verify_fastdiv.c checks all 256 codes against the identity
+//     y0 = RN(q*r127);  y = RN(y0 + RN(q - y0*127)*r127),  r127 = RN(1/127)
+__device__ __forceinline__ float dequantize(uint32_t code_u8, float s) {
+    float qf = (float)(int)(int8_t)code_u8;
+    const float r127 = 0.007874015718698502f;  // RN(1/127) = 0x3c010204
+    float y0 = __fmul_rn(qf, r127);
+    float e = __fmaf_rn(-y0, 127.0f, qf);
+    float y = __fmaf_rn(e, r127, y0);
+    return __fmul_rn(y, s);
+}
+
+}  // namespace speckv

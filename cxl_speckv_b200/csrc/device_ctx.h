@@ -1,0 +1,10 @@
+// device_ctx.h -- process-wide CUDA device bookkeeping shared by the C ABI files.
+#pragma once
+#include <cuda_runtime.h>
+#include "../../include/speckv.h"
+namespace speckv {
+int device_count();                       // 0 when no CUDA device is usable
+int current_sm_count();                   // SMs of the current device
+speckv_status_t status_of(cudaError_t e); // cudaError_t -> speckv_status_t (clears the sticky error)
+void release_host_pipe();                 // frees the staging buffers of the *_host calls
+}  // namespace speckv

@@ -1,0 +1,516 @@
+// kv_codec_generic.cu -- KV block codec, generic path (any group size / alignment).
+//
+// One CTA owns one group at a time and walks it in tiles, carrying the encoder
+// state (last code, last delta, last natural change, last run head, pairs
+// emitted) from tile to tile, so delta and RLE run over the whole flat group
+// exactly as the reference does (src/fpga_engine/cache_engine.cpp:198-239).
+// Used for odd group sizes, unaligned buffers and fp32 input; the tuned
+// kernels for the common geometries live in kv_codec_fast.cu.
+//
+// Reference functions replaced:
+//   compress   = compute_scale_factor + quantize_to_int8 + delta_encode +
+//                run_length_encode                     cache_engine.cpp:40-82,172-239
+//   decompress = run_length_decode + delta_decode + dequantize_from_int8
+//                                                      cache_engine.cpp:84-116,241-284
+#include "codec_math.cuh"
+#include "kv_codec.h"
+
+namespace speckv {
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kWarps = kThreads / 32;
+constexpr int kEPT = 16;                     // elements per thread per tile (compress)
+constexpr int kTile = kThreads * kEPT;       // 4096 elements
+constexpr int kPPT = 8;                      // pairs per thread per chunk (decompress)
+constexpr int kChunk = kThreads * kPPT;      // 2048 pairs
+constexpr int kWindow = 4096;                // decompress staging window (elements)
+
+__device__ __forceinline__ uint4 ldg_stream(const uint4* p) {
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p));
+    return r;
+}
+
+// exclusive block scans; `wbuf` holds one int per warp.  Two __syncthreads each.
+__device__ __forceinline__ int block_excl_sum(int v, int& total, int* wbuf) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    int inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    if (lane == 31) wbuf[wid] = inc;
+    __syncthreads();
+    int before = 0, tot = 0;
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w) {
+        int x = wbuf[w];
+        if (w < wid) before += x;
+        tot += x;
+    }
+    __syncthreads();
+    total = tot;
+    return before + inc - v;
+}
+
+__device__ __forceinline__ int block_excl_max(int v, int& total, int* wbuf) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    int inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc = max(inc, t);
+    }
+    int excl = __shfl_up_sync(0xffffffffu, inc, 1);
+    if (lane == 0) excl = -1;
+    if (lane == 31) wbuf[wid] = inc;
+    __syncthreads();
+    int before = -1, tot = -1;
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w) {
+        int x = wbuf[w];
+        if (w < wid) before = max(before, x);
+        tot = max(tot, x);
+    }
+    __syncthreads();
+    total = tot;
+    return max(before, excl);
+}
+
+__device__ __forceinline__ float block_max_f(float v, float* wbuf) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    if (lane == 0) wbuf[wid] = v;
+    __syncthreads();
+    float m = wbuf[0];
+#pragma unroll
+    for (int w = 1; w < kWarps; ++w) m = fmaxf(m, wbuf[w]);
+    __syncthreads();
+    return m;
+}
+
+// max |x| over one group, coalesced 128-bit loads when the group is 16 B aligned
+template <typename T>
+__device__ __forceinline__ float group_absmax(const T* __restrict__ gin, uint32_t G, bool vec_ok, float* wbuf) {
+    constexpr int VN = 16 / sizeof(T);
+    float m = 0.0f;
+    uint32_t done = 0;
+    if (vec_ok) {
+        const uint32_t nvec = G / VN;
+        const uint4* p = reinterpret_cast<const uint4*>(gin);
+        for (uint32_t v = threadIdx.x; v < nvec; v += kThreads) {
+            uint4 w = ldg_stream(p + v);
+            const T* e = reinterpret_cast<const T*>(&w);
+#pragma unroll
+            for (int j = 0; j < VN; ++j) m = absmax_step(m, widen<T>(e[j]));
+        }
+        done = nvec * VN;
+    }
+    for (uint32_t i = done + threadIdx.x; i < G; i += kThreads) m = absmax_step(m, widen<T>(gin[i]));
+    return block_max_f(m, wbuf);
+}
+
+template <typename T>
+__device__ __forceinline__ void load_elems(const T* __restrict__ gin, uint32_t start, uint32_t G, bool vec_ok,
+                                           float (&x)[kEPT]) {
+    if (vec_ok && start + kEPT <= G) {
+        constexpr int NV = kEPT * sizeof(T) / 16;
+        uint4 v[NV];
+        const uint4* p = reinterpret_cast<const uint4*>(gin + start);
+#pragma unroll
+        for (int i = 0; i < NV; ++i) v[i] = __ldg(p + i);
+        const T* e = reinterpret_cast<const T*>(v);
+#pragma unroll
+        for (int j = 0; j < kEPT; ++j) x[j] = widen<T>(e[j]);
+    } else {
+#pragma unroll
+        for (int j = 0; j < kEPT; ++j) x[j] = (start + j < G) ? widen<T>(gin[start + j]) : 0.0f;
+    }
+}
+
+// ---------------------------------------------------------------------------------
+// compress, scheme INT8_DELTA_RLE
+// ---------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+compress_rle_generic_kernel(const T* __restrict__ in, uint32_t G, uint32_t n_groups,
+                            uint8_t* __restrict__ payload, size_t slot_bytes,
+                            float* __restrict__ scales, uint32_t* __restrict__ comp_bytes) {
+    __shared__ __align__(16) uint16_t stage[kTile + 16];
+    __shared__ int wbuf[kWarps];
+    __shared__ float fbuf[kWarps];
+    __shared__ uint32_t sh_q[kThreads], sh_d[kThreads];
+    __shared__ uint32_t carry_sm[3];
+    const int tid = threadIdx.x;
+
+    for (uint32_t g = blockIdx.x; g < n_groups; g += gridDim.x) {
+        const T* gin = in + (size_t)g * G;
+        uint8_t* gout = payload + (size_t)g * slot_bytes;
+        const bool vec_ok = (reinterpret_cast<uintptr_t>(gin) & 15) == 0;
+
+        const float m = group_absmax<T>(gin, G, vec_ok, fbuf);
+        const float s = scale_from_max(m);
+        const bool fast = fast_quant_ok<T>(m);
+        const float r = fast ? __frcp_rn(s) : 0.0f;
+
+        uint32_t carry_q = 0, carry_d = 0;
+        int carry_p0 = 0, carry_lh = 0, carry_nh = 0, stage_base = 0;
+
+        for (uint32_t tile = 0; tile < G; tile += kTile) {
+            const uint32_t start = tile + tid * kEPT;
+            const int cnt = start < G ? min((uint32_t)kEPT, G - start) : 0;
+            float x[kEPT];
+            load_elems<T>(gin, start, G, vec_ok, x);
+            uint32_t q[kEPT];
+            if (fast) {
+#pragma unroll
+                for (int j = 0; j < kEPT; ++j) q[j] = quantize_fast(x[j], s, r);
+            } else {
+#pragma unroll
+                for (int j = 0; j < kEPT; ++j) q[j] = quantize_exact(x[j], s);
+            }
+            if (cnt > 0) sh_q[tid] = q[cnt - 1];
+            __syncthreads();
+            const uint32_t prev_q = tid == 0 ? carry_q : sh_q[tid - 1];
+            uint32_t d[kEPT];
+#pragma unroll
+            for (int j = 0; j < kEPT; ++j) d[j] = (q[j] - (j ? q[j - 1] : prev_q)) & 0xffu;
+            if (cnt > 0) sh_d[tid] = d[cnt - 1];
+            __syncthreads();
+            const uint32_t prev_d = tid == 0 ? carry_d : sh_d[tid - 1];
+
+            // natural run boundaries: delta differs from its predecessor (position 0 always)
+            uint32_t chg = 0;
+#pragma unroll
+            for (int j = 0; j < kEPT; ++j) {
+                const bool c = (start + j == 0) || (d[j] != (j ? d[j - 1] : prev_d));
+                if (j < cnt && c) chg |= 1u << j;
+            }
+            int tot_lc;
+            const int lc = chg ? (int)start + (31 - __clz(chg)) : -1;
+            const int p0_in = max(carry_p0, block_excl_max(lc, tot_lc, wbuf));
+
+            // run heads = natural boundaries + a forced cut every 255 elements (count < 255, :223)
+            const int lh_in = start > 0 ? p0_in + 255 * (((int)start - 1 - p0_in) / 255) : 0;
+            int lh = lh_in;
+            uint32_t heads = 0;
+#pragma unroll
+            for (int j = 0; j < kEPT; ++j) {
+                const int pos = (int)start + j;
+                if (j < cnt && (((chg >> j) & 1u) || pos - lh == 255)) {
+                    heads |= 1u << j;
+                    lh = pos;
+                }
+            }
+            int tot_h;
+            int nh = carry_nh + block_excl_sum(__popc(heads), tot_h, wbuf);
+
+            // a head at pos closes the previous run: pair (delta[pos-1], pos - head_of_that_run)
+            int lh2 = lh_in;
+            uint32_t dprev = prev_d;
+#pragma unroll
+            for (int j = 0; j < kEPT; ++j) {
+                if ((heads >> j) & 1u) {
+                    const int pos = (int)start + j;
+                    if (pos > 0) stage[(nh - 1) - stage_base] = (uint16_t)(dprev | ((uint32_t)(pos - lh2) << 8));
+                    ++nh;
+                    lh2 = pos;
+                }
+                dprev = d[j];
+            }
+            const uint32_t last_valid = min(G, tile + kTile) - 1;
+            if (cnt > 0 && start + cnt - 1 == last_valid) {
+                carry_sm[0] = q[cnt - 1];
+                carry_sm[1] = d[cnt - 1];
+                carry_sm[2] = (uint32_t)lh;
+            }
+            __syncthreads();
+            carry_q = carry_sm[0];
+            carry_d = carry_sm[1];
+            carry_lh = (int)carry_sm[2];
+            carry_p0 = max(carry_p0, tot_lc);
+            carry_nh += tot_h;
+
+            // stream out the completed pairs in whole 16-byte vectors, keep the tail
+            const int avail = (carry_nh - 1) - stage_base;
+            const int nvec = avail >> 3;
+            uint4* dst = reinterpret_cast<uint4*>(gout + (size_t)stage_base * 2);
+            const uint4* src = reinterpret_cast<const uint4*>(stage);
+            for (int v = tid; v < nvec; v += kThreads) dst[v] = src[v];
+            const int rem = avail - (nvec << 3);
+            const uint16_t keep = tid < rem ? stage[(nvec << 3) + tid] : (uint16_t)0;
+            __syncthreads();
+            if (tid < rem) stage[tid] = keep;
+            stage_base += nvec << 3;
+        }
+
+        __syncthreads();
+        if (G > 0) {
+            // the run still open at the end of the group (:235-236)
+            const int rem = (carry_nh - 1) - stage_base;  // pairs waiting in the stage, < 8
+            if (tid == 0) stage[rem] = (uint16_t)(carry_d | ((uint32_t)((int)G - carry_lh) << 8));
+            if (tid > rem && tid < 8) stage[tid] = 0;
+            __syncthreads();
+            if (tid == 0) *reinterpret_cast<uint4*>(gout + (size_t)stage_base * 2) = *reinterpret_cast<const uint4*>(stage);
+        }
+        if (tid == 0) {
+            scales[g] = s;
+            comp_bytes[g] = 2u * (uint32_t)carry_nh;
+        }
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------
+// decompress, scheme INT8_DELTA_RLE
+// ---------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+decompress_rle_generic_kernel(const uint8_t* __restrict__ payload, size_t slot_bytes,
+                              const float* __restrict__ scales, const uint32_t* __restrict__ comp_bytes,
+                              uint32_t G, uint32_t n_groups, T* __restrict__ out,
+                              uint32_t* __restrict__ out_elems) {
+    constexpr int V = 16 / sizeof(T);
+    __shared__ __align__(16) T stage[kWindow + V];
+    __shared__ int wbuf[kWarps];
+    const int tid = threadIdx.x;
+
+    for (uint32_t g = blockIdx.x; g < n_groups; g += gridDim.x) {
+        const uint8_t* gp = payload + (size_t)g * slot_bytes;
+        uint32_t npairs = comp_bytes[g] >> 1;  // a trailing odd byte is ignored (:245-247)
+        npairs = min(npairs, (uint32_t)(slot_bytes >> 1));
+        const float s = scales[g];
+        T* gout = out + (size_t)g * G;
+        const bool vec_ok = (reinterpret_cast<uintptr_t>(gout) & 15) == 0;
+        const bool in_vec_ok = (reinterpret_cast<uintptr_t>(gp) & 15) == 0;
+
+        uint32_t out_pos = 0, acc = 0, stage_base = 0;
+        for (uint32_t c0 = 0; c0 < npairs && out_pos < G; c0 += kChunk) {
+            const uint32_t pbase = c0 + tid * kPPT;
+            const int np = pbase < npairs ? min((uint32_t)kPPT, npairs - pbase) : 0;
+            uint32_t w[4] = {0u, 0u, 0u, 0u};
+            if (np == kPPT && in_vec_ok) {
+                uint4 t = ldg_stream(reinterpret_cast<const uint4*>(gp + (size_t)pbase * 2));
+                w[0] = t.x; w[1] = t.y; w[2] = t.z; w[3] = t.w;
+            } else {
+                const uint16_t* p16 = reinterpret_cast<const uint16_t*>(gp) + pbase;
+                for (int k = 0; k < np; ++k) w[k >> 1] |= (uint32_t)p16[k] << (16 * (k & 1));
+            }
+            uint32_t val[kPPT], cntv[kPPT];
+            uint32_t C = 0, S = 0;
+#pragma unroll
+            for (int k = 0; k < kPPT; ++k) {
+                const uint32_t pr = (w[k >> 1] >> (16 * (k & 1))) & 0xffffu;
+                val[k] = pr & 0xffu;
+                cntv[k] = pr >> 8;
+                C += cntv[k];
+                S += val[k] * cntv[k];
+            }
+            int totC, totS;
+            const uint32_t exclC = (uint32_t)block_excl_sum((int)C, totC, wbuf);
+            const uint32_t exclS = (uint32_t)block_excl_sum((int)S, totS, wbuf);
+            const uint32_t chunk_end = (uint32_t)min((uint64_t)out_pos + (uint64_t)totC, (uint64_t)G);
+            const uint32_t my_start = out_pos + exclC;
+            const uint32_t qbase = acc + exclS;
+
+            uint32_t cur = out_pos;
+            while (true) {
+                const uint32_t hi = min(chunk_end, stage_base + (uint32_t)kWindow);
+                uint32_t p = my_start, qb = qbase;
+#pragma unroll
+                for (int k = 0; k < kPPT; ++k) {
+                    const uint32_t lo = max(p, cur), e = min(p + cntv[k], hi);
+                    for (uint32_t pos = lo; pos < e; ++pos) {
+                        const uint32_t code = (qb + val[k] * (pos - p + 1)) & 0xffu;
+                        stage[pos - stage_base] = narrow<T>(dequantize(code, s));
+                    }
+                    p += cntv[k];
+                    qb += val[k] * cntv[k];
+                }
+                __syncthreads();
+                const uint32_t flushable = hi - stage_base;
+                const uint32_t nvec = flushable / V;
+                if (vec_ok) {
+                    uint4* dst = reinterpret_cast<uint4*>(gout + stage_base);
+                    const uint4* src = reinterpret_cast<const uint4*>(stage);
+                    for (uint32_t v = tid; v < nvec; v += kThreads) dst[v] = src[v];
+                } else {
+                    for (uint32_t i = tid; i < nvec * V; i += kThreads) gout[stage_base + i] = stage[i];
+                }
+                const uint32_t rem = flushable - nvec * V;
+                T keep = stage[0];
+                if ((uint32_t)tid < rem) keep = stage[nvec * V + tid];
+                __syncthreads();
+                if ((uint32_t)tid < rem) stage[tid] = keep;
+                stage_base += nvec * V;
+                cur = hi;
+                __syncthreads();
+                if (cur >= chunk_end) break;
+            }
+            out_pos = chunk_end;
+            acc = (acc + (uint32_t)totS) & 0xffu;
+        }
+        if ((uint32_t)tid < out_pos - stage_base) gout[stage_base + tid] = stage[tid];
+        if (tid == 0 && out_elems) out_elems[g] = out_pos;
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------
+// scheme INT8: codes only (quantize_to_int8 / dequantize_from_int8)
+// ---------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+compress_int8_generic_kernel(const T* __restrict__ in, uint32_t G, uint32_t n_groups,
+                             uint8_t* __restrict__ payload, size_t slot_bytes,
+                             float* __restrict__ scales, uint32_t* __restrict__ comp_bytes) {
+    __shared__ float fbuf[kWarps];
+    const int tid = threadIdx.x;
+    for (uint32_t g = blockIdx.x; g < n_groups; g += gridDim.x) {
+        const T* gin = in + (size_t)g * G;
+        uint8_t* gout = payload + (size_t)g * slot_bytes;
+        const bool vec_ok = (reinterpret_cast<uintptr_t>(gin) & 15) == 0;
+        const float m = group_absmax<T>(gin, G, vec_ok, fbuf);
+        const float s = scale_from_max(m);
+        const bool fast = fast_quant_ok<T>(m);
+        const float r = fast ? __frcp_rn(s) : 0.0f;
+        for (uint32_t tile = 0; tile < G; tile += kTile) {
+            const uint32_t start = tile + tid * kEPT;
+            float x[kEPT];
+            load_elems<T>(gin, start, G, vec_ok, x);
+            uint32_t w[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+            for (int j = 0; j < kEPT; ++j) {
+                const uint32_t q = fast ? quantize_fast(x[j], s, r) : quantize_exact(x[j], s);
+                w[j >> 2] |= q << (8 * (j & 3));
+            }
+            if (start + kEPT <= G) {
+                *reinterpret_cast<uint4*>(gout + start) = make_uint4(w[0], w[1], w[2], w[3]);
+            } else {
+                for (uint32_t j = 0; start + j < G && j < kEPT; ++j) gout[start + j] = (uint8_t)(w[j >> 2] >> (8 * (j & 3)));
+            }
+        }
+        if (tid == 0) {
+            scales[g] = s;
+            comp_bytes[g] = G;
+        }
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+decompress_int8_generic_kernel(const uint8_t* __restrict__ payload, size_t slot_bytes,
+                               const float* __restrict__ scales, const uint32_t* __restrict__ comp_bytes,
+                               uint32_t G, uint32_t n_groups, T* __restrict__ out,
+                               uint32_t* __restrict__ out_elems) {
+    const int tid = threadIdx.x;
+    for (uint32_t g = blockIdx.x; g < n_groups; g += gridDim.x) {
+        const uint8_t* gp = payload + (size_t)g * slot_bytes;
+        const uint32_t n = min(min(comp_bytes[g], G), (uint32_t)slot_bytes);
+        const float s = scales[g];
+        T* gout = out + (size_t)g * G;
+        for (uint32_t i = tid; i < n; i += kThreads) gout[i] = narrow<T>(dequantize(gp[i], s));
+        if (tid == 0 && out_elems) out_elems[g] = n;
+    }
+}
+
+// scheme FP16: raw 16-bit passthrough of fp16 / bf16 groups
+__global__ void __launch_bounds__(kThreads)
+passthrough_meta_kernel(uint32_t n_groups, uint32_t bytes, float* __restrict__ scales,
+                        uint32_t* __restrict__ comp_bytes) {
+    const uint32_t g = blockIdx.x * kThreads + threadIdx.x;
+    if (g < n_groups) {
+        scales[g] = 1.0f;
+        comp_bytes[g] = bytes;
+    }
+}
+
+__global__ void __launch_bounds__(kThreads)
+passthrough_out_kernel(const uint8_t* __restrict__ payload, size_t slot_bytes,
+                       const uint32_t* __restrict__ comp_bytes, uint32_t G, uint32_t n_groups,
+                       uint16_t* __restrict__ out, uint32_t* __restrict__ out_elems) {
+    for (uint32_t g = blockIdx.x; g < n_groups; g += gridDim.x) {
+        const uint16_t* gp = reinterpret_cast<const uint16_t*>(payload + (size_t)g * slot_bytes);
+        const uint32_t n = min(min(comp_bytes[g] >> 1, G), (uint32_t)(slot_bytes >> 1));
+        for (uint32_t i = threadIdx.x; i < n; i += kThreads) out[(size_t)g * G + i] = gp[i];
+        if (threadIdx.x == 0 && out_elems) out_elems[g] = n;
+    }
+}
+
+inline int grid_for(uint32_t n_groups, int sm_count, int per_sm) {
+    const long long cap = (long long)sm_count * per_sm;
+    return (int)((long long)n_groups < cap ? (n_groups ? n_groups : 1) : cap);
+}
+
+}  // namespace
+
+template <typename T>
+static cudaError_t launch_compress_t(const CodecArgs& a, cudaStream_t st) {
+    const T* in = static_cast<const T*>(a.in);
+    uint8_t* pay = static_cast<uint8_t*>(a.payload);
+    const int grid = grid_for(a.n_groups, a.sm_count, 8);
+    if (a.scheme == 2) {
+        compress_rle_generic_kernel<T><<<grid, kThreads, 0, st>>>(in, a.group_elems, a.n_groups, pay, a.slot_bytes,
+                                                                  a.scales, a.comp_bytes);
+    } else {
+        compress_int8_generic_kernel<T><<<grid, kThreads, 0, st>>>(in, a.group_elems, a.n_groups, pay, a.slot_bytes,
+                                                                   a.scales, a.comp_bytes);
+    }
+    return cudaGetLastError();
+}
+
+template <typename T>
+static cudaError_t launch_decompress_t(const CodecArgs& a, cudaStream_t st) {
+    T* out = static_cast<T*>(a.out);
+    const uint8_t* pay = static_cast<const uint8_t*>(a.payload);
+    const int grid = grid_for(a.n_groups, a.sm_count, 8);
+    if (a.scheme == 2) {
+        decompress_rle_generic_kernel<T><<<grid, kThreads, 0, st>>>(pay, a.slot_bytes, a.scales, a.comp_bytes,
+                                                                    a.group_elems, a.n_groups, out, a.out_elems);
+    } else {
+        decompress_int8_generic_kernel<T><<<grid, kThreads, 0, st>>>(pay, a.slot_bytes, a.scales, a.comp_bytes,
+                                                                     a.group_elems, a.n_groups, out, a.out_elems);
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_compress_generic(const CodecArgs& a, cudaStream_t st) {
+    if (a.n_groups == 0) return cudaSuccess;
+    if (a.scheme == 0) {
+        const uint32_t bytes = a.group_elems * 2u;
+        cudaError_t e = cudaMemcpy2DAsync(a.payload, a.slot_bytes, a.in, bytes, bytes, a.n_groups,
+                                          cudaMemcpyDeviceToDevice, st);
+        if (e != cudaSuccess) return e;
+        passthrough_meta_kernel<<<(a.n_groups + kThreads - 1) / kThreads, kThreads, 0, st>>>(a.n_groups, bytes, a.scales,
+                                                                                            a.comp_bytes);
+        return cudaGetLastError();
+    }
+    switch (a.dtype) {
+        case DT_F16: return launch_compress_t<__half>(a, st);
+        case DT_BF16: return launch_compress_t<__nv_bfloat16>(a, st);
+        default: return launch_compress_t<float>(a, st);
+    }
+}
+
+cudaError_t launch_decompress_generic(const CodecArgs& a, cudaStream_t st) {
+    if (a.n_groups == 0) return cudaSuccess;
+    if (a.scheme == 0) {
+        passthrough_out_kernel<<<grid_for(a.n_groups, a.sm_count, 8), kThreads, 0, st>>>(
+            static_cast<const uint8_t*>(a.payload), a.slot_bytes, a.comp_bytes, a.group_elems, a.n_groups,
+            static_cast<uint16_t*>(a.out), a.out_elems);
+        return cudaGetLastError();
+    }
+    switch (a.dtype) {
+        case DT_F16: return launch_decompress_t<__half>(a, st);
+        case DT_BF16: return launch_decompress_t<__nv_bfloat16>(a, st);
+        default: return launch_decompress_t<float>(a, st);
+    }
+}
+
+}  // namespace speckv

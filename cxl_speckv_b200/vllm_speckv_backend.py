@@ -1,0 +1,77 @@
+"""CxlSpeckvKVAllocator -- the vLLM-facing allocator of the reference
+(host/python/vllm_speckv_backend.py:9-100), same constructor and method
+signatures, over the B200 libcxlspeckv.so.
+
+The KV region of one handle is laid out [req][layer][kind (K=0,V=1)][pos][head] x
+entry_bytes (`_calc_offset`, reference :87-100); `get_kv_ptr` turns that offset
+into an address through speckv_access and `prefetch_step` forwards the recent
+token history to speckv_prefetch.
+"""
+import ctypes
+from typing import Any, Dict, List, Optional
+
+try:  # the reference imports it relatively (:5); its tests import it top-level
+    from .speckv_ctypes import SpeckvLib
+except ImportError:  # pragma: no cover
+    from speckv_ctypes import SpeckvLib
+
+
+class CxlSpeckvKVAllocator:
+    def __init__(self, lib_path: str, dev_path: str = "/dev/speckv0", page_size: int = 4096):
+        self._speckv = SpeckvLib(lib_path, dev_path)
+        self._page_size = page_size
+        self._handle: Optional[int] = None
+        self._req_id_counter = 1
+        self._req_state: Dict[int, Dict[str, Any]] = {}
+        self._num_layers = 0
+        self._num_heads = 0
+        self._num_tokens = 0
+        self._head_dim = 0
+        self._bytes_per_element = 0
+
+    def allocate(self, num_tokens: int, num_layers: int, num_heads: int, head_dim: int, bytes_per_element: int):
+        """Allocate the KV region of one request: tokens x layers x heads x head_dim x bytes x 2 (K+V)."""
+        self._num_tokens = num_tokens
+        self._num_layers = num_layers
+        self._num_heads = num_heads
+        self._head_dim = head_dim
+        self._bytes_per_element = bytes_per_element
+        total_bytes = num_tokens * num_layers * num_heads * head_dim * bytes_per_element * 2
+        self._handle = self._speckv.alloc(total_bytes, preferred_node=0)
+        return self._handle
+
+    def get_kv_ptr(self, req_id: int, layer: int, head: int, pos: int, kind: int, entry_bytes: int) -> int:
+        """Address of one KV entry (ensures its page is resident, fetching it if needed)."""
+        offset = self._calc_offset(req_id, layer, head, pos, kind, entry_bytes)
+        gpu_ptr = ctypes.c_void_p()
+        ret = self._speckv.lib.speckv_access(self._handle, offset, entry_bytes, ctypes.byref(gpu_ptr))
+        if ret != 0:
+            raise RuntimeError(f"speckv_access failed: {ret}")
+        return gpu_ptr.value
+
+    def prefetch_step(self, req_id: int, layer: int, cur_pos: int, recent_tokens: List[int], depth_k: int = 4):
+        """Issue the speculative prefetch for the next tokens of (req_id, layer)."""
+        hist_len = len(recent_tokens)
+        arr = (ctypes.c_int32 * hist_len)(*recent_tokens)
+        ret = self._speckv.lib.speckv_prefetch(req_id, layer, cur_pos, depth_k, arr, hist_len)
+        if ret != 0:
+            raise RuntimeError(f"speckv_prefetch failed: {ret}")
+
+    def _calc_offset(self, req_id: int, layer: int, head: int, pos: int, kind: int, entry_bytes: int) -> int:
+        # [req][layer][kind][pos][head] * entry_bytes  (reference :95-100)
+        return ((((req_id * self._num_layers + layer) * 2 + kind) * self._num_tokens + pos)
+                * self._num_heads + head) * entry_bytes
+
+
+def decode_step_example(model, kv_allocator: CxlSpeckvKVAllocator, state, depth_k: int = 4):
+    """The decode-loop sketch of the reference (:104-129), made importable: one forward
+    step, then a prefetch per layer on the last 16 tokens."""
+    logits = model(state)
+    new_token = int(logits.argmax(-1))
+    state.tokens.append(new_token)
+    last_tokens = state.tokens[-16:]
+    for layer in range(model.num_layers):
+        kv_allocator.prefetch_step(req_id=state.req_id, layer=layer, cur_pos=state.cur_pos,
+                                   recent_tokens=last_tokens, depth_k=depth_k)
+    state.cur_pos += 1
+    return logits, new_token

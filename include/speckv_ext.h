@@ -1,0 +1,118 @@
+/*
+ * speckv_ext.h -- additive, stream-ordered batch entry points of libcxlspeckv.so.
+ *
+ * The reference has no batch API: its cache engine is a C++ class
+ * (src/fpga_engine/cache_engine.h:21-125) that nothing calls, and its host path
+ * moves one 4 KiB page per ioctl (host/src/speckv_allocator.cpp:115-138).  These
+ * functions are what a reference maintainer binds to replace
+ *   FPGACacheEngine::compress / decompress / translate_address
+ *       (src/fpga_engine/cache_engine.cpp:40-140),
+ *   AddressTranslationUnit::translate (src/utils/address_translation.cpp:19-46),
+ *   SpeckvAllocator's page table + sync fetch (host/src/speckv_allocator.cpp:11-138),
+ *   SpeckvDriver::submit_dma_batch (host/src/speckv_driver.cpp:24-47) and
+ *   LSTMPredictor::predict_top_k + SpeculativePrefetcher::prefetch
+ *       (src/prefetcher/lstm_predictor.cpp:40-94, speculative_prefetcher.cpp:25-82)
+ * with sm_100a CUDA kernels.  Plain C: pointers, sizes, enums; `cuda_stream` is
+ * a cudaStream_t passed as void* (NULL = the legacy default stream).  Pointers
+ * named d_* are device pointers, h_* host pointers.  All calls are
+ * asynchronous on the stream unless stated; they return SPECKV_ERR_DRIVER when
+ * no CUDA device is usable (there is no CPU fallback) and SPECKV_ERR_INVAL for
+ * bad arguments.
+ *
+ * Container format (the reference has none; CompressedData is an in-memory
+ * struct, cache_engine.h:35-40): group g owns a fixed slot
+ *   payload + g * slot_bytes     (slot_bytes >= speckv_ext_slot_bytes(), 16 B aligned)
+ * whose first comp_bytes[g] bytes equal CompressedData::rle_data exactly, plus
+ * scales[g] (== scale_factor) and comp_bytes[g] (== compressed_size).
+ */
+#ifndef SPECKV_EXT_H
+#define SPECKV_EXT_H
+
+#include "speckv.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+    SPECKV_DTYPE_F16  = 0,   /* IEEE half  */
+    SPECKV_DTYPE_BF16 = 1,   /* bfloat16   */
+    SPECKV_DTYPE_F32  = 2,   /* what the reference engine consumes (std::vector<float>) */
+} speckv_dtype_t;
+
+/* ---- library / device ----------------------------------------------------- */
+/* Number of usable CUDA devices (0 when none: every other call then fails with
+ * SPECKV_ERR_DRIVER). */
+SPECKV_API int speckv_ext_device_count(void);
+/* Human readable build id, e.g. "cxl-speckv-b200 sm_100a". */
+SPECKV_API const char* speckv_ext_version(void);
+
+/* ---- KV block codec -------------------------------------------------------- */
+/* Worst-case bytes a group of group_elems elements can occupy under `scheme`,
+ * rounded up to 16: INT8_DELTA_RLE 2*n (every element its own [value][count]
+ * pair, cache_engine.cpp:213-239), INT8 n, FP16 2*n. */
+SPECKV_API size_t speckv_ext_slot_bytes(size_t group_elems, speckv_comp_scheme_t scheme);
+
+/* FPGACacheEngine::compress (cache_engine.cpp:40-82) over n_groups independent
+ * groups of group_elems consecutive elements of d_in.  One fp32 scale per group
+ * (:172-184), wrapped int8 quantisation (:186-196), delta across the whole flat
+ * group (:198-211), byte-pair RLE with the 255 cap (:213-239); bit-exact.
+ * scheme INT8 stops after quantisation (payload = the int8 codes);
+ * scheme FP16 stores the elements unchanged (scale 1).  */
+SPECKV_API speckv_status_t speckv_ext_compress(const void* d_in, speckv_dtype_t dtype,
+                                    size_t group_elems, size_t n_groups,
+                                    void* d_payload, size_t slot_bytes,
+                                    float* d_scales, uint32_t* d_comp_bytes,
+                                    speckv_comp_scheme_t scheme, void* cuda_stream);
+
+/* FPGACacheEngine::decompress (cache_engine.cpp:84-116): RLE expand (:241-258,
+ * odd trailing byte ignored, count 0 emits nothing), mod-256 prefix sum
+ * (:260-273), (float)q / 127.0f * scale (:275-284) rounded to `dtype`.
+ * At most group_elems elements are written per group at d_out + g*group_elems;
+ * d_out_elems[g] (optional, may be NULL) receives the number produced. */
+SPECKV_API speckv_status_t speckv_ext_decompress(const void* d_payload, size_t slot_bytes,
+                                      const float* d_scales, const uint32_t* d_comp_bytes,
+                                      size_t group_elems, size_t n_groups,
+                                      speckv_dtype_t dtype, void* d_out, uint32_t* d_out_elems,
+                                      speckv_comp_scheme_t scheme, void* cuda_stream);
+
+/* Same two operations on HOST buffers: chunks are staged through device
+ * buffers on internal streams (H2D, kernel, D2H overlapped) and the call
+ * returns when the results are in host memory.  Pinned host memory
+ * (speckv_ext_host_alloc) gives full PCIe rate.  This is the call the
+ * end-to-end benchmark times. */
+SPECKV_API speckv_status_t speckv_ext_compress_host(const void* h_in, speckv_dtype_t dtype,
+                                         size_t group_elems, size_t n_groups,
+                                         void* h_payload, size_t slot_bytes,
+                                         float* h_scales, uint32_t* h_comp_bytes,
+                                         speckv_comp_scheme_t scheme);
+SPECKV_API speckv_status_t speckv_ext_decompress_host(const void* h_payload, size_t slot_bytes,
+                                           const float* h_scales, const uint32_t* h_comp_bytes,
+                                           size_t group_elems, size_t n_groups,
+                                           speckv_dtype_t dtype, void* h_out, uint32_t* h_out_elems,
+                                           speckv_comp_scheme_t scheme);
+/* Pinned host memory for the *_host calls and the host tier. */
+SPECKV_API void* speckv_ext_host_alloc(size_t bytes);
+SPECKV_API void speckv_ext_host_free(void* p);
+
+/* ---- address translation ---------------------------------------------------- */
+/* FPGACacheEngine::translate_address (cache_engine.cpp:118-140) for n addresses:
+ * pa = 0x4000000000 + (va & 0xFFFFFFFFFFFF); the 1024-entry TLB never changes
+ * the value, only hit/miss counts. */
+SPECKV_API speckv_status_t speckv_ext_translate(const uint64_t* d_va, uint64_t* d_pa, size_t n, void* cuda_stream);
+
+/* ---- statistics (EngineStatistics, cache_engine.h:65-72) --------------------- */
+typedef struct {
+    uint64_t total_compressions;     /* groups compressed   */
+    uint64_t total_decompressions;   /* groups decompressed */
+    uint64_t total_translations;
+    uint64_t bytes_in_compress;      /* uncompressed bytes consumed */
+    uint64_t bytes_out_decompress;   /* uncompressed bytes produced (capacity) */
+} speckv_ext_stats_t;
+SPECKV_API void speckv_ext_get_stats(speckv_ext_stats_t* out);
+SPECKV_API void speckv_ext_reset_stats(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPECKV_EXT_H */

@@ -1,0 +1,325 @@
+"""GPU parity tests: the CUDA codec (through the C ABI of libcxlspeckv.so) against
+the fixtures recorded from the reference's C++ model and against the CPU oracle on
+the same seeded inputs.  Bar: compressed bytes, scales, int8 codes, byte counts and
+translated addresses bit-exact; decompressed fp32 bit-exact; fp16/bf16 outputs
+within 1 ulp of the oracle's fp32 value rounded to the type (in practice equal)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+from oracle.oracle import Port, splitmix64_block
+from tests.helpers import F16, BF16, F32, bf16_from_f32, bf16_to_f32, case_input, f32_bits, narrow
+
+pytestmark = pytest.mark.gpu
+
+from cxl_speckv_b200 import codec  # noqa: E402
+from cxl_speckv_b200 import COMP_FP16, COMP_INT8, COMP_INT8_DELTA_RLE  # noqa: E402
+
+DEV = "cuda:0"
+TORCH_DT = {F16: torch.float16, BF16: torch.bfloat16, F32: torch.float32}
+
+
+def to_dev(raw, dtype):
+    if dtype == BF16:
+        return torch.from_numpy(raw.astype(np.int16)).to(DEV).view(torch.bfloat16)
+    return torch.from_numpy(np.ascontiguousarray(raw)).to(DEV)
+
+
+def out_bits(t):
+    if t.dtype == torch.float32:
+        return t.cpu().numpy().view(np.uint32)
+    return t.view(torch.int16).cpu().numpy().view(np.uint16)
+
+
+def ulp_diff16(a_bits, b_bits):
+    """distance in representable values between two fp16/bf16 bit patterns (sign-magnitude order)"""
+    def key(u):
+        u = u.astype(np.int32)
+        return np.where(u & 0x8000, -(u & 0x7FFF), u & 0x7FFF)
+    return np.abs(key(a_bits) - key(b_bits))
+
+
+def check_group_against_oracle(c, g, xf):
+    s, p = Port.compress(xf)
+    assert f32_bits(c.scales[g:g + 1].cpu().numpy())[0] == f32_bits([s])[0]
+    nb = int(c.comp_bytes[g].item()) & 0xFFFFFFFF
+    assert nb == p.size
+    assert np.array_equal(c.payload[g, :nb].cpu().numpy(), p)
+    return s, p
+
+
+def test_golden_fixtures_rle(golden):
+    meta, cz = golden["meta"], golden["codec"]
+    for name, m in meta["codec"].items():
+        raw, xf, dtype = case_input(cz, meta, name)
+        x = to_dev(raw, dtype)
+        c = codec.compress(x, m["n"])
+        torch.cuda.synchronize()
+        assert f32_bits(c.scales.cpu().numpy())[0] == m["scale_bits"], name
+        nb = int(c.comp_bytes[0].item())
+        assert nb == m["comp_bytes"], name
+        assert np.array_equal(c.payload[0, :nb].cpu().numpy(), cz[name + ".payload"]), name
+        # fp32 output: bit-exact against the reference's decompress()
+        oel = torch.zeros(1, dtype=torch.int32, device=DEV)
+        y32 = codec.decompress(c, dtype=torch.float32, out_elems=oel)
+        assert int(oel.item()) == m["out_elems"], name
+        assert np.array_equal(out_bits(y32)[0, :m["out_elems"]], cz[name + ".out_f32_bits"]), name
+        # native dtype: reference fp32 rounded to the type, tolerance 1 ulp (north_star)
+        if dtype != F32:
+            y = codec.decompress(c)
+            want = narrow(cz[name + ".out_f32_bits"].view(np.float32), dtype)
+            got = out_bits(y)[0]
+            finite = ~np.isnan(cz[name + ".out_f32_bits"].view(np.float32))
+            assert (ulp_diff16(got[finite], want[finite]) <= 1).all(), name
+            assert np.array_equal(got[finite], want[finite]), name   # in practice exact
+
+
+def test_golden_fixtures_int8_codes(golden):
+    meta, cz = golden["meta"], golden["codec"]
+    for name, m in meta["codec"].items():
+        raw, xf, dtype = case_input(cz, meta, name)
+        c = codec.compress(to_dev(raw, dtype), m["n"], scheme=COMP_INT8)
+        assert f32_bits(c.scales.cpu().numpy())[0] == m["scale_bits"], name
+        assert int(c.comp_bytes[0].item()) == m["n"]
+        assert np.array_equal(c.payload[0, :m["n"]].cpu().numpy().view(np.int8), cz[name + ".codes"]), name
+        y = codec.decompress(c, dtype=torch.float32)
+        want = (cz[name + ".codes"].astype(np.float32) / np.float32(127.0)) * np.uint32(m["scale_bits"]).view(np.float32)
+        assert np.array_equal(out_bits(y)[0], f32_bits(want)), name
+
+
+def test_bulk_group_digest(golden):
+    m = golden["meta"]["bulk"]["splitmix42_131072"]
+    x = splitmix64_block(42, 131072).astype(np.float16)
+    c = codec.compress(torch.from_numpy(x).to(DEV), 131072)
+    assert f32_bits(c.scales.cpu().numpy())[0] == m["scale_bits"]
+    nb = int(c.comp_bytes[0].item())
+    assert nb == m["comp_bytes"]
+    assert "%016x" % Port.fnv1a64(c.payload[0, :nb].cpu().numpy()) == m["payload_fnv1a64"]
+    y32 = codec.decompress(c, dtype=torch.float32)
+    assert "%016x" % Port.fnv1a64(y32.cpu().numpy()) == m["out_f32_fnv1a64"]
+    y16 = codec.decompress(c)
+    assert "%016x" % Port.fnv1a64(y16.cpu().numpy()) == m["out_f16_fnv1a64"]
+
+
+def make_inputs(rng, n_groups, G, kind):
+    n = n_groups * G
+    if kind == "randn":
+        x = rng.standard_normal(n).astype(np.float16)
+    elif kind == "runs":
+        x = np.repeat(rng.standard_normal(n // 300 + 1), 300)[:n].astype(np.float16)
+    elif kind == "zeros":
+        x = np.zeros(n, np.float16)
+    elif kind == "mixed":
+        x = rng.standard_normal(n).astype(np.float16)
+        for _ in range(max(1, n // 5000)):
+            a = int(rng.integers(0, n))
+            b = min(n, a + int(rng.integers(1, 1500)))
+            x[a:b] = x[a]
+        x[rng.integers(0, n, max(1, n // 4000))] = np.nan
+    elif kind == "ramp":
+        x = ((np.arange(n) % 251) / 16.0).astype(np.float16)
+    else:
+        raise ValueError(kind)
+    return x
+
+
+@pytest.mark.parametrize("G,n_groups", [(2048, 96), (131072, 5), (1000, 37), (4099, 11), (8, 300), (1, 17),
+                                        (65536, 3), (16384, 9), (32768, 4), (262144, 2), (131080, 2)])
+@pytest.mark.parametrize("kind", ["randn", "mixed", "runs", "zeros", "ramp"])
+def test_batches_vs_oracle_f16(G, n_groups, kind):
+    rng = np.random.default_rng(hash((G, n_groups, kind)) % (2**32))
+    x = make_inputs(rng, n_groups, G, kind)
+    xd = torch.from_numpy(x).to(DEV)
+    c = codec.compress(xd, G)
+    payload, scales, comp = Port.compress_batch(x, G, threads=8)
+    assert np.array_equal(f32_bits(c.scales.cpu().numpy()), f32_bits(scales))
+    got_comp = c.comp_bytes.cpu().numpy().view(np.uint32)
+    assert np.array_equal(got_comp, comp)
+    gp = c.payload.cpu().numpy()
+    for g in range(n_groups):
+        assert np.array_equal(gp[g, :comp[g]], payload[g, :comp[g]]), (g, comp[g])
+    oel = torch.zeros(n_groups, dtype=torch.int32, device=DEV)
+    y = codec.decompress(c, out_elems=oel)
+    want, want_n = Port.decompress_batch(payload, scales, comp, G, F16, threads=8)
+    assert np.array_equal(oel.cpu().numpy().view(np.uint32), want_n) and (want_n == G).all()
+    assert np.array_equal(out_bits(y), want.view(np.uint16))
+    # INT8 scheme on the same data
+    c8 = codec.compress(xd, G, scheme=COMP_INT8)
+    g0 = int(rng.integers(0, n_groups))
+    q = Port.quantize(x[g0 * G:(g0 + 1) * G].astype(np.float32), scales[g0])
+    assert np.array_equal(c8.payload[g0, :G].cpu().numpy().view(np.int8), q)
+
+
+@pytest.mark.parametrize("G,n_groups", [(2048, 40), (131072, 3), (777, 9)])
+def test_batches_vs_oracle_bf16_f32(G, n_groups):
+    rng = np.random.default_rng(G)
+    # bf16, including groups whose max is below 2^-60 (exact-division path) and huge values
+    mags = np.exp(rng.uniform(-75, 60, n_groups)).repeat(G)
+    xb = bf16_from_f32(rng.standard_normal(n_groups * G) * mags)
+    xd = torch.from_numpy(xb.astype(np.int16)).to(DEV).view(torch.bfloat16)
+    c = codec.compress(xd, G)
+    payload, scales, comp = Port.compress_batch(xb, G, dtype=BF16, threads=8)
+    assert np.array_equal(f32_bits(c.scales.cpu().numpy()), f32_bits(scales))
+    assert np.array_equal(c.comp_bytes.cpu().numpy().view(np.uint32), comp)
+    gp = c.payload.cpu().numpy()
+    for g in range(n_groups):
+        assert np.array_equal(gp[g, :comp[g]], payload[g, :comp[g]]), g
+    y = codec.decompress(c)
+    want, _ = Port.decompress_batch(payload, scales, comp, G, BF16, threads=8)
+    assert np.array_equal(out_bits(y), want)
+    # fp32 in / fp32 out: what the reference engine itself consumes and produces
+    xf = (rng.standard_normal(n_groups * G) * np.exp(rng.uniform(-20, 20, n_groups * G))).astype(np.float32)
+    c = codec.compress(torch.from_numpy(xf).to(DEV), G)
+    payload, scales, comp = Port.compress_batch(xf, G, threads=8)
+    assert np.array_equal(f32_bits(c.scales.cpu().numpy()), f32_bits(scales))
+    assert np.array_equal(c.comp_bytes.cpu().numpy().view(np.uint32), comp)
+    gp = c.payload.cpu().numpy()
+    for g in range(n_groups):
+        assert np.array_equal(gp[g, :comp[g]], payload[g, :comp[g]]), g
+    y = codec.decompress(c)
+    want, _ = Port.decompress_batch(payload, scales, comp, G, F32, threads=8)
+    assert np.array_equal(out_bits(y), f32_bits(want))
+
+
+def test_unaligned_input_pointer():
+    rng = np.random.default_rng(5)
+    G, n_groups = 2048, 6
+    x = rng.standard_normal(n_groups * G + 3).astype(np.float16)
+    xd = torch.from_numpy(x).to(DEV)[3:]          # 6-byte offset: no 128-bit loads possible
+    c = codec.compress(xd, G)
+    payload, scales, comp = Port.compress_batch(x[3:], G)
+    assert np.array_equal(c.comp_bytes.cpu().numpy().view(np.uint32), comp)
+    for g in range(n_groups):
+        assert np.array_equal(c.payload[g, :comp[g]].cpu().numpy(), payload[g, :comp[g]])
+    buf = torch.zeros(n_groups * G + 1, dtype=torch.float16, device=DEV)
+    y = codec.decompress(c, out=buf[1:].view(n_groups, G))
+    want, _ = Port.decompress_batch(payload, scales, comp, G, F16)
+    assert np.array_equal(out_bits(y), want.view(np.uint16))
+
+
+def test_decode_arbitrary_payloads():
+    """payloads the encoder never produces: zero counts, odd trailing byte, overlong output."""
+    rng = np.random.default_rng(9)
+    G, n_groups = 3000, 24
+    sb = codec.slot_bytes(G)
+    payload = np.zeros((n_groups, sb), np.uint8)
+    comp = np.zeros(n_groups, np.uint32)
+    scales = rng.uniform(0.01, 2.0, n_groups).astype(np.float32)
+    for g in range(n_groups):
+        nbytes = int(rng.integers(0, 700))
+        p = rng.integers(0, 256, nbytes, dtype=np.uint8)
+        if g % 3 == 0:
+            p[1::2] = rng.integers(0, 3, p[1::2].size)       # many zero counts, short output
+        if g % 3 == 1:
+            p[1::2] = 255                                    # overlong: clipped at G
+        payload[g, :nbytes] = p
+        comp[g] = nbytes
+    c = codec.CompressedKV(torch.from_numpy(payload).to(DEV), torch.from_numpy(scales).to(DEV),
+                           torch.from_numpy(comp.view(np.int32)).to(DEV), G, torch.float32, COMP_INT8_DELTA_RLE)
+    out = torch.full((n_groups, G), -7.0, dtype=torch.float32, device=DEV)
+    oel = torch.zeros(n_groups, dtype=torch.int32, device=DEV)
+    codec.decompress(c, out=out, out_elems=oel)
+    got, got_n = out.cpu().numpy(), oel.cpu().numpy()
+    for g in range(n_groups):
+        want = Port.decompress(scales[g], payload[g, :comp[g]], G)
+        assert got_n[g] == want.size, g
+        assert np.array_equal(f32_bits(got[g, :want.size]), f32_bits(want)), g
+        assert (got[g, want.size:] == -7.0).all()            # nothing written past the decoded length
+
+
+def test_fp16_passthrough_scheme():
+    x = torch.randn(8 * 2048, device=DEV).half()
+    c = codec.compress(x, 2048, scheme=COMP_FP16)
+    assert (c.comp_bytes == 4096).all() and (c.scales == 1).all()
+    y = codec.decompress(c)
+    assert torch.equal(y.view(-1), x)
+
+
+def test_translate(golden):
+    tr = golden["translate"]
+    va = torch.from_numpy(tr["va"].view(np.int64)).to(DEV)
+    pa = codec.translate(va)
+    assert np.array_equal(pa.cpu().numpy().view(np.uint64), tr["engine_pa"])
+    rng = np.random.default_rng(1)
+    big = rng.integers(0, 2**63, 1_000_003, dtype=np.uint64) * np.uint64(2) + np.uint64(1)
+    pa = codec.translate(torch.from_numpy(big.view(np.int64)).to(DEV))
+    assert np.array_equal(pa.cpu().numpy().view(np.uint64), Port.translate(big))
+    pa = codec.translate(torch.from_numpy(big.view(np.int64)).to(DEV)[1:])      # 8-byte aligned only
+    assert np.array_equal(pa.cpu().numpy().view(np.uint64), Port.translate(big[1:]))
+
+
+def test_host_buffer_api_matches_device_api():
+    from cxl_speckv_b200 import lib
+    L = lib()
+    rng = np.random.default_rng(2)
+    G, n_groups = 131072, 300                 # 75 MiB: several pipeline chunks
+    x = rng.standard_normal(n_groups * G).astype(np.float16)
+    x[5 * G:6 * G] = 0
+    sb = codec.slot_bytes(G)
+    payload = np.zeros((n_groups, sb), np.uint8)
+    scales = np.zeros(n_groups, np.float32)
+    comp = np.zeros(n_groups, np.uint32)
+    st = L.speckv_ext_compress_host(x.ctypes.data, 0, G, n_groups, payload.ctypes.data, sb, scales.ctypes.data,
+                                    comp.ctypes.data, 2)
+    assert st == 0
+    c = codec.compress(torch.from_numpy(x).to(DEV), G)
+    assert np.array_equal(c.comp_bytes.cpu().numpy().view(np.uint32), comp)
+    assert np.array_equal(f32_bits(c.scales.cpu().numpy()), f32_bits(scales))
+    gp = c.payload.cpu().numpy()
+    for g in range(0, n_groups, 17):
+        assert np.array_equal(gp[g, :comp[g]], payload[g, :comp[g]])
+    out = np.zeros((n_groups, G), np.float16)
+    oel = np.zeros(n_groups, np.uint32)
+    st = L.speckv_ext_decompress_host(payload.ctypes.data, sb, scales.ctypes.data, comp.ctypes.data, G, n_groups, 0,
+                                      out.ctypes.data, oel.ctypes.data, 2)
+    assert st == 0 and (oel == G).all()
+    y = codec.decompress(c)
+    assert np.array_equal(out.view(np.uint16), out_bits(y))
+    for g in (0, 5, 299):
+        want = Port.decompress(scales[g], payload[g, :comp[g]], G)
+        assert np.array_equal(out[g].view(np.uint16), want.astype(np.float16).view(np.uint16))
+
+
+def test_bad_arguments_are_rejected():
+    from cxl_speckv_b200 import SpeckvError
+    x = torch.randn(4096, device=DEV).half()
+    with pytest.raises(ValueError):
+        codec.compress(x, 1000)
+    c = codec.compress(x, 2048)
+    bad = codec.CompressedKV(c.payload[:, :4080].contiguous(), c.scales, c.comp_bytes, 2048, c.dtype, c.scheme)
+    with pytest.raises(SpeckvError):
+        codec.decompress(bad)                  # slot smaller than the worst case
+
+
+def test_full_size_properties_llama70b_layer():
+    """BASELINE config 3 geometry at full per-layer size (8 KV heads x 8192 tokens x 128,
+    K and V: 128 groups of 1024x128), several layers at once: size-independent properties +
+    oracle spot checks."""
+    torch.manual_seed(1234)
+    G, layers = 131072, 8
+    n_groups = layers * 2 * 8 * 8
+    x = torch.randn(n_groups * G, device=DEV, dtype=torch.float32).half()
+    c = codec.compress(x, G)
+    comp = c.comp_bytes.cpu().numpy().view(np.uint32)
+    assert (comp % 2 == 0).all() and (comp <= 2 * G).all() and (comp > 1.9 * G).all()
+    # scale == max|x| / 127 in IEEE fp32 for every group
+    amax = x.view(n_groups, G).float().abs().amax(dim=1)
+    assert torch.equal(c.scales, amax / 127.0)
+    # every pair count >= 1 and counts sum to G (decoder length) for every group
+    oel = torch.zeros(n_groups, dtype=torch.int32, device=DEV)
+    y = codec.decompress(c, out_elems=oel)
+    assert (oel == G).all()
+    # decode is the inverse of delta+RLE: re-encoding the INT8 codes path agrees with it
+    c8 = codec.compress(x, G, scheme=COMP_INT8)
+    y8 = codec.decompress(c8)
+    assert torch.equal(y8.view(torch.int16), y.view(torch.int16))
+    # reconstruction error equals the reference's (~0.996 MSE for N(0,1))
+    mse = ((y.float() - x.view(n_groups, G).float()) ** 2).mean().item()
+    assert 0.9 < mse < 1.1
+    xs = x.view(n_groups, G)
+    for g in (0, 1, n_groups // 2, n_groups - 1):
+        s, p = check_group_against_oracle(c, g, xs[g].cpu().numpy().astype(np.float32))
+        want = Port.decompress(s, p, G).astype(np.float16)
+        assert np.array_equal(out_bits(y[g]), want.view(np.uint16))
