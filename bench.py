@@ -1,0 +1,414 @@
+#!/usr/bin/env python
+"""bench.py -- KV block codec throughput on B200 (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path
+
+One "step" = one pass of the hot path over one batch of synthetic KV: every group of
+the workload is compressed (scale -> wrapped int8 -> delta -> byte-pair RLE) and then
+decompressed again, layer by layer.  `value` = uncompressed fp16 KV bytes that made the
+round trip per second, whole job (all ranks), inputs resident in HBM.  `e2e` = the same
+metric through the host-buffer C ABI (speckv_ext_compress_host / _decompress_host) with
+the H2D / D2H copies inside the timed region.
+
+Workloads (BASELINE.json `configs`):
+  cfg2  Llama-2-7B KV, batch 32 x 4K ctx per GPU: 32 L x 2 x 32 H x 32 x 4 blocks of
+        1024 tok x 128 d = 262144 groups = 64 GiB fp16 per GPU (default; weak scaling)
+  cfg3  Llama-2-70B GQA KV, 80 L x 8 KVH x 8K ctx: 10240 groups = 2.5 GiB, layers
+        sharded 80/N across ranks (strong scaling)
+  cfg4p Llama-3-8B 32K ctx as 4 KiB page groups (2048 elems): 1 Mi groups = 4 GiB
+One process per GPU (torchrun), no data-path collective; at N > 1 the only exchange is
+an NCCL all-gather of the per-group page-table metadata (comp_bytes) per step.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+G_BLOCK = 131072          # 1024 tokens x 128 dims: one (layer, head, K|V) block
+METRIC = "kv_compress_decompress_roundtrip_throughput"
+UNIT = "GB/s"             # 1e9 bytes of uncompressed fp16 KV per second
+
+
+def workload_spec(name: str, world: int, rank: int, scale: float):
+    """-> dict(label, group_elems, n_groups (this rank), chunk_groups, scaling)"""
+    if name == "cfg2":
+        layers, per_layer = 32, 2 * 32 * 32 * 4          # K|V x heads x batch x (4096/1024)
+        layers = max(1, int(round(layers * scale)))
+        return dict(label=f"cfg2: Llama-2-7B KV, batch 32 x 4K ctx per GPU ({layers} layers x {per_layer} blocks of 1024x128 fp16)",
+                    group_elems=G_BLOCK, n_groups=layers * per_layer, chunk_groups=per_layer, scaling="weak",
+                    global_batch=32 * world)
+    if name == "cfg3":
+        layers, per_layer = 80, 2 * 8 * 8                # K|V x KV heads x (8192/1024)
+        mine = [l for l in range(layers) if l % world == rank] if world > 1 else list(range(layers))
+        return dict(label=f"cfg3: Llama-2-70B GQA KV, 80 L x 8 KVH x 8K ctx, layers sharded {layers}/{world}",
+                    group_elems=G_BLOCK, n_groups=len(mine) * per_layer, chunk_groups=per_layer * 8, scaling="strong",
+                    global_batch=1)
+    if name == "cfg4p":
+        layers, per_layer = 32, 2 * 8 * 32768 * 128 // 2048
+        layers = max(1, int(round(layers * scale)))
+        return dict(label=f"cfg4p: Llama-3-8B 32K ctx paged KV, {layers} layers x {per_layer} page groups of 2048 fp16",
+                    group_elems=2048, n_groups=layers * per_layer, chunk_groups=per_layer, scaling="weak",
+                    global_batch=world)
+    raise SystemExit(f"unknown workload {name}")
+
+
+def hbm_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic(kernel_key: str):
+    """dram bytes per launch from the committed ncu --set full capture, if one matches."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            return json.load(f).get(kernel_key)
+    except Exception:
+        return None
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index: int, period: float = 0.05):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if not self.nv:
+            return
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksEventReasonHwSlowdown", getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8)): "hw_slowdown",
+            getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40)): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20)): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwPowerCap", getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4)): "sw_power_cap",
+        }
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, nm in names.items():
+                    if r & bit:
+                        self.reasons.add(nm)
+            except Exception:
+                pass
+            self._stop.wait(self.period)
+
+    def stop(self):
+        self._stop.set()
+        self.join(timeout=2)
+        s = sorted(self.samples)
+        return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(s)}
+
+
+# --------------------------------------------------------------------------------------
+# reference arm: the reference's own C++ engine (oracle/_ref) on the host cores
+# --------------------------------------------------------------------------------------
+def cpu_roundtrip_rate(group_elems: int, budget_s: float, threads: int, seed: int = 1234):
+    """Times the reference CPU path (oracle/_ref when it was built here, else the C port) on a
+    bounded sample of the workload: round trip of `n` groups of N(0,1) fp16.  -> dict"""
+    import numpy as np
+    from oracle.oracle import Port, Ref
+
+    rng = np.random.default_rng(seed)
+    kind = "reference" if Ref.available() else "port"
+
+    def run(x16, ngroups):
+        t0 = time.perf_counter()
+        if kind == "reference":
+            Ref.roundtrip_batch(x16, 0, group_elems, threads)
+        else:
+            payload, scales, comp = Port.compress_batch(x16, group_elems, threads=threads)
+            Port.decompress_batch(payload, scales, comp, group_elems, 0, threads=threads)
+        return time.perf_counter() - t0
+
+    probe_groups = max(threads, 8) if group_elems >= 65536 else max(threads * 16, 256)
+    xp = rng.standard_normal(probe_groups * group_elems).astype(np.float16)
+    run(xp, probe_groups)                                    # warm-up (page faults, thread start)
+    t_probe = run(xp, probe_groups)
+    # one pass over <= 512 MiB of KV, repeated until the time budget is used
+    cap = max(probe_groups, (512 << 20) // (group_elems * 2))
+    n = int(max(probe_groups, min(probe_groups * budget_s / max(t_probe, 1e-6), cap)))
+    n = (n // threads) * threads or threads
+    x = rng.standard_normal(n * group_elems).astype(np.float16)
+    dt, reps = 0.0, 0
+    while dt < budget_s and reps < 1000:
+        dt += run(x, n)
+        reps += 1
+    gbs = reps * n * group_elems * 2 / dt / 1e9
+    return {"value": gbs, "unit": UNIT, "cores": threads, "kind": kind, "seconds": dt,
+            "sample": f"{reps} x {n} groups of {group_elems} fp16 N(0,1) elements ({n * group_elems * 2 / 2**20:.0f} MiB per pass), "
+                      f"compress+decompress round trip, {threads} threads, {dt:.1f} s"}
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    spec = workload_spec(args.workload, world, 0, args.scale)
+    threads = os.cpu_count() or 1
+    per_step_budget = max(2.0, min(10.0, 90.0 / max(1, args.steps + args.warmup)))
+    vals = []
+    for i in range(args.warmup + args.steps):
+        r = cpu_roundtrip_rate(spec["group_elems"], per_step_budget, threads, seed=1234 + i)
+        if i >= args.warmup:
+            vals.append(r)
+    tot_bytes = sum(v["value"] * v["seconds"] for v in vals)
+    tot_s = sum(v["seconds"] for v in vals)
+    value = tot_bytes / tot_s
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_s / len(vals),
+            "higher_is_better": True, "scaling": spec["scaling"], "vs_baseline": None, "dtype": "f32+i8",
+            "data": "synthetic N(0,1) fp16 KV (numpy default_rng)",
+            "config": {"workload": spec["label"], "group_elems": spec["group_elems"],
+                       "note": "reference CPU engine (FPGACacheEngine::compress/decompress) on host cores; "
+                               "each step is a bounded sample of the workload"},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": vals[-1]["kind"],
+                             "sample": vals[-1]["sample"]},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------
+# CUDA arm
+# --------------------------------------------------------------------------------------
+def run_cuda(args, rank, world, local_rank):
+    import ctypes as C
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import cxl_speckv_b200 as pkg
+    from cxl_speckv_b200 import codec
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the CUDA path has no CPU fallback "
+                         "(use --impl reference for the CPU baseline)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    L = pkg.lib()
+
+    spec = workload_spec(args.workload, world, rank, args.scale)
+    G, n_groups, cg = spec["group_elems"], spec["n_groups"], spec["chunk_groups"]
+    sb = codec.slot_bytes(G)
+    n_chunks = (n_groups + cg - 1) // cg
+    # ---- resident synthetic KV (N(0,1), seed 1234 + rank), payload slots, one output chunk ------
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(1234 + rank)
+    x = torch.empty(n_groups * G, dtype=torch.float16, device=dev)
+    for c0 in range(0, n_groups, cg):
+        c1 = min(n_groups, c0 + cg)
+        x[c0 * G:c1 * G].normal_(generator=gen)
+    payload = torch.empty((n_groups, sb), dtype=torch.uint8, device=dev)
+    scales = torch.empty(n_groups, dtype=torch.float32, device=dev)
+    comp = torch.empty(n_groups, dtype=torch.int32, device=dev)
+    out = torch.empty((min(cg, n_groups), G), dtype=torch.float16, device=dev)
+    gathered = torch.empty(world * n_groups, dtype=torch.int32, device=dev) if world > 1 else None
+    stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    def compress_all():
+        for c0 in range(0, n_groups, cg):
+            n = min(cg, n_groups - c0)
+            st = L.speckv_ext_compress(x.data_ptr() + c0 * G * 2, 0, G, n, payload.data_ptr() + c0 * sb, sb,
+                                       scales.data_ptr() + c0 * 4, comp.data_ptr() + c0 * 4, 2, stream)
+            assert st == 0, st
+
+    def decompress_all():
+        for c0 in range(0, n_groups, cg):
+            n = min(cg, n_groups - c0)
+            st = L.speckv_ext_decompress(payload.data_ptr() + c0 * sb, sb, scales.data_ptr() + c0 * 4,
+                                         comp.data_ptr() + c0 * 4, G, n, 0, out.data_ptr(), None, 2, stream)
+            assert st == 0, st
+
+    def step(ev=None):
+        if ev:
+            ev[0].record()
+        compress_all()
+        if ev:
+            ev[1].record()
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, comp)     # page-table metadata exchange
+        if ev:
+            ev[2].record()
+        decompress_all()
+        if ev:
+            ev[3].record()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    codec_stats0 = codec.stats()
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t_start.record()
+    for i in range(args.steps):
+        step(evs[i])
+    t_end.record()
+    barrier()
+    clocks = sampler.stop()
+    launches = codec.stats()["kernel_launches"] - codec_stats0["kernel_launches"]
+    elapsed_ms = t_start.elapsed_time(t_end)
+    t_comp = sum(e[0].elapsed_time(e[1]) for e in evs) / args.steps
+    t_dec = sum(e[2].elapsed_time(e[3]) for e in evs) / args.steps
+    tt = torch.tensor([elapsed_ms, t_comp, t_dec], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    elapsed_ms, t_comp_max, t_dec_max = tt.tolist()
+
+    kv_bytes = n_groups * G * 2                                   # this rank, per step
+    comp_total = int(comp.to(torch.int64).sum().item())           # payload bytes c, this rank
+    tot = torch.tensor([kv_bytes, comp_total, n_groups], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    kv_bytes_all, comp_all, groups_all = tot.tolist()
+    ms_per_step = elapsed_ms / args.steps
+    value = kv_bytes_all / (ms_per_step * 1e-3) / 1e9
+
+    # ---- roofline of the dominant kernel (per launch = one chunk of cg groups) -------------------
+    peak, peak_src = hbm_peak()
+    alg_comp = 2 * G * n_groups + comp_total + 12 * n_groups       # 2n read + c write + header
+    alg_dec = comp_total + 12 * n_groups + 2 * G * n_groups        # c read + header + 2n write
+    comp_gbs = alg_comp / (t_comp * 1e-3) / 1e9
+    dec_gbs = alg_dec / (t_dec * 1e-3) / 1e9
+    dom = "compress" if t_comp >= t_dec else "decompress"
+    dom_bytes_per_launch = (alg_comp if dom == "compress" else alg_dec) / n_chunks
+    dom_ms_per_launch = (t_comp if dom == "compress" else t_dec) / n_chunks
+    achieved = comp_gbs if dom == "compress" else dec_gbs
+    roofline = {"bound": "hbm", "kernel": f"kv_{dom}", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "peak_source": peak_src,
+                "traffic": ncu_traffic(f"{args.workload}:{dom}"),
+                "algorithmic_bytes_per_launch": dom_bytes_per_launch, "ms_per_launch": dom_ms_per_launch,
+                "compress": {"GB/s": comp_gbs, "frac": comp_gbs / peak, "ms_per_step": t_comp,
+                             "kv_GB/s": kv_bytes / (t_comp * 1e-3) / 1e9},
+                "decompress": {"GB/s": dec_gbs, "frac": dec_gbs / peak, "ms_per_step": t_dec,
+                               "kv_GB/s": kv_bytes / (t_dec * 1e-3) / 1e9},
+                "frac_of_nominal_8TBs": achieved / 8000.0}
+
+    # ---- e2e: host buffers through the C ABI, copies inside the timed region ----------------------
+    e2e = None
+    if not args.no_e2e:
+        ng = min(n_groups, max(1, int(args.e2e_mib * 2**20) // (G * 2)))
+        nb_in, nb_pay = ng * G * 2, ng * sb
+        h_in = L.speckv_ext_host_alloc(nb_in)
+        h_pay = L.speckv_ext_host_alloc(nb_pay)
+        h_out = L.speckv_ext_host_alloc(nb_in)
+        h_sc = L.speckv_ext_host_alloc(ng * 4)
+        h_cb = L.speckv_ext_host_alloc(ng * 4)
+        assert h_in and h_pay and h_out and h_sc and h_cb, "pinned host allocation failed"
+        C.memmove(h_in, x[:ng * G].cpu().numpy().ctypes.data, nb_in)
+
+        def e2e_step():
+            st = L.speckv_ext_compress_host(h_in, 0, G, ng, h_pay, sb, h_sc, h_cb, 2)
+            assert st == 0, st
+            st = L.speckv_ext_decompress_host(h_pay, sb, h_sc, h_cb, G, ng, 0, h_out, None, 2)
+            assert st == 0, st
+
+        e2e_step()
+        e2e_steps = max(1, min(args.steps, 5))
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            e2e_step()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        te = torch.tensor([dt], dtype=torch.float64, device=dev)
+        tb = torch.tensor([float(nb_in)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+            dist.all_reduce(tb, op=dist.ReduceOp.SUM)
+        e2e = {"value": tb.item() * e2e_steps / te.item() / 1e9, "unit": UNIT,
+               "h2d_bytes_per_step": nb_in + nb_pay + 8 * ng, "d2h_bytes_per_step": nb_pay + 8 * ng + nb_in,
+               "steps": e2e_steps, "api": "speckv_ext_compress_host + speckv_ext_decompress_host (pinned host buffers)",
+               "sample": f"{ng} groups ({nb_in / 2**20:.0f} MiB fp16) per rank per step"}
+        # the host path must reproduce the device path bit for bit
+        y = np.ctypeslib.as_array(C.cast(h_out, C.POINTER(C.c_uint16)), shape=(ng * G,))
+        codec_out = codec.decompress(codec.compress(x[:min(ng, 64) * G], G))
+        assert np.array_equal(y[:min(ng, 64) * G], codec_out.view(torch.int16).cpu().numpy().view(np.uint16).ravel())
+        for p in (h_in, h_pay, h_out, h_sc, h_cb):
+            L.speckv_ext_host_free(p)
+
+    # ---- CPU baseline (rank 0, N = 1 only) ----------------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cpu = cpu_roundtrip_rate(G, args.cpu_seconds, os.cpu_count() or 1)
+        cpu.pop("seconds", None)
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
+                "scaling": spec["scaling"], "vs_baseline": None, "dtype": "f32+i8", "data": "synthetic N(0,1) fp16 KV (torch seed 1234+rank)",
+                "config": {"workload": spec["label"], "group_elems": G, "groups_per_rank": n_groups,
+                           "groups_total": int(groups_all), "kv_bytes_per_step_total": int(kv_bytes_all),
+                           "launch_chunk_groups": cg, "global_batch": spec["global_batch"],
+                           "parallelism": f"independent shards x{world}, all-gather of comp_bytes only" if world > 1 else "single GPU",
+                           "cache": "inputs larger than L2 (no flush needed)" if kv_bytes > (1 << 30) else "inputs + outputs exceed L2 per step"},
+                "per_gpu_value": value / world,
+                "compression_ratio": {"vs_fp16": kv_bytes_all / comp_all, "vs_fp32_reference_accounting": 2 * kv_bytes_all / comp_all},
+                "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg3", "cfg4p"])
+    ap.add_argument("--scale", type=float, default=1.0, help="fraction of the workload's layers (debug only; 1.0 = the named config)")
+    ap.add_argument("--e2e-mib", type=float, default=2048.0, help="host-buffer sample per e2e step (MiB of fp16 KV)")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_cuda(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

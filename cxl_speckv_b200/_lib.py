@@ -23,7 +23,7 @@ class SpeckvError(RuntimeError):
 class Stats(C.Structure):
     _fields_ = [("total_compressions", C.c_uint64), ("total_decompressions", C.c_uint64),
                 ("total_translations", C.c_uint64), ("bytes_in_compress", C.c_uint64),
-                ("bytes_out_decompress", C.c_uint64)]
+                ("bytes_out_decompress", C.c_uint64), ("kernel_launches", C.c_uint64)]
 
 
 def lib_path() -> str:

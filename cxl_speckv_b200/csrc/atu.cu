@@ -7,6 +7,7 @@
 // Pure integer streaming: 8 B in + 8 B out per address, two addresses per thread
 // as one 128-bit load/store.
 #include "atu.h"
+#include "device_ctx.h"
 
 namespace speckv {
 
@@ -43,6 +44,7 @@ cudaError_t launch_translate(const uint64_t* d_va, uint64_t* d_pa, size_t n, int
     const size_t cap = (size_t)sm_count * 8;
     if (blocks > cap) blocks = cap;
     translate_kernel<<<(unsigned)blocks, 256, 0, st>>>(d_va, d_pa, n, vec_ok);
+    count_launch();
     return cudaGetLastError();
 }
 

@@ -96,4 +96,16 @@ __device__ __forceinline__ float dequantize(uint32_t code_u8, float s) {
     return __fmul_rn(y, s);
 }
 
+// Non-finite scale (a group that contained +-inf, or a caller-supplied NaN): x86
+// produces the "real indefinite" NaN 0xFFC00000 for 0*inf and propagates a NaN
+// operand quieted, whereas the GPU would return its canonical 0x7FFFFFFF.  Keep
+// the fp32 output bit-identical to the reference in those groups too.
+__device__ __forceinline__ bool scale_is_special(float s) { return !(fabsf(s) < __int_as_float(0x7f800000)); }
+__device__ __forceinline__ float dequantize_special(uint32_t code_u8, float s) {
+    const int q = (int)(int8_t)code_u8;
+    if (s != s) return __int_as_float(__float_as_int(s) | 0x00400000);
+    if (q == 0) return __int_as_float(0xffc00000);
+    return ((q < 0) != (s < 0.0f)) ? __int_as_float(0xff800000) : __int_as_float(0x7f800000);
+}
+
 }  // namespace speckv

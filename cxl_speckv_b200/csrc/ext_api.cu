@@ -59,6 +59,8 @@ speckv_status_t status_of(cudaError_t e) {
 
 // ---- statistics ---------------------------------------------------------------------
 static std::atomic<uint64_t> g_n_comp{0}, g_n_decomp{0}, g_n_xlate{0}, g_b_comp{0}, g_b_decomp{0};
+std::atomic<uint64_t> g_kernel_launches{0};
+void count_launch(unsigned n) { g_kernel_launches += n; }
 
 static size_t elem_bytes(int dtype) { return dtype == DT_F32 ? 4 : 2; }
 
@@ -338,6 +340,7 @@ void speckv_ext_get_stats(speckv_ext_stats_t* out) {
     out->total_translations = g_n_xlate.load();
     out->bytes_in_compress = g_b_comp.load();
     out->bytes_out_decompress = g_b_decomp.load();
+    out->kernel_launches = g_kernel_launches.load();
 }
 
 void speckv_ext_reset_stats(void) {
@@ -346,6 +349,7 @@ void speckv_ext_reset_stats(void) {
     g_n_xlate = 0;
     g_b_comp = 0;
     g_b_decomp = 0;
+    g_kernel_launches = 0;
 }
 
 }  // extern "C"

@@ -14,6 +14,7 @@
 //                                                      cache_engine.cpp:84-116,241-284
 #include "codec_math.cuh"
 #include "kv_codec.h"
+#include "device_ctx.h"
 
 namespace speckv {
 
@@ -286,6 +287,7 @@ decompress_rle_generic_kernel(const uint8_t* __restrict__ payload, size_t slot_b
         uint32_t npairs = comp_bytes[g] >> 1;  // a trailing odd byte is ignored (:245-247)
         npairs = min(npairs, (uint32_t)(slot_bytes >> 1));
         const float s = scales[g];
+        const bool special = scale_is_special(s);
         T* gout = out + (size_t)g * G;
         const bool vec_ok = (reinterpret_cast<uintptr_t>(gout) & 15) == 0;
         const bool in_vec_ok = (reinterpret_cast<uintptr_t>(gp) & 15) == 0;
@@ -328,7 +330,7 @@ decompress_rle_generic_kernel(const uint8_t* __restrict__ payload, size_t slot_b
                     const uint32_t lo = max(p, cur), e = min(p + cntv[k], hi);
                     for (uint32_t pos = lo; pos < e; ++pos) {
                         const uint32_t code = (qb + val[k] * (pos - p + 1)) & 0xffu;
-                        stage[pos - stage_base] = narrow<T>(dequantize(code, s));
+                        stage[pos - stage_base] = narrow<T>(special ? dequantize_special(code, s) : dequantize(code, s));
                     }
                     p += cntv[k];
                     qb += val[k] * cntv[k];
@@ -415,7 +417,9 @@ decompress_int8_generic_kernel(const uint8_t* __restrict__ payload, size_t slot_
         const uint32_t n = min(min(comp_bytes[g], G), (uint32_t)slot_bytes);
         const float s = scales[g];
         T* gout = out + (size_t)g * G;
-        for (uint32_t i = tid; i < n; i += kThreads) gout[i] = narrow<T>(dequantize(gp[i], s));
+        const bool special = scale_is_special(s);
+        for (uint32_t i = tid; i < n; i += kThreads)
+            gout[i] = narrow<T>(special ? dequantize_special(gp[i], s) : dequantize(gp[i], s));
         if (tid == 0 && out_elems) out_elems[g] = n;
     }
 }
@@ -462,6 +466,7 @@ static cudaError_t launch_compress_t(const CodecArgs& a, cudaStream_t st) {
         compress_int8_generic_kernel<T><<<grid, kThreads, 0, st>>>(in, a.group_elems, a.n_groups, pay, a.slot_bytes,
                                                                    a.scales, a.comp_bytes);
     }
+    count_launch();
     return cudaGetLastError();
 }
 
@@ -477,6 +482,7 @@ static cudaError_t launch_decompress_t(const CodecArgs& a, cudaStream_t st) {
         decompress_int8_generic_kernel<T><<<grid, kThreads, 0, st>>>(pay, a.slot_bytes, a.scales, a.comp_bytes,
                                                                      a.group_elems, a.n_groups, out, a.out_elems);
     }
+    count_launch();
     return cudaGetLastError();
 }
 
@@ -489,6 +495,7 @@ cudaError_t launch_compress_generic(const CodecArgs& a, cudaStream_t st) {
         if (e != cudaSuccess) return e;
         passthrough_meta_kernel<<<(a.n_groups + kThreads - 1) / kThreads, kThreads, 0, st>>>(a.n_groups, bytes, a.scales,
                                                                                             a.comp_bytes);
+        count_launch();
         return cudaGetLastError();
     }
     switch (a.dtype) {
@@ -504,6 +511,7 @@ cudaError_t launch_decompress_generic(const CodecArgs& a, cudaStream_t st) {
         passthrough_out_kernel<<<grid_for(a.n_groups, a.sm_count, 8), kThreads, 0, st>>>(
             static_cast<const uint8_t*>(a.payload), a.slot_bytes, a.comp_bytes, a.group_elems, a.n_groups,
             static_cast<uint16_t*>(a.out), a.out_elems);
+        count_launch();
         return cudaGetLastError();
     }
     switch (a.dtype) {

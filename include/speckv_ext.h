@@ -108,6 +108,7 @@ typedef struct {
     uint64_t total_translations;
     uint64_t bytes_in_compress;      /* uncompressed bytes consumed */
     uint64_t bytes_out_decompress;   /* uncompressed bytes produced (capacity) */
+    uint64_t kernel_launches;        /* CUDA kernels this library launched */
 } speckv_ext_stats_t;
 SPECKV_API void speckv_ext_get_stats(speckv_ext_stats_t* out);
 SPECKV_API void speckv_ext_reset_stats(void);
