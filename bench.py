@@ -86,7 +86,7 @@ class ClockSampler(threading.Thread):
         super().__init__(daemon=True)
         self.index, self.period = index, period
         self.samples, self.reasons, self.max_mhz = [], set(), None
-        self._stop = threading.Event()
+        self._halt = threading.Event()
         try:
             import pynvml
             pynvml.nvmlInit()
@@ -106,7 +106,7 @@ class ClockSampler(threading.Thread):
             getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20)): "sw_thermal_slowdown",
             getattr(nv, "nvmlClocksEventReasonSwPowerCap", getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4)): "sw_power_cap",
         }
-        while not self._stop.is_set():
+        while not self._halt.is_set():
             try:
                 self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
                 try:
@@ -118,10 +118,10 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(nm)
             except Exception:
                 pass
-            self._stop.wait(self.period)
+            self._halt.wait(self.period)
 
     def stop(self):
-        self._stop.set()
+        self._halt.set()
         self.join(timeout=2)
         s = sorted(self.samples)
         return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz,
@@ -333,7 +333,9 @@ def run_cuda(args, rank, world, local_rank):
         h_sc = L.speckv_ext_host_alloc(ng * 4)
         h_cb = L.speckv_ext_host_alloc(ng * 4)
         assert h_in and h_pay and h_out and h_sc and h_cb, "pinned host allocation failed"
-        C.memmove(h_in, x[:ng * G].cpu().numpy().ctypes.data, nb_in)
+        x_host = x[:ng * G].cpu().numpy()                      # keep alive across the memmove
+        C.memmove(h_in, x_host.ctypes.data, nb_in)
+        del x_host
 
         def e2e_step():
             st = L.speckv_ext_compress_host(h_in, 0, G, ng, h_pay, sb, h_sc, h_cb, 2)

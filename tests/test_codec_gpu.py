@@ -91,7 +91,7 @@ def test_golden_fixtures_int8_codes(golden):
 
 def test_bulk_group_digest(golden):
     m = golden["meta"]["bulk"]["splitmix42_131072"]
-    x = splitmix64_block(42, 131072).astype(np.float16)
+    x = splitmix64_block(42, 131072)          # fp32: values in [2,4) are not all fp16-representable
     c = codec.compress(torch.from_numpy(x).to(DEV), 131072)
     assert f32_bits(c.scales.cpu().numpy())[0] == m["scale_bits"]
     nb = int(c.comp_bytes[0].item())
@@ -99,7 +99,7 @@ def test_bulk_group_digest(golden):
     assert "%016x" % Port.fnv1a64(c.payload[0, :nb].cpu().numpy()) == m["payload_fnv1a64"]
     y32 = codec.decompress(c, dtype=torch.float32)
     assert "%016x" % Port.fnv1a64(y32.cpu().numpy()) == m["out_f32_fnv1a64"]
-    y16 = codec.decompress(c)
+    y16 = codec.decompress(c, dtype=torch.float16)
     assert "%016x" % Port.fnv1a64(y16.cpu().numpy()) == m["out_f16_fnv1a64"]
 
 
@@ -305,8 +305,8 @@ def test_full_size_properties_llama70b_layer():
     comp = c.comp_bytes.cpu().numpy().view(np.uint32)
     assert (comp % 2 == 0).all() and (comp <= 2 * G).all() and (comp > 1.9 * G).all()
     # scale == max|x| / 127 in IEEE fp32 for every group
-    amax = x.view(n_groups, G).float().abs().amax(dim=1)
-    assert torch.equal(c.scales, amax / 127.0)
+    amax = x.view(n_groups, G).float().abs().amax(dim=1).cpu().numpy()
+    assert np.array_equal(f32_bits(c.scales.cpu().numpy()), f32_bits(amax / np.float32(127.0)))  # IEEE divide on the host
     # every pair count >= 1 and counts sum to G (decoder length) for every group
     oel = torch.zeros(n_groups, dtype=torch.int32, device=DEV)
     y = codec.decompress(c, out_elems=oel)
