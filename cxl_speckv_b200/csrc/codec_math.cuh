@@ -75,6 +75,17 @@ __device__ __forceinline__ uint32_t quantize_fast(float x, float s, float r) {
     return round_wrap_u8<false>(__fmul_rn(y, 127.0f));
 }
 
+// Same value as an int (only its low byte is meaningful): t + copysign(0.5, t) added
+// round-toward-zero, then truncated.  Used where the byte mask is applied later (packing).
+__device__ __forceinline__ uint32_t quantize_fast_i(float x, float s, float r) {
+    const float y0 = __fmul_rn(x, r);
+    const float e = __fmaf_rn(-y0, s, x);
+    const float y = __fmaf_rn(e, r, y0);
+    const float t = __fmul_rn(y, 127.0f);
+    const float half = __uint_as_float((__float_as_uint(t) & 0x80000000u) | 0x3f000000u);
+    return (uint32_t)__float2int_rz(__fadd_rz(t, half));
+}
+
 // Is the fast form valid for a group whose max-abs is m (element type T)?
 template <typename T> __device__ __forceinline__ bool fast_quant_ok(float m);
 template <> __device__ __forceinline__ bool fast_quant_ok<__half>(float m) { return m > 0.0f && m < __int_as_float(0x7f800000); }

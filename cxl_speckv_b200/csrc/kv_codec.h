@@ -23,8 +23,16 @@ struct CodecArgs {
 };
 
 // any geometry, any alignment (kv_codec_generic.cu)
-cudaError_t launch_compress_generic(const CodecArgs& a, cudaStream_t st);
-cudaError_t launch_decompress_generic(const CodecArgs& a, cudaStream_t st);
+// `only_flagged` (optional, device): process group g only if only_flagged[g] != 0
+cudaError_t launch_compress_generic(const CodecArgs& a, cudaStream_t st, const uint32_t* only_flagged = nullptr);
+cudaError_t launch_decompress_generic(const CodecArgs& a, cudaStream_t st, const uint32_t* only_flagged = nullptr);
+
+// tuned fp16/bf16 kernels for groups of R * 2048 elements (kv_codec_fast.cu).  fast_regions()
+// returns R when they cover the call, else 0; they set flags[g] = 1 for every group they leave
+// to the generic kernel.
+int fast_regions(const CodecArgs& a, bool decompress);
+cudaError_t launch_compress_fast(int R, const CodecArgs& a, uint32_t* flags, cudaStream_t st);
+cudaError_t launch_decompress_fast(int R, const CodecArgs& a, uint32_t* flags, cudaStream_t st);
 
 // dispatch: tuned kernels for the common geometries, generic otherwise (kv_codec_dispatch.cu)
 cudaError_t launch_compress(const CodecArgs& a, cudaStream_t st);

@@ -1,10 +1,44 @@
 // kv_codec_dispatch.cu -- picks the kernel family for a codec call.
+//
+// fp16/bf16 groups of R * 2048 elements (R a power of two up to 128) go to the tuned
+// TMA/cluster kernels; every group those flag (runs of 8+ equal deltas, non-finite or
+// tiny scales) and every other geometry goes to the generic kernel.  Both launches are
+// ordered on the caller's stream; the flag array comes from the stream-ordered pool.
+#include <cstdlib>
+
 #include "kv_codec.h"
 
 namespace speckv {
 
-cudaError_t launch_compress(const CodecArgs& a, cudaStream_t st) { return launch_compress_generic(a, st); }
+static bool force_generic() {
+    static const bool v = [] {
+        const char* e = std::getenv("SPECKV_FORCE_GENERIC");
+        return e && e[0] == '1';
+    }();
+    return v;
+}
 
-cudaError_t launch_decompress(const CodecArgs& a, cudaStream_t st) { return launch_decompress_generic(a, st); }
+template <typename Fast, typename Generic>
+static cudaError_t two_pass(const CodecArgs& a, cudaStream_t st, bool decompress, Fast fast, Generic generic) {
+    const int R = force_generic() ? 0 : fast_regions(a, decompress);
+    if (R == 0) return generic(a, st, nullptr);
+    uint32_t* flags = nullptr;
+    cudaError_t e = cudaMallocAsync(reinterpret_cast<void**>(&flags), (size_t)a.n_groups * sizeof(uint32_t), st);
+    if (e != cudaSuccess) return e;
+    e = fast(R, a, flags, st);
+    if (e == cudaSuccess) e = generic(a, st, flags);
+    cudaError_t e2 = cudaFreeAsync(flags, st);
+    return e != cudaSuccess ? e : e2;
+}
+
+cudaError_t launch_compress(const CodecArgs& a, cudaStream_t st) {
+    return two_pass(a, st, false, launch_compress_fast,
+                    [](const CodecArgs& x, cudaStream_t s, const uint32_t* f) { return launch_compress_generic(x, s, f); });
+}
+
+cudaError_t launch_decompress(const CodecArgs& a, cudaStream_t st) {
+    return two_pass(a, st, true, launch_decompress_fast,
+                    [](const CodecArgs& x, cudaStream_t s, const uint32_t* f) { return launch_decompress_generic(x, s, f); });
+}
 
 }  // namespace speckv

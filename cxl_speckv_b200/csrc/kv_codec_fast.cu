@@ -1,0 +1,778 @@
+// kv_codec_fast.cu -- KV block codec, tuned sm_100a path for fp16/bf16 groups of
+// R * 2048 elements (R = 1, 2, 4 ... 128; the 4 KiB page group and the
+// 1024-token x 128-dim block are R = 1 and R = 64).
+//
+// Geometry.  A *region* is 2048 consecutive elements (compress) or 2048
+// consecutive [value][count] pairs (decompress): 4 KiB, owned by one warp and
+// brought into shared memory by ONE bulk-TMA copy (cp.async.bulk, completion on
+// a per-warp mbarrier).  A CTA has 16 warps = 16 regions = 64 KiB of tiles.
+// A group of R regions is R warps of one CTA (R <= 16; 16/R groups per CTA) or a
+// thread-block cluster of R/16 CTAs (R = 32/64/128 -> clusters of 2/4/8) whose
+// CTAs exchange one word per region through distributed shared memory:
+//   * the region max-abs  (group scale, cache_engine.cpp:172-184)
+//   * the region run-head count / the region (sum count, sum value*count)
+//     (exclusive sums give every region its output offset and, for decode, its
+//     starting code), so delta + RLE still run over the whole flat group exactly
+//     as the reference's sequential loops do (cache_engine.cpp:198-273).
+// HBM traffic is the algorithmic minimum: each input byte is read once (TMA ->
+// smem, max-abs and quantisation both read the smem tile), each output byte is
+// written once with 128-bit stores.
+//
+// The tuned kernels assume what holds for KV activations: no run of equal deltas
+// spans a whole 8-element lane chunk (compress) / ordinary payloads (decompress).
+// Groups that violate it (constant blocks, zeros, +-inf, tiny bf16 scales) are
+// flagged in `needs_generic` and re-done by the generic kernel
+// (kv_codec_generic.cu) in the same stream, so results are bit-exact for every
+// input.
+#include <cooperative_groups.h>
+
+#include "codec_math.cuh"
+#include "device_ctx.h"
+#include "kv_codec.h"
+
+namespace cg = cooperative_groups;
+
+namespace speckv {
+
+namespace {
+
+constexpr int kW = 16;                  // warps (= regions) per CTA
+constexpr int kThreadsF = kW * 32;
+constexpr int kRegion = 2048;           // elements / pairs per region
+constexpr int kIters = 8;               // 256 per warp iteration, 8 per lane
+constexpr int kRegionBytes = 4096;
+constexpr int kRingBytes = 1024;        // 512 pairs (compress) / 256 elements + slack (decompress)
+constexpr unsigned kFull = 0xffffffffu;
+
+constexpr int kPadBytes = 512;          // staging slack in front of every region tile (in-place emission)
+constexpr int kBlockBytes = kPadBytes + kRegionBytes;
+
+struct FastSmem {
+    alignas(128) uint8_t tile[kW][kBlockBytes];   // [pad][4 KiB region]; outputs are staged in place, 16 B..512 B behind the reads
+    alignas(8) unsigned long long mbar[kW];
+    uint32_t xa[kW];   // exchange word A: region max bits | head count | sum of counts
+    uint32_t xb[kW];   // exchange word B: flags | sum of value*count
+};
+
+// PRMT selectors that delete 16-bit unit h from a quad W0..W3 (out_k = prmt(W_k, W_{k+1}, sel[h][k]))
+__constant__ uint32_t c_del_sel[8][4] = {
+    {0x5432, 0x5432, 0x5432, 0x5432}, {0x5410, 0x5432, 0x5432, 0x5432}, {0x3210, 0x5432, 0x5432, 0x5432},
+    {0x3210, 0x5410, 0x5432, 0x5432}, {0x3210, 0x3210, 0x5432, 0x5432}, {0x3210, 0x3210, 0x5410, 0x5432},
+    {0x3210, 0x3210, 0x3210, 0x5432}, {0x3210, 0x3210, 0x3210, 0x5410}};
+// PRMT selectors that duplicate byte h of the 8 bytes (A = bytes 0-3, B = bytes 4-7) into 9 bytes:
+// O0 = prmt(A, A, sel[h][0]), O1 = prmt(A, B, sel[h][1]), byte 8 = B >> 24
+__constant__ uint32_t c_dup_sel[8][2] = {{0x2100, 0x6543}, {0x2110, 0x6543}, {0x2210, 0x6543}, {0x3210, 0x6543},
+                                         {0x3210, 0x6544}, {0x3210, 0x6554}, {0x3210, 0x6654}, {0x3210, 0x7654}};
+
+// ---- PTX helpers ------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t a, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(a), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t a, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(a), "r"(bytes) : "memory");
+}
+// one bulk-TMA copy global -> shared, completion counted in bytes on the mbarrier
+__device__ __forceinline__ void tma_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t mbar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(mbar)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t a, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}" ::"r"(a),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ uint4 lds128(const void* p) { return *reinterpret_cast<const uint4*>(p); }
+__device__ __forceinline__ void stg128(void* p, uint4 v) {
+    asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
+                 : "memory");
+}
+
+// 4-bit mask of the non-zero bytes of x (bit i <- byte i != 0)
+__device__ __forceinline__ uint32_t nonzero_bytes4(uint32_t x) {
+    uint32_t t = ((x & 0x7f7f7f7fu) + 0x7f7f7f7fu) | x;
+    t = (t >> 7) & 0x01010101u;
+    return (t * 0x01020408u) >> 24;
+}
+
+template <typename T> __device__ __forceinline__ void unpack8(const uint4& raw, float (&x)[8]);
+template <> __device__ __forceinline__ void unpack8<__half>(const uint4& raw, float (&x)[8]) {
+    const __half2* h = reinterpret_cast<const __half2*>(&raw);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        float2 f = __half22float2(h[i]);
+        x[2 * i] = f.x;
+        x[2 * i + 1] = f.y;
+    }
+}
+template <> __device__ __forceinline__ void unpack8<__nv_bfloat16>(const uint4& raw, float (&x)[8]) {
+    const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        x[2 * i] = __uint_as_float(w[i] << 16);
+        x[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+    }
+}
+
+// |x| max of 8 packed elements folded into a packed running max (NaN operands are dropped)
+template <typename T> struct Pack2;
+template <> struct Pack2<__half> { using type = __half2; };
+template <> struct Pack2<__nv_bfloat16> { using type = __nv_bfloat162; };
+
+template <typename T>
+__device__ __forceinline__ typename Pack2<T>::type absmax8(typename Pack2<T>::type m, const uint4& raw) {
+    using P = typename Pack2<T>::type;
+    const P* h = reinterpret_cast<const P*>(&raw);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) m = __hmax2(m, __habs2(h[i]));
+    return m;
+}
+__device__ __forceinline__ float pack_max_to_float(__half2 m) { return fmaxf(__low2float(m), __high2float(m)); }
+__device__ __forceinline__ float pack_max_to_float(__nv_bfloat162 m) { return fmaxf(__low2float(m), __high2float(m)); }
+
+template <typename T> __device__ __forceinline__ uint32_t pack2_out(float a, float b);
+template <> __device__ __forceinline__ uint32_t pack2_out<__half>(float a, float b) {
+    __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+}
+template <> __device__ __forceinline__ uint32_t pack2_out<__nv_bfloat16>(float a, float b) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+}
+template <typename T> __device__ __forceinline__ uint16_t out_bits(float a) {
+    T h = narrow<T>(a);
+    return *reinterpret_cast<uint16_t*>(&h);
+}
+
+// synchronise the warps (CTAs) that share a group
+template <int R>
+__device__ __forceinline__ void group_sync() {
+    if (R == 1) __syncwarp();
+    else if (R <= kW) __syncthreads();
+    else cg::this_cluster().sync();
+}
+
+// Exchange: every region published one word in its CTA's `arr[warp]`; returns to all lanes
+// the reduction over the R regions of this group.  `sum_before` = sum over regions with a
+// lower index (exclusive prefix), `total` = sum over all, `mx` = max over all.
+template <int R>
+__device__ __forceinline__ void group_gather(uint32_t* arr, int warp, int lane, int ridx, uint32_t& sum_before,
+                                             uint32_t& total, uint32_t& mx) {
+    uint32_t before = 0, tot = 0, m = 0;
+    if (R == 1) {
+        const uint32_t v = arr[warp];
+        tot = v;
+        m = v;
+    } else if (R <= kW) {
+        const int base = (warp / R) * R;
+        uint32_t v = 0;
+        if (lane < R) v = arr[base + lane];
+        before = __reduce_add_sync(kFull, lane < ridx ? v : 0u);
+        tot = __reduce_add_sync(kFull, v);
+        m = __reduce_max_sync(kFull, v);
+    } else {
+        constexpr int C = R / kW;
+        cg::cluster_group cluster = cg::this_cluster();
+        uint32_t b = 0, t = 0, mm = 0;
+        if (lane < kW) {
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                const uint32_t* remote = cluster.map_shared_rank(arr, c);
+                const uint32_t v = remote[lane];
+                t += v;
+                mm = max(mm, v);
+                if (c * kW + lane < ridx) b += v;
+            }
+        }
+        before = __reduce_add_sync(kFull, b);
+        tot = __reduce_add_sync(kFull, t);
+        m = __reduce_max_sync(kFull, mm);
+    }
+    sum_before = before;
+    total = tot;
+    mx = m;
+}
+
+__device__ __forceinline__ void sts32(uint32_t a, uint32_t v) { asm volatile("st.shared.b32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ void sts16(uint32_t a, uint32_t v) {
+    asm volatile("st.shared.b16 [%0], %1;" ::"r"(a), "h"((unsigned short)v) : "memory");
+}
+__device__ __forceinline__ uint4 lds128s(uint32_t a) {
+    uint4 r;
+    asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(a));
+    return r;
+}
+__device__ __forceinline__ uint32_t lds16s(uint32_t a) {
+    unsigned short r;
+    asm volatile("ld.shared.b16 %0, [%1];" : "=h"(r) : "r"(a));
+    return r;
+}
+
+// Store n (<= 8, or <= 9 with w4) consecutive 16-bit units held in w0..w3 (w4) at a 2-byte aligned
+// shared address.  `n_full` is the register capacity (8 or 9 units); n is n_full or n_full - 1.
+__device__ __forceinline__ void store_units8(uint32_t a, uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3, int n) {
+    if ((a & 2u) == 0) {
+        sts32(a, w0);
+        sts32(a + 4, w1);
+        sts32(a + 8, w2);
+        if (n == 8) sts32(a + 12, w3);
+        else sts16(a + 12, w3);
+    } else {
+        sts16(a, w0);
+        sts32(a + 2, __byte_perm(w0, w1, 0x5432));
+        sts32(a + 6, __byte_perm(w1, w2, 0x5432));
+        sts32(a + 10, __byte_perm(w2, w3, 0x5432));
+        if (n == 8) sts16(a + 14, w3 >> 16);
+    }
+}
+__device__ __forceinline__ void store_units9(uint32_t a, uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3, uint32_t w4,
+                                             int n) {
+    if ((a & 2u) == 0) {
+        sts32(a, w0);
+        sts32(a + 4, w1);
+        sts32(a + 8, w2);
+        sts32(a + 12, w3);
+        if (n == 9) sts16(a + 16, w4);
+    } else {
+        sts16(a, w0);
+        sts32(a + 2, __byte_perm(w0, w1, 0x5432));
+        sts32(a + 6, __byte_perm(w1, w2, 0x5432));
+        sts32(a + 10, __byte_perm(w2, w3, 0x5432));
+        if (n == 9) sts32(a + 14, __byte_perm(w3, w4, 0x5432));
+        else sts16(a + 14, w3 >> 16);
+    }
+}
+
+// Copy the staged 16-bit units [lo, hi) (indices in the group's output stream) to global memory.
+// Unit i lives at shared address sbase + 2*i and at global address gout + 2*i; both are congruent
+// mod 16, so whole vectors move with one 128-bit load + one 128-bit store; the ragged first/last
+// vectors (shared with the neighbouring regions' streams) are written in 2-byte pieces.
+__device__ __forceinline__ void flush_region(uint32_t sbase, uint8_t* gout, int lo, int hi, int lane) {
+    if (hi <= lo) return;
+    const int v0 = lo >> 3, v1 = (hi + 7) >> 3;
+    for (int v = v0 + lane; v < v1; v += 32) {
+        const int a = v << 3, b = a + 8;
+        if (a >= lo && b <= hi) {
+            stg128(gout + ((size_t)v << 4), lds128s(sbase + ((uint32_t)v << 4)));
+        } else {
+            const int s = max(a, lo), e = min(b, hi);
+            for (int i = s; i < e; ++i)
+                *reinterpret_cast<uint16_t*>(gout + ((size_t)i << 1)) = (uint16_t)lds16s(sbase + ((uint32_t)i << 1));
+        }
+    }
+}
+
+// ===================================================================================
+// compress
+// ===================================================================================
+template <typename T, int R>
+__global__ void __launch_bounds__(kThreadsF, 2)
+compress_fast_kernel(const T* __restrict__ in, uint32_t n_groups, uint8_t* __restrict__ payload, size_t slot_bytes,
+                     float* __restrict__ scales, uint32_t* __restrict__ comp_bytes,
+                     uint32_t* __restrict__ needs_generic) {
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    FastSmem& sm = *reinterpret_cast<FastSmem*>(smem_raw);
+    constexpr int C = R > kW ? R / kW : 1;        // CTAs per group (cluster size)
+    constexpr int GPC = R >= kW ? 1 : kW / R;     // groups per CTA
+    constexpr uint32_t G = (uint32_t)R * kRegion;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const unsigned lt_mask = (1u << lane) - 1u;
+
+    uint32_t g;
+    int ridx;
+    if (R >= kW) {
+        const unsigned crank = C > 1 ? cg::this_cluster().block_rank() : 0u;
+        g = blockIdx.x / C;
+        ridx = (int)crank * kW + warp;
+    } else {
+        g = blockIdx.x * GPC + warp / R;
+        ridx = warp % R;
+    }
+    const bool active = g < n_groups;
+    const T* rin = in + (size_t)g * G + (size_t)ridx * kRegion;
+    uint8_t* reg = sm.tile[warp] + kPadBytes;
+    const uint32_t reg_s = smem_u32(reg);
+    const uint32_t mb = smem_u32(&sm.mbar[warp]);
+
+    // ---- 0. one bulk-TMA copy per region -------------------------------------------------------
+    if (lane == 0) {
+        mbar_init(mb, 1);
+        if (active) {
+            mbar_expect_tx(mb, kRegionBytes);
+            tma_load_1d(reg_s, rin, kRegionBytes, mb);
+        }
+    }
+    __syncwarp();
+
+    // ---- 1. region max-abs, then the group max over its R regions -------------------------------
+    float m = 0.0f;
+    if (active) {
+        mbar_wait(mb, 0);
+        const uint32_t z = 0u;
+        typename Pack2<T>::type pm = *reinterpret_cast<const typename Pack2<T>::type*>(&z);
+#pragma unroll
+        for (int k = 0; k < kIters; ++k) pm = absmax8<T>(pm, lds128(reg + k * 512 + lane * 16));
+        m = pack_max_to_float(pm);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(kFull, m, o));
+    }
+    if (lane == 0) sm.xa[warp] = __float_as_uint(m);   // non-negative floats order like their bit patterns
+    group_sync<R>();
+    uint32_t t0, t1, gmax_bits;
+    group_gather<R>(sm.xa, warp, lane, ridx, t0, t1, gmax_bits);
+    const float gmax = __uint_as_float(gmax_bits);
+    const float s = scale_from_max(gmax);
+    const bool fast = fast_quant_ok<T>(gmax);
+    const float r = __frcp_rn(s);
+    group_sync<R>();   // xa is reused below
+
+    // ---- 2a. quantise, delta, run-boundary flags; results parked in the lane's own 16-byte slot ----
+    // slot = { dsh0, dsh1 : deltas shifted by one element (byte j = delta[pos_j - 1]),
+    //          nz0,  nz1  : bit 7 of byte j set iff position j starts a run (delta[j] != delta[j-1]) }
+    uint32_t heads = 0;
+    bool cplx = !fast;
+    uint32_t carry_q = 0, carry_d1 = 0, halo_nz0 = 0u, halo_nz1 = 0x80000000u;
+    if (active && fast) {
+        if (ridx > 0) {
+            // halo: the 16 elements before the region give the last code, the last delta and the
+            // run boundaries among the last 4 positions before the region (all local, no neighbour needed)
+            uint32_t qh = 0;
+            if (lane < 16) qh = quantize_fast(widen<T>(rin[lane - 16]), s, r);
+            const uint32_t qp = __shfl_up_sync(kFull, qh, 1);
+            const uint32_t dh = (qh - qp) & 0xffu;
+            const uint32_t dp = __shfl_up_sync(kFull, dh, 1);
+            const unsigned chg = __ballot_sync(kFull, lane >= 8 && lane < 16 && dh != dp) >> 8;   // 8 bits
+            halo_nz0 = ((chg & 1u) << 7) | ((chg & 2u) << 14) | ((chg & 4u) << 21) | ((chg & 8u) << 28);
+            halo_nz1 = ((chg & 16u) << 3) | ((chg & 32u) << 10) | ((chg & 64u) << 17) | ((chg & 128u) << 24);
+            carry_q = __shfl_sync(kFull, qh, 15);
+            carry_d1 = __shfl_sync(kFull, dh, 15) << 24;
+            if (chg == 0) cplx = true;   // a run of 9+ equal deltas reaches the region edge
+        }
+        const int src_lane = (lane + 31) & 31;
+#pragma unroll
+        for (int k = 0; k < kIters; ++k) {
+            uint8_t* slot = reg + k * 512 + lane * 16;
+            const uint4 raw = lds128(slot);
+            float x[8];
+            unpack8<T>(raw, x);
+            uint32_t q[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) q[j] = quantize_fast_i(x[j], s, r);
+            // previous element's code: lane - 1, or (lane 0) lane 31 of the previous iteration
+            const uint32_t rq = __shfl_sync(kFull, q[7], src_lane);
+            const uint32_t pq = lane == 0 ? carry_q : rq;
+            carry_q = rq;
+            uint32_t d[8];
+            d[0] = q[0] - pq;
+#pragma unroll
+            for (int j = 1; j < 8; ++j) d[j] = q[j] - q[j - 1];
+            const uint32_t d0 = __byte_perm(__byte_perm(d[0], d[1], 0x0040), __byte_perm(d[2], d[3], 0x0040), 0x5410);
+            const uint32_t d1 = __byte_perm(__byte_perm(d[4], d[5], 0x0040), __byte_perm(d[6], d[7], 0x0040), 0x5410);
+            const uint32_t rd = __shfl_sync(kFull, d1, src_lane);
+            const uint32_t pd1 = lane == 0 ? carry_d1 : rd;
+            carry_d1 = rd;
+            const uint32_t dsh0 = __byte_perm(pd1, d0, 0x6543);
+            const uint32_t dsh1 = __byte_perm(d0, d1, 0x6543);
+            const uint32_t x0 = d0 ^ dsh0, x1 = d1 ^ dsh1;
+            uint32_t nz0 = (((x0 & 0x7f7f7f7fu) + 0x7f7f7f7fu) | x0) & 0x80808080u;
+            const uint32_t nz1 = (((x1 & 0x7f7f7f7fu) + 0x7f7f7f7fu) | x1) & 0x80808080u;
+            if (ridx == 0 && k == 0 && lane == 0) nz0 |= 0x80u;   // position 0 always starts a run
+            const int nh = __popc(nz0) + __popc(nz1);
+            cplx |= (nh == 0);                                    // a run of 9+ equal deltas: generic kernel
+            heads += nh;
+            *reinterpret_cast<uint4*>(slot) = make_uint4(dsh0, dsh1, nz0, nz1);
+        }
+        // after the loop lane 0's carries hold lane 31's last code word; make them warp-uniform
+        carry_d1 = __shfl_sync(kFull, carry_d1, 0);
+        heads = __reduce_add_sync(kFull, heads);
+    }
+    cplx = __any_sync(kFull, cplx);
+    if (lane == 0) {
+        sm.xa[warp] = active ? heads : 0u;
+        sm.xb[warp] = (active && cplx) ? 1u : 0u;
+    }
+    group_sync<R>();
+    uint32_t h_before, h_total, any_cplx;
+    group_gather<R>(sm.xa, warp, lane, ridx, h_before, h_total, t0);
+    group_gather<R>(sm.xb, warp, lane, ridx, t0, t1, any_cplx);
+    if (C > 1) cg::this_cluster().sync();   // peers may still be reading this CTA's exchange words
+    if (!active) return;
+    if (ridx == 0 && lane == 0) needs_generic[g] = any_cplx ? 1u : 0u;
+    if (any_cplx) return;
+
+    // ---- 2b. emit: a head at position p closes the previous run -> pair (delta[p-1], p - previous head).
+    //          Pairs are staged IN PLACE (behind the slots still to be read) at the alignment they
+    //          will have in global memory, then the region goes out in 128-bit stores.
+    uint8_t* gout = payload + (size_t)g * slot_bytes;
+    // Region 0 starts at pair index -1: the head at position 0 closes nothing, so its "pair" is
+    // staged in the pad in front of the tile and never flushed.
+    int pidx = (int)h_before - 1;
+    const int p0 = max(pidx, 0);                         // first real pair index of this region
+    const uint32_t sbase = reg_s - 16u - 2u * (uint32_t)(p0 & ~7);   // pair i is staged at sbase + 2*i
+    uint32_t carry_nz0 = halo_nz0, carry_nz1 = halo_nz1;
+    const int src_lane = (lane + 31) & 31;
+#pragma unroll 1
+    for (int k = 0; k < kIters; ++k) {
+        const uint4 st = lds128(reg + k * 512 + lane * 16);
+        __syncwarp();   // every lane has read its slot before any pair of this iteration lands on it
+        const uint32_t dsh0 = st.x, dsh1 = st.y;
+        const uint32_t nz0 = st.z, nz1 = st.w;
+        const uint32_t rn0 = __shfl_sync(kFull, nz0, src_lane), rn1 = __shfl_sync(kFull, nz1, src_lane);
+        const uint32_t pnz0 = lane == 0 ? carry_nz0 : rn0, pnz1 = lane == 0 ? carry_nz1 : rn1;
+        carry_nz0 = rn0;
+        carry_nz1 = rn1;
+        // distance back to the previous head (the previous lane chunk has at least one on this path)
+        const uint32_t lf = pnz1 ? ((uint32_t)__clz((int)pnz1) >> 3) + 1u : ((uint32_t)__clz((int)pnz0) >> 3) + 5u;
+        const uint32_t hw0 = ~nz0 & 0x80808080u, hw1 = ~nz1 & 0x80808080u;
+        const int nhole = __popc(hw0) + __popc(hw1);
+        if (!__any_sync(kFull, nhole > 1)) {
+            // ---- common case: every lane emits 8 pairs, or 7 (one position continues a run) ----
+            const unsigned bal = __ballot_sync(kFull, nhole != 0);
+            const int idx = pidx + 8 * lane - __popc(bal & lt_mask);
+            // counts: 1 everywhere, lf for the first unit; the unit after a hole inherits the hole's count
+            uint32_t c0 = 0x01010100u | lf, c1 = 0x01010101u;
+            int h = 8;
+            if (nhole) {
+                h = hw0 ? (__ffs((int)hw0) >> 3) - 1 : (__ffs((int)hw1) >> 3) + 3;
+                const uint32_t add = h == 0 ? lf : 1u;
+                if (h < 3) c0 += add << (8 * (h + 1));
+                else if (h < 7) c1 += add << (8 * (h - 3));
+            }
+            uint32_t w0 = __byte_perm(dsh0, c0, 0x5140), w1 = __byte_perm(dsh0, c0, 0x7362);
+            uint32_t w2 = __byte_perm(dsh1, c1, 0x5140), w3 = __byte_perm(dsh1, c1, 0x7362);
+            if (nhole) {
+                const uint4 sel = *reinterpret_cast<const uint4*>(c_del_sel[h]);
+                w0 = __byte_perm(w0, w1, sel.x);
+                w1 = __byte_perm(w1, w2, sel.y);
+                w2 = __byte_perm(w2, w3, sel.z);
+                w3 = __byte_perm(w3, 0u, sel.w);
+            }
+            store_units8(sbase + 2u * (uint32_t)idx, w0, w1, w2, w3, 8 - nhole);
+            pidx += 256 - __popc(bal);
+        } else {
+            // ---- some lane has two or more continuing positions: scan + one store per head ----
+            const int n = 8 - nhole;
+            int inc = n;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(kFull, inc, o);
+                if (lane >= o) inc += t;
+            }
+            int idx = pidx + inc - n;
+            uint32_t run = lf;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const uint32_t v = (j < 4 ? dsh0 >> (8 * j) : dsh1 >> (8 * (j - 4))) & 0xffu;
+                const uint32_t isz = (j < 4 ? nz0 >> (8 * j) : nz1 >> (8 * (j - 4))) & 0x80u;
+                if (isz) {
+                    sts16(sbase + 2u * (uint32_t)idx, v | (run << 8));
+                    ++idx;
+                    run = 1;
+                } else {
+                    ++run;
+                }
+            }
+            pidx += __shfl_sync(kFull, inc, 31);
+        }
+    }
+    if (ridx == R - 1) {
+        // the run still open at the end of the group (cache_engine.cpp:235-236)
+        if (lane == 0) {
+            const uint32_t cnt = carry_nz1 ? ((uint32_t)__clz((int)carry_nz1) >> 3) + 1u
+                                           : ((uint32_t)__clz((int)carry_nz0) >> 3) + 5u;
+            sts16(sbase + 2u * (uint32_t)pidx, (carry_d1 >> 24) | (cnt << 8));
+            scales[g] = s;
+            comp_bytes[g] = 2u * (uint32_t)(pidx + 1);
+        }
+        ++pidx;
+    }
+    __syncwarp();
+    flush_region(sbase, gout, p0, pidx, lane);
+}
+
+// ===================================================================================
+// decompress
+// ===================================================================================
+template <typename T, int R>
+__global__ void __launch_bounds__(kThreadsF, 2)
+decompress_fast_kernel(const uint8_t* __restrict__ payload, size_t slot_bytes, const float* __restrict__ scales,
+                       const uint32_t* __restrict__ comp_bytes, uint32_t n_groups, T* __restrict__ out,
+                       uint32_t* __restrict__ out_elems, uint32_t* __restrict__ needs_generic) {
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    FastSmem& sm = *reinterpret_cast<FastSmem*>(smem_raw);
+    constexpr int C = R > kW ? R / kW : 1;
+    constexpr int GPC = R >= kW ? 1 : kW / R;
+    constexpr uint32_t G = (uint32_t)R * kRegion;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const unsigned lt_mask = (1u << lane) - 1u;
+
+    uint32_t g;
+    int ridx;
+    if (R >= kW) {
+        const unsigned crank = C > 1 ? cg::this_cluster().block_rank() : 0u;
+        g = blockIdx.x / C;
+        ridx = (int)crank * kW + warp;
+    } else {
+        g = blockIdx.x * GPC + warp / R;
+        ridx = warp % R;
+    }
+    const bool active = g < n_groups;
+    uint8_t* reg = sm.tile[warp] + kPadBytes;
+    const uint32_t reg_s = smem_u32(reg);
+    const uint32_t mb = smem_u32(&sm.mbar[warp]);
+
+    // pairs of this region: [ridx * 2048, ridx * 2048 + np)
+    uint32_t np = 0;
+    float s = 1.0f;
+    bool cplx = false;
+    if (active) {
+        const uint32_t cb = comp_bytes[g];
+        uint32_t npairs = cb >> 1;                            // a trailing odd byte is ignored (:245-247)
+        if ((size_t)cb > slot_bytes) cplx = true;             // malformed: leave it to the generic kernel's clamping
+        npairs = min(npairs, (uint32_t)(R * kRegion));
+        const uint32_t first = (uint32_t)ridx * kRegion;
+        np = npairs > first ? min(npairs - first, (uint32_t)kRegion) : 0u;
+        s = scales[g];
+        cplx |= scale_is_special(s);
+    }
+    const uint8_t* rp = payload + (size_t)g * slot_bytes + (size_t)ridx * kRegionBytes;
+
+    if (lane == 0) {
+        mbar_init(mb, 1);
+        if (np > 0) {
+            const uint32_t bytes = ((np * 2u) + 15u) & ~15u;
+            mbar_expect_tx(mb, bytes);
+            tma_load_1d(reg_s, rp, bytes, mb);
+        }
+    }
+    __syncwarp();
+
+    // ---- A. region totals: elements produced (sum of counts) and code advance (sum of value*count) ----
+    uint32_t csum = 0, ssum = 0, nnz = 0;
+    if (np > 0) {
+        mbar_wait(mb, 0);
+#pragma unroll
+        for (int k = 0; k < kIters; ++k) {
+            const int pbase = k * 256 + lane * 8;
+            const int nv = min(max((int)np - pbase, 0), 8);
+            uint8_t* slot = reg + k * 512 + lane * 16;
+            uint4 w = lds128(slot);
+            if (nv < 8) {   // blank the pairs past the end of the payload (count 0 emits nothing)
+                uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    if (2 * i >= nv) ww[i] = 0u;
+                    else if (2 * i + 1 >= nv) ww[i] &= 0x0000ffffu;
+                }
+                w = make_uint4(ww[0], ww[1], ww[2], ww[3]);
+                *reinterpret_cast<uint4*>(slot) = w;
+            }
+            const uint32_t va = __byte_perm(w.x, w.y, 0x6420), ca = __byte_perm(w.x, w.y, 0x7531);
+            const uint32_t vb = __byte_perm(w.z, w.w, 0x6420), cb = __byte_perm(w.z, w.w, 0x7531);
+            csum = __dp4a(ca, 0x01010101u, csum);
+            csum = __dp4a(cb, 0x01010101u, csum);
+            ssum = __dp4a(va, ca, ssum);
+            ssum = __dp4a(vb, cb, ssum);
+            nnz += __popc((((ca & 0x7f7f7f7fu) + 0x7f7f7f7fu) | ca) & 0x80808080u) +
+                   __popc((((cb & 0x7f7f7f7fu) + 0x7f7f7f7fu) | cb) & 0x80808080u);
+        }
+        csum = __reduce_add_sync(kFull, csum);
+        ssum = __reduce_add_sync(kFull, ssum) & 0xffu;
+        nnz = __reduce_add_sync(kFull, nnz);
+        // in-place staging needs the output stream to stay within kPadBytes of the read position
+        if (csum - nnz > (uint32_t)(kPadBytes / 2 - 8)) cplx = true;
+    }
+    if (lane == 0) {
+        sm.xa[warp] = min(csum, G + 1u);   // saturate: sums stay < 2^32 and "> G" is still detectable
+        sm.xb[warp] = ssum | (cplx ? (1u << 24) : 0u);
+    }
+    group_sync<R>();
+    uint32_t e_before, e_total, q_before, xb_total, t0;
+    group_gather<R>(sm.xa, warp, lane, ridx, e_before, e_total, t0);
+    group_gather<R>(sm.xb, warp, lane, ridx, q_before, xb_total, t0);
+    if (C > 1) cg::this_cluster().sync();
+    if (!active) return;
+    const bool any_cplx = (xb_total >> 24) != 0 || e_total > G;   // output longer than the group: generic kernel clips
+    if (ridx == 0 && lane == 0) {
+        needs_generic[g] = any_cplx ? 1u : 0u;
+        if (out_elems && !any_cplx) out_elems[g] = e_total;
+    }
+    if (any_cplx || np == 0) return;
+
+    // ---- C. expand in place: element e of run j carries code q_before + ... + v_j * (e - start_j + 1) ----
+    uint8_t* gout = reinterpret_cast<uint8_t*>(out + (size_t)g * G);
+    const uint32_t e0 = e_before;
+    uint32_t ecur = e0;                       // next element index to produce
+    uint32_t qcur = q_before & 0xffu;         // code of element ecur - 1
+    const uint32_t sbase = reg_s - (uint32_t)kPadBytes - 2u * (e0 & ~7u);   // element i is staged at sbase + 2*i
+#pragma unroll 1
+    for (int k = 0; k < kIters; ++k) {
+        if (k * 256 >= (int)np) break;
+        const uint4 w = lds128(reg + k * 512 + lane * 16);
+        __syncwarp();
+        const uint32_t va = __byte_perm(w.x, w.y, 0x6420), ca = __byte_perm(w.x, w.y, 0x7531);
+        const uint32_t vb = __byte_perm(w.z, w.w, 0x6420), cb = __byte_perm(w.z, w.w, 0x7531);
+        // counts: z = c ^ 1 is 0 for a count of 1 and 3 for a count of 2
+        const uint32_t za = ca ^ 0x01010101u, zb = cb ^ 0x01010101u;
+        const bool small = (((za | zb) & 0xfcfcfcfcu) == 0) && (((za ^ (za >> 1)) & 0x01010101u) == 0) &&
+                           (((zb ^ (zb >> 1)) & 0x01010101u) == 0);
+        const uint32_t ta = za & 0x01010101u, tb = zb & 0x01010101u;   // byte j = 1 iff count j is 2
+        const int ntwo = __popc(ta) + __popc(tb);
+        const bool slow = __any_sync(kFull, !small || ntwo > 1);
+        const uint32_t sl = __dp4a(vb, cb, __dp4a(va, ca, 0u));
+        if (!slow) {
+            // every lane: 8 pairs -> 8 or 9 elements
+            const unsigned bal = __ballot_sync(kFull, ntwo != 0);
+            const uint32_t idx = ecur + 8u * lane + __popc(bal & lt_mask);
+            uint32_t inc = sl;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t t = __shfl_up_sync(kFull, inc, o);
+                if (lane >= o) inc += t;
+            }
+            const uint32_t tot = __shfl_sync(kFull, inc, 31);
+            uint32_t qb = qcur + inc - sl;
+            uint32_t v0 = va, v1 = vb, v2 = vb >> 24;
+            if (ntwo) {
+                const int h = ta ? (__ffs((int)ta) >> 3) : (__ffs((int)tb) >> 3) + 4;
+                const uint2 sel = *reinterpret_cast<const uint2*>(c_dup_sel[h]);
+                v0 = __byte_perm(va, va, sel.x);
+                v1 = __byte_perm(va, vb, sel.y);
+            }
+            float y[9];
+#pragma unroll
+            for (int j = 0; j < 9; ++j) {
+                qb += (j < 4 ? v0 >> (8 * j) : (j < 8 ? v1 >> (8 * (j - 4)) : v2)) & 0xffu;
+                y[j] = dequantize(qb & 0xffu, s);
+            }
+            store_units9(sbase + 2u * idx, pack2_out<T>(y[0], y[1]), pack2_out<T>(y[2], y[3]), pack2_out<T>(y[4], y[5]),
+                         pack2_out<T>(y[6], y[7]), pack2_out<T>(y[8], 0.0f), 8 + ntwo);
+            ecur += 256u + __popc(bal);
+            qcur = (qcur + tot) & 0xffu;
+        } else {
+            // any counts: exclusive scan of (elements, code advance), then per-pair loops
+            const uint32_t cl = __dp4a(cb, 0x01010101u, __dp4a(ca, 0x01010101u, 0u));
+            uint32_t inc = cl | (sl << 24);
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t t = __shfl_up_sync(kFull, inc, o);
+                if (lane >= o) inc += t;
+            }
+            const uint32_t tot = __shfl_sync(kFull, inc, 31);
+            const uint32_t excl = inc - (cl | (sl << 24));
+            uint32_t p = ecur + (excl & 0xffffffu);
+            uint32_t q = qcur + (excl >> 24);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const uint32_t v = (j < 4 ? va >> (8 * j) : vb >> (8 * (j - 4))) & 0xffu;
+                const uint32_t c = (j < 4 ? ca >> (8 * j) : cb >> (8 * (j - 4))) & 0xffu;
+                for (uint32_t t = 0; t < c; ++t) {
+                    q += v;
+                    sts16(sbase + 2u * (p + t), out_bits<T>(dequantize(q & 0xffu, s)));
+                }
+                p += c;
+            }
+            ecur += tot & 0xffffffu;
+            qcur = (qcur + (tot >> 24)) & 0xffu;
+        }
+    }
+    __syncwarp();
+    flush_region(sbase, gout, (int)e0, (int)ecur, lane);
+}
+
+// ---- launch -------------------------------------------------------------------------
+template <typename K>
+cudaError_t launch_clustered(K kernel, int R, uint32_t n_groups, cudaStream_t st, void** args) {
+    const int C = R > kW ? R / kW : 1;
+    const int gpc = R >= kW ? 1 : kW / R;
+    const size_t smem = sizeof(FastSmem);
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(R >= kW ? (size_t)n_groups * C : ((size_t)n_groups + gpc - 1) / gpc));
+    cfg.blockDim = dim3(kThreadsF);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = C;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    e = cudaLaunchKernelExC(&cfg, reinterpret_cast<const void*>(kernel), args);
+    count_launch();
+    return e;
+}
+
+template <typename T>
+cudaError_t compress_fast_t(int R, const CodecArgs& a, uint32_t* flags, cudaStream_t st) {
+    const T* in = static_cast<const T*>(a.in);
+    uint32_t n = a.n_groups;
+    uint8_t* pay = static_cast<uint8_t*>(a.payload);
+    size_t sb = a.slot_bytes;
+    float* sc = a.scales;
+    uint32_t* cb = a.comp_bytes;
+    void* args[] = {&in, &n, &pay, &sb, &sc, &cb, &flags};
+    switch (R) {
+#define SPECKV_CASE(RR) case RR: return launch_clustered(compress_fast_kernel<T, RR>, RR, n, st, args);
+        SPECKV_CASE(1) SPECKV_CASE(2) SPECKV_CASE(4) SPECKV_CASE(8) SPECKV_CASE(16) SPECKV_CASE(32) SPECKV_CASE(64) SPECKV_CASE(128)
+#undef SPECKV_CASE
+        default: return cudaErrorInvalidValue;
+    }
+}
+
+template <typename T>
+cudaError_t decompress_fast_t(int R, const CodecArgs& a, uint32_t* flags, cudaStream_t st) {
+    const uint8_t* pay = static_cast<const uint8_t*>(a.payload);
+    size_t sb = a.slot_bytes;
+    const float* sc = a.scales;
+    const uint32_t* cb = a.comp_bytes;
+    uint32_t n = a.n_groups;
+    T* out = static_cast<T*>(a.out);
+    uint32_t* oe = a.out_elems;
+    void* args[] = {&pay, &sb, &sc, &cb, &n, &out, &oe, &flags};
+    switch (R) {
+#define SPECKV_CASE(RR) case RR: return launch_clustered(decompress_fast_kernel<T, RR>, RR, n, st, args);
+        SPECKV_CASE(1) SPECKV_CASE(2) SPECKV_CASE(4) SPECKV_CASE(8) SPECKV_CASE(16) SPECKV_CASE(32) SPECKV_CASE(64) SPECKV_CASE(128)
+#undef SPECKV_CASE
+        default: return cudaErrorInvalidValue;
+    }
+}
+
+}  // namespace
+
+// regions per group if the tuned kernels cover this geometry, else 0
+int fast_regions(const CodecArgs& a, bool decompress) {
+    if (a.scheme != 2 || (a.dtype != DT_F16 && a.dtype != DT_BF16)) return 0;
+    if (a.group_elems == 0 || a.group_elems % kRegion) return 0;
+    const uint32_t R = a.group_elems / kRegion;
+    if (R > 128 || (R & (R - 1))) return 0;
+    const void* elems = decompress ? a.out : a.in;
+    if ((reinterpret_cast<uintptr_t>(elems) | reinterpret_cast<uintptr_t>(a.payload)) & 15) return 0;
+    if (a.slot_bytes < (size_t)R * kRegionBytes) return 0;
+    return (int)R;
+}
+
+cudaError_t launch_compress_fast(int R, const CodecArgs& a, uint32_t* flags, cudaStream_t st) {
+    return a.dtype == DT_F16 ? compress_fast_t<__half>(R, a, flags, st) : compress_fast_t<__nv_bfloat16>(R, a, flags, st);
+}
+
+cudaError_t launch_decompress_fast(int R, const CodecArgs& a, uint32_t* flags, cudaStream_t st) {
+    return a.dtype == DT_F16 ? decompress_fast_t<__half>(R, a, flags, st)
+                             : decompress_fast_t<__nv_bfloat16>(R, a, flags, st);
+}
+
+}  // namespace speckv

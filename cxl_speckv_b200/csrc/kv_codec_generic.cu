@@ -142,7 +142,8 @@ template <typename T>
 __global__ void __launch_bounds__(kThreads)
 compress_rle_generic_kernel(const T* __restrict__ in, uint32_t G, uint32_t n_groups,
                             uint8_t* __restrict__ payload, size_t slot_bytes,
-                            float* __restrict__ scales, uint32_t* __restrict__ comp_bytes) {
+                            float* __restrict__ scales, uint32_t* __restrict__ comp_bytes,
+                            const uint32_t* __restrict__ only_flagged) {
     __shared__ __align__(16) uint16_t stage[kTile + 16];
     __shared__ int wbuf[kWarps];
     __shared__ float fbuf[kWarps];
@@ -151,6 +152,7 @@ compress_rle_generic_kernel(const T* __restrict__ in, uint32_t G, uint32_t n_gro
     const int tid = threadIdx.x;
 
     for (uint32_t g = blockIdx.x; g < n_groups; g += gridDim.x) {
+        if (only_flagged && !only_flagged[g]) continue;   // second pass after the tuned kernel
         const T* gin = in + (size_t)g * G;
         uint8_t* gout = payload + (size_t)g * slot_bytes;
         const bool vec_ok = (reinterpret_cast<uintptr_t>(gin) & 15) == 0;
@@ -276,13 +278,14 @@ __global__ void __launch_bounds__(kThreads)
 decompress_rle_generic_kernel(const uint8_t* __restrict__ payload, size_t slot_bytes,
                               const float* __restrict__ scales, const uint32_t* __restrict__ comp_bytes,
                               uint32_t G, uint32_t n_groups, T* __restrict__ out,
-                              uint32_t* __restrict__ out_elems) {
+                              uint32_t* __restrict__ out_elems, const uint32_t* __restrict__ only_flagged) {
     constexpr int V = 16 / sizeof(T);
     __shared__ __align__(16) T stage[kWindow + V];
     __shared__ int wbuf[kWarps];
     const int tid = threadIdx.x;
 
     for (uint32_t g = blockIdx.x; g < n_groups; g += gridDim.x) {
+        if (only_flagged && !only_flagged[g]) continue;   // second pass after the tuned kernel
         const uint8_t* gp = payload + (size_t)g * slot_bytes;
         uint32_t npairs = comp_bytes[g] >> 1;  // a trailing odd byte is ignored (:245-247)
         npairs = min(npairs, (uint32_t)(slot_bytes >> 1));
@@ -455,13 +458,13 @@ inline int grid_for(uint32_t n_groups, int sm_count, int per_sm) {
 }  // namespace
 
 template <typename T>
-static cudaError_t launch_compress_t(const CodecArgs& a, cudaStream_t st) {
+static cudaError_t launch_compress_t(const CodecArgs& a, cudaStream_t st, const uint32_t* only_flagged) {
     const T* in = static_cast<const T*>(a.in);
     uint8_t* pay = static_cast<uint8_t*>(a.payload);
     const int grid = grid_for(a.n_groups, a.sm_count, 8);
     if (a.scheme == 2) {
         compress_rle_generic_kernel<T><<<grid, kThreads, 0, st>>>(in, a.group_elems, a.n_groups, pay, a.slot_bytes,
-                                                                  a.scales, a.comp_bytes);
+                                                                  a.scales, a.comp_bytes, only_flagged);
     } else {
         compress_int8_generic_kernel<T><<<grid, kThreads, 0, st>>>(in, a.group_elems, a.n_groups, pay, a.slot_bytes,
                                                                    a.scales, a.comp_bytes);
@@ -471,13 +474,13 @@ static cudaError_t launch_compress_t(const CodecArgs& a, cudaStream_t st) {
 }
 
 template <typename T>
-static cudaError_t launch_decompress_t(const CodecArgs& a, cudaStream_t st) {
+static cudaError_t launch_decompress_t(const CodecArgs& a, cudaStream_t st, const uint32_t* only_flagged) {
     T* out = static_cast<T*>(a.out);
     const uint8_t* pay = static_cast<const uint8_t*>(a.payload);
     const int grid = grid_for(a.n_groups, a.sm_count, 8);
     if (a.scheme == 2) {
         decompress_rle_generic_kernel<T><<<grid, kThreads, 0, st>>>(pay, a.slot_bytes, a.scales, a.comp_bytes,
-                                                                    a.group_elems, a.n_groups, out, a.out_elems);
+                                                                    a.group_elems, a.n_groups, out, a.out_elems, only_flagged);
     } else {
         decompress_int8_generic_kernel<T><<<grid, kThreads, 0, st>>>(pay, a.slot_bytes, a.scales, a.comp_bytes,
                                                                      a.group_elems, a.n_groups, out, a.out_elems);
@@ -486,7 +489,7 @@ static cudaError_t launch_decompress_t(const CodecArgs& a, cudaStream_t st) {
     return cudaGetLastError();
 }
 
-cudaError_t launch_compress_generic(const CodecArgs& a, cudaStream_t st) {
+cudaError_t launch_compress_generic(const CodecArgs& a, cudaStream_t st, const uint32_t* only_flagged) {
     if (a.n_groups == 0) return cudaSuccess;
     if (a.scheme == 0) {
         const uint32_t bytes = a.group_elems * 2u;
@@ -499,13 +502,13 @@ cudaError_t launch_compress_generic(const CodecArgs& a, cudaStream_t st) {
         return cudaGetLastError();
     }
     switch (a.dtype) {
-        case DT_F16: return launch_compress_t<__half>(a, st);
-        case DT_BF16: return launch_compress_t<__nv_bfloat16>(a, st);
-        default: return launch_compress_t<float>(a, st);
+        case DT_F16: return launch_compress_t<__half>(a, st, only_flagged);
+        case DT_BF16: return launch_compress_t<__nv_bfloat16>(a, st, only_flagged);
+        default: return launch_compress_t<float>(a, st, only_flagged);
     }
 }
 
-cudaError_t launch_decompress_generic(const CodecArgs& a, cudaStream_t st) {
+cudaError_t launch_decompress_generic(const CodecArgs& a, cudaStream_t st, const uint32_t* only_flagged) {
     if (a.n_groups == 0) return cudaSuccess;
     if (a.scheme == 0) {
         passthrough_out_kernel<<<grid_for(a.n_groups, a.sm_count, 8), kThreads, 0, st>>>(
@@ -515,9 +518,9 @@ cudaError_t launch_decompress_generic(const CodecArgs& a, cudaStream_t st) {
         return cudaGetLastError();
     }
     switch (a.dtype) {
-        case DT_F16: return launch_decompress_t<__half>(a, st);
-        case DT_BF16: return launch_decompress_t<__nv_bfloat16>(a, st);
-        default: return launch_decompress_t<float>(a, st);
+        case DT_F16: return launch_decompress_t<__half>(a, st, only_flagged);
+        case DT_BF16: return launch_decompress_t<__nv_bfloat16>(a, st, only_flagged);
+        default: return launch_decompress_t<float>(a, st, only_flagged);
     }
 }
 
