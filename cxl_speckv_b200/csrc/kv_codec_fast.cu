@@ -43,6 +43,7 @@ constexpr int kIters = 8;               // 256 per warp iteration, 8 per lane
 constexpr int kRegionBytes = 4096;
 constexpr int kRingBytes = 1024;        // 512 pairs (compress) / 256 elements + slack (decompress)
 constexpr unsigned kFull = 0xffffffffu;
+constexpr int kMaxR = 128;              // regions per group, at most
 
 constexpr int kPadBytes = 512;          // staging slack in front of every region tile (in-place emission)
 constexpr int kBlockBytes = kPadBytes + kRegionBytes;
@@ -50,8 +51,11 @@ constexpr int kBlockBytes = kPadBytes + kRegionBytes;
 struct FastSmem {
     alignas(128) uint8_t tile[kW][kBlockBytes];   // [pad][4 KiB region]; outputs are staged in place, 16 B..512 B behind the reads
     alignas(8) unsigned long long mbar[kW];
-    uint32_t xa[kW];   // exchange word A: region max bits | head count | sum of counts
-    uint32_t xb[kW];   // exchange word B: flags | sum of value*count
+    // exchange words of ALL regions of the group (every region pushes its word into every CTA of the
+    // cluster), indexed by region for cluster groups and by warp for groups inside one CTA
+    uint32_t xa[kMaxR];   // region max bits | head count + flags | sum of counts
+    uint32_t xb[kMaxR];   // sum of value*count + flags
+    uint32_t xc[kMaxR];   // second round of xa (no reuse hazard between rounds)
 };
 
 // PRMT selectors that delete 16-bit unit h from a quad W0..W3 (out_k = prmt(W_k, W_{k+1}, sel[h][k]))
@@ -164,45 +168,43 @@ __device__ __forceinline__ void group_sync() {
     else cg::this_cluster().sync();
 }
 
-// Exchange: every region published one word in its CTA's `arr[warp]`; returns to all lanes
-// the reduction over the R regions of this group.  `sum_before` = sum over regions with a
-// lower index (exclusive prefix), `total` = sum over all, `mx` = max over all.
+// Exchange between the regions of a group.  publish(): the region's lane 0 (lanes 0..C-1 for a
+// cluster) stores its word into the array of every CTA of the group -- local shared memory, or
+// distributed shared memory through mapa/st.shared::cluster.  After group_sync() every warp reads
+// the words of its group locally: `before` = sum over lower-indexed regions, `total`, `mx` = max.
 template <int R>
-__device__ __forceinline__ void group_gather(uint32_t* arr, int warp, int lane, int ridx, uint32_t& sum_before,
-                                             uint32_t& total, uint32_t& mx) {
-    uint32_t before = 0, tot = 0, m = 0;
-    if (R == 1) {
-        const uint32_t v = arr[warp];
-        tot = v;
-        m = v;
-    } else if (R <= kW) {
-        const int base = (warp / R) * R;
-        uint32_t v = 0;
-        if (lane < R) v = arr[base + lane];
-        before = __reduce_add_sync(kFull, lane < ridx ? v : 0u);
-        tot = __reduce_add_sync(kFull, v);
-        m = __reduce_max_sync(kFull, v);
+__device__ __forceinline__ void group_publish(uint32_t* arr, int warp, int lane, int ridx, uint32_t v) {
+    if (R <= kW) {
+        if (lane == 0) arr[warp] = v;
     } else {
         constexpr int C = R / kW;
-        cg::cluster_group cluster = cg::this_cluster();
-        uint32_t b = 0, t = 0, mm = 0;
-        if (lane < kW) {
-#pragma unroll
-            for (int c = 0; c < C; ++c) {
-                const uint32_t* remote = cluster.map_shared_rank(arr, c);
-                const uint32_t v = remote[lane];
-                t += v;
-                mm = max(mm, v);
-                if (c * kW + lane < ridx) b += v;
-            }
-        }
-        before = __reduce_add_sync(kFull, b);
-        tot = __reduce_add_sync(kFull, t);
-        m = __reduce_max_sync(kFull, mm);
+        if (lane < C) cg::this_cluster().map_shared_rank(arr, lane)[ridx] = v;
     }
-    sum_before = before;
-    total = tot;
-    mx = m;
+}
+
+template <int R>
+__device__ __forceinline__ void group_reduce(const uint32_t* arr, int warp, int lane, int ridx, uint32_t& before,
+                                             uint32_t& total, uint32_t& mx) {
+    if (R == 1) {
+        before = 0;
+        total = mx = arr[warp];
+        return;
+    }
+    const int base = R <= kW ? (warp / R) * R : 0;
+    uint32_t b = 0, t = 0, m = 0;
+#pragma unroll
+    for (int i = 0; i < (R + 31) / 32; ++i) {
+        const int j = i * 32 + lane;
+        if (j < R) {
+            const uint32_t v = arr[base + j];
+            t += v;
+            m = max(m, v);
+            if (j < ridx) b += v;
+        }
+    }
+    before = __reduce_add_sync(kFull, b);
+    total = __reduce_add_sync(kFull, t);
+    mx = __reduce_max_sync(kFull, m);
 }
 
 __device__ __forceinline__ void sts32(uint32_t a, uint32_t v) { asm volatile("st.shared.b32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
@@ -258,20 +260,19 @@ __device__ __forceinline__ void store_units9(uint32_t a, uint32_t w0, uint32_t w
 // Copy the staged 16-bit units [lo, hi) (indices in the group's output stream) to global memory.
 // Unit i lives at shared address sbase + 2*i and at global address gout + 2*i; both are congruent
 // mod 16, so whole vectors move with one 128-bit load + one 128-bit store; the ragged first/last
-// vectors (shared with the neighbouring regions' streams) are written in 2-byte pieces.
+// vectors (shared with the neighbouring regions' streams) are written in 2-byte pieces, one per lane.
 __device__ __forceinline__ void flush_region(uint32_t sbase, uint8_t* gout, int lo, int hi, int lane) {
     if (hi <= lo) return;
-    const int v0 = lo >> 3, v1 = (hi + 7) >> 3;
-    for (int v = v0 + lane; v < v1; v += 32) {
-        const int a = v << 3, b = a + 8;
-        if (a >= lo && b <= hi) {
-            stg128(gout + ((size_t)v << 4), lds128s(sbase + ((uint32_t)v << 4)));
-        } else {
-            const int s = max(a, lo), e = min(b, hi);
-            for (int i = s; i < e; ++i)
-                *reinterpret_cast<uint16_t*>(gout + ((size_t)i << 1)) = (uint16_t)lds16s(sbase + ((uint32_t)i << 1));
-        }
-    }
+    const int lo_al = min((lo + 7) & ~7, hi);
+    const int hi_al = max(hi & ~7, lo_al);
+    int i = lo + lane;
+    if (i < lo_al) *reinterpret_cast<uint16_t*>(gout + ((size_t)i << 1)) = (uint16_t)lds16s(sbase + ((uint32_t)i << 1));
+    i = hi_al + lane;
+    if (i < hi) *reinterpret_cast<uint16_t*>(gout + ((size_t)i << 1)) = (uint16_t)lds16s(sbase + ((uint32_t)i << 1));
+    const int nv = (hi_al - lo_al) >> 3;
+    uint32_t sa = sbase + 2u * (uint32_t)lo_al + 16u * (uint32_t)lane;
+    uint8_t* ga = gout + 2 * (size_t)lo_al + 16 * (size_t)lane;
+    for (int v = lane; v < nv; v += 32, sa += 512u, ga += 512) stg128(ga, lds128s(sa));
 }
 
 // ===================================================================================
@@ -328,15 +329,14 @@ compress_fast_kernel(const T* __restrict__ in, uint32_t n_groups, uint8_t* __res
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(kFull, m, o));
     }
-    if (lane == 0) sm.xa[warp] = __float_as_uint(m);   // non-negative floats order like their bit patterns
+    group_publish<R>(sm.xa, warp, lane, ridx, __float_as_uint(m));   // non-negative floats order like their bits
     group_sync<R>();
     uint32_t t0, t1, gmax_bits;
-    group_gather<R>(sm.xa, warp, lane, ridx, t0, t1, gmax_bits);
+    group_reduce<R>(sm.xa, warp, lane, ridx, t0, t1, gmax_bits);
     const float gmax = __uint_as_float(gmax_bits);
     const float s = scale_from_max(gmax);
     const bool fast = fast_quant_ok<T>(gmax);
     const float r = __frcp_rn(s);
-    group_sync<R>();   // xa is reused below
 
     // ---- 2a. quantise, delta, run-boundary flags; results parked in the lane's own 16-byte slot ----
     // slot = { dsh0, dsh1 : deltas shifted by one element (byte j = delta[pos_j - 1]),
@@ -399,15 +399,13 @@ compress_fast_kernel(const T* __restrict__ in, uint32_t n_groups, uint8_t* __res
         heads = __reduce_add_sync(kFull, heads);
     }
     cplx = __any_sync(kFull, cplx);
-    if (lane == 0) {
-        sm.xa[warp] = active ? heads : 0u;
-        sm.xb[warp] = (active && cplx) ? 1u : 0u;
-    }
+    // one word per region: head count (<= 2048) in the low 20 bits, "needs the generic kernel" above
+    group_publish<R>(sm.xc, warp, lane, ridx, active ? (heads | (cplx ? (1u << 20) : 0u)) : 0u);
     group_sync<R>();
-    uint32_t h_before, h_total, any_cplx;
-    group_gather<R>(sm.xa, warp, lane, ridx, h_before, h_total, t0);
-    group_gather<R>(sm.xb, warp, lane, ridx, t0, t1, any_cplx);
-    if (C > 1) cg::this_cluster().sync();   // peers may still be reading this CTA's exchange words
+    uint32_t h_before, h_total;
+    group_reduce<R>(sm.xc, warp, lane, ridx, h_before, h_total, t0);
+    const bool any_cplx = (h_total >> 20) != 0;
+    h_before &= 0xfffffu;
     if (!active) return;
     if (ridx == 0 && lane == 0) needs_generic[g] = any_cplx ? 1u : 0u;
     if (any_cplx) return;
@@ -421,7 +419,9 @@ compress_fast_kernel(const T* __restrict__ in, uint32_t n_groups, uint8_t* __res
     int pidx = (int)h_before - 1;
     const int p0 = max(pidx, 0);                         // first real pair index of this region
     const uint32_t sbase = reg_s - 16u - 2u * (uint32_t)(p0 & ~7);   // pair i is staged at sbase + 2*i
-    uint32_t carry_nz0 = halo_nz0, carry_nz1 = halo_nz1;
+    // tail = distance from the end of a lane chunk back to its last head; the next chunk's first
+    // pair closes a run of that length (+ its own offset)
+    uint32_t carry_tail = halo_nz1 ? ((uint32_t)__clz((int)halo_nz1) >> 3) + 1u : ((uint32_t)__clz((int)halo_nz0) >> 3) + 5u;
     const int src_lane = (lane + 31) & 31;
 #pragma unroll 1
     for (int k = 0; k < kIters; ++k) {
@@ -429,12 +429,10 @@ compress_fast_kernel(const T* __restrict__ in, uint32_t n_groups, uint8_t* __res
         __syncwarp();   // every lane has read its slot before any pair of this iteration lands on it
         const uint32_t dsh0 = st.x, dsh1 = st.y;
         const uint32_t nz0 = st.z, nz1 = st.w;
-        const uint32_t rn0 = __shfl_sync(kFull, nz0, src_lane), rn1 = __shfl_sync(kFull, nz1, src_lane);
-        const uint32_t pnz0 = lane == 0 ? carry_nz0 : rn0, pnz1 = lane == 0 ? carry_nz1 : rn1;
-        carry_nz0 = rn0;
-        carry_nz1 = rn1;
-        // distance back to the previous head (the previous lane chunk has at least one on this path)
-        const uint32_t lf = pnz1 ? ((uint32_t)__clz((int)pnz1) >> 3) + 1u : ((uint32_t)__clz((int)pnz0) >> 3) + 5u;
+        const uint32_t tail = nz1 ? ((uint32_t)__clz((int)nz1) >> 3) + 1u : ((uint32_t)__clz((int)nz0) >> 3) + 5u;
+        const uint32_t rt = __shfl_sync(kFull, tail, src_lane);
+        const uint32_t lf = lane == 0 ? carry_tail : rt;   // distance back to the previous head
+        carry_tail = rt;
         const uint32_t hw0 = ~nz0 & 0x80808080u, hw1 = ~nz1 & 0x80808080u;
         const int nhole = __popc(hw0) + __popc(hw1);
         if (!__any_sync(kFull, nhole > 1)) {
@@ -490,8 +488,7 @@ compress_fast_kernel(const T* __restrict__ in, uint32_t n_groups, uint8_t* __res
     if (ridx == R - 1) {
         // the run still open at the end of the group (cache_engine.cpp:235-236)
         if (lane == 0) {
-            const uint32_t cnt = carry_nz1 ? ((uint32_t)__clz((int)carry_nz1) >> 3) + 1u
-                                           : ((uint32_t)__clz((int)carry_nz0) >> 3) + 5u;
+            const uint32_t cnt = carry_tail;
             sts16(sbase + 2u * (uint32_t)pidx, (carry_d1 >> 24) | (cnt << 8));
             scales[g] = s;
             comp_bytes[g] = 2u * (uint32_t)(pidx + 1);
@@ -594,15 +591,12 @@ decompress_fast_kernel(const uint8_t* __restrict__ payload, size_t slot_bytes, c
         // in-place staging needs the output stream to stay within kPadBytes of the read position
         if (csum - nnz > (uint32_t)(kPadBytes / 2 - 8)) cplx = true;
     }
-    if (lane == 0) {
-        sm.xa[warp] = min(csum, G + 1u);   // saturate: sums stay < 2^32 and "> G" is still detectable
-        sm.xb[warp] = ssum | (cplx ? (1u << 24) : 0u);
-    }
+    group_publish<R>(sm.xa, warp, lane, ridx, min(csum, G + 1u));   // saturated: sums stay < 2^32, "> G" still shows
+    group_publish<R>(sm.xb, warp, lane, ridx, ssum | (cplx ? (1u << 24) : 0u));
     group_sync<R>();
     uint32_t e_before, e_total, q_before, xb_total, t0;
-    group_gather<R>(sm.xa, warp, lane, ridx, e_before, e_total, t0);
-    group_gather<R>(sm.xb, warp, lane, ridx, q_before, xb_total, t0);
-    if (C > 1) cg::this_cluster().sync();
+    group_reduce<R>(sm.xa, warp, lane, ridx, e_before, e_total, t0);
+    group_reduce<R>(sm.xb, warp, lane, ridx, q_before, xb_total, t0);
     if (!active) return;
     const bool any_cplx = (xb_total >> 24) != 0 || e_total > G;   // output longer than the group: generic kernel clips
     if (ridx == 0 && lane == 0) {
