@@ -279,7 +279,7 @@ __device__ __forceinline__ void flush_region(uint32_t sbase, uint8_t* gout, int 
 // compress
 // ===================================================================================
 template <typename T, int R>
-__global__ void __launch_bounds__(kThreadsF, 2)
+__global__ void __launch_bounds__(kThreadsF, 3)
 compress_fast_kernel(const T* __restrict__ in, uint32_t n_groups, uint8_t* __restrict__ payload, size_t slot_bytes,
                      float* __restrict__ scales, uint32_t* __restrict__ comp_bytes,
                      uint32_t* __restrict__ needs_generic) {
@@ -503,7 +503,7 @@ compress_fast_kernel(const T* __restrict__ in, uint32_t n_groups, uint8_t* __res
 // decompress
 // ===================================================================================
 template <typename T, int R>
-__global__ void __launch_bounds__(kThreadsF, 2)
+__global__ void __launch_bounds__(kThreadsF, 3)
 decompress_fast_kernel(const uint8_t* __restrict__ payload, size_t slot_bytes, const float* __restrict__ scales,
                        const uint32_t* __restrict__ comp_bytes, uint32_t n_groups, T* __restrict__ out,
                        uint32_t* __restrict__ out_elems, uint32_t* __restrict__ needs_generic) {
