@@ -69,6 +69,10 @@ def lib() -> C.CDLL:
     L.speckv_ext_host_alloc.argtypes = [sz]; L.speckv_ext_host_alloc.restype = vp
     L.speckv_ext_host_free.argtypes = [vp]; L.speckv_ext_host_free.restype = None
     L.speckv_ext_translate.argtypes = [vp, vp, sz, vp]; L.speckv_ext_translate.restype = C.c_int
+    L.speckv_ext_page_table_export.argtypes = [C.c_uint64, vp, sz, C.POINTER(sz), vp]
+    L.speckv_ext_page_table_export.restype = C.c_int
+    L.speckv_ext_page_lookup.argtypes = [vp, sz, C.c_uint64, vp, vp, vp, sz, vp]
+    L.speckv_ext_page_lookup.restype = C.c_int
     L.speckv_ext_get_stats.argtypes = [C.POINTER(Stats)]; L.speckv_ext_get_stats.restype = None
     L.speckv_ext_reset_stats.argtypes = []; L.speckv_ext_reset_stats.restype = None
     _LIB = L

@@ -16,6 +16,7 @@
 
 #include "../../include/speckv_ext.h"
 #include "device_ctx.h"
+#include "page_lookup.h"
 #include "page_table.h"
 
 namespace speckv {
@@ -147,6 +148,34 @@ speckv_status_t speckv_set_compression_scheme(speckv_comp_scheme_t scheme) {
     if ((int)scheme < 0 || (int)scheme > 2) return SPECKV_ERR_DRIVER;  // the device has no such mode
     g_rt->scheme = (int)scheme;
     return SPECKV_OK;
+}
+
+speckv_status_t speckv_ext_page_table_export(speckv_handle_t handle, speckv_page_t* d_pages, size_t capacity,
+                                             size_t* out_count, void* cuda_stream) {
+    std::lock_guard<std::mutex> lock(g_mutex);
+    if (!g_rt || !out_count) return SPECKV_ERR_INVAL;
+    if (g_rt->cuda_device < 0) return SPECKV_ERR_DRIVER;
+    KvAllocation* a = g_rt->table.find(handle);
+    if (!a) return SPECKV_ERR_GENERAL;
+    *out_count = a->pages.size();
+    const size_t n = a->pages.size() < capacity ? a->pages.size() : capacity;
+    if (n == 0) return SPECKV_OK;
+    if (!d_pages) return SPECKV_ERR_INVAL;
+    static_assert(sizeof(KvPage) == sizeof(speckv_page_t) && sizeof(KvPage) == 24, "page record layout");
+    cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+    cudaError_t e = cudaMemcpyAsync(d_pages, a->pages.data(), n * sizeof(KvPage), cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);   // the host vector may change after we return
+    return status_of(e);
+}
+
+speckv_status_t speckv_ext_page_lookup(const speckv_page_t* d_pages, size_t num_pages, uint64_t va_base,
+                                       const uint64_t* d_va, uint64_t* d_pa, uint32_t* d_flags, size_t n,
+                                       void* cuda_stream) {
+    if (device_count() <= 0) return SPECKV_ERR_DRIVER;
+    if (n == 0) return SPECKV_OK;
+    if (!d_va || !d_pa || (!d_pages && num_pages)) return SPECKV_ERR_INVAL;
+    return status_of(launch_page_lookup(reinterpret_cast<const KvPageDev*>(d_pages), num_pages, va_base, d_va, d_pa,
+                                        d_flags, n, current_sm_count(), static_cast<cudaStream_t>(cuda_stream)));
 }
 
 }  // extern "C"

@@ -101,6 +101,33 @@ SPECKV_API void speckv_ext_host_free(void* p);
  * the value, only hit/miss counts. */
 SPECKV_API speckv_status_t speckv_ext_translate(const uint64_t* d_va, uint64_t* d_pa, size_t n, void* cuda_stream);
 
+/* ---- page table --------------------------------------------------------------- */
+/* One page-table entry: identical to the reference's KvPageHandle
+ * (host/include/speckv_allocator.hpp:22-27): flags bit0 = in L1, bit1 = in L2, bit2 = compressed. */
+typedef struct {
+    uint64_t virt_page_id;   /* (handle << 32) | (page << 12)                 speckv_allocator.cpp:24 */
+    uint64_t phys_page_id;   /* 0x4000000000 + (handle << 20) + (page << 12)  speckv_allocator.cpp:25 */
+    uint32_t page_size;      /* 4096 */
+    uint32_t flags;
+} speckv_page_t;
+
+/* Copies the page table of `handle` (speckv_alloc) into the device array d_pages (capacity
+ * entries) so that lookups can run on the GPU; *out_count receives the number of pages of the
+ * handle (copied entries = min(count, capacity)).  Needs speckv_init; unknown handle ->
+ * SPECKV_ERR_GENERAL. */
+SPECKV_API speckv_status_t speckv_ext_page_table_export(speckv_handle_t handle, speckv_page_t* d_pages,
+                                                        size_t capacity, size_t* out_count, void* cuda_stream);
+
+/* Batched page-table lookup (SpeckvAllocator::access address arithmetic + is_in_l1_or_l2,
+ * speckv_allocator.cpp:54-74,105-113; same form as CXLMemoryManager::translate_virtual_to_physical,
+ * cxl_memory_manager.cpp:106-117): for each va, entry = d_pages[(va - va_base) >> 12];
+ * d_pa[i] = entry.phys_page_id + (va & 0xFFF), d_flags[i] = entry.flags (d_flags may be NULL);
+ * outside the table, or entry.virt_page_id != (va & ~0xFFF): d_pa[i] = 0, d_flags[i] = 0.
+ * For a speckv_alloc handle h: va_base = h << 32 and va = va_base + byte offset. */
+SPECKV_API speckv_status_t speckv_ext_page_lookup(const speckv_page_t* d_pages, size_t num_pages, uint64_t va_base,
+                                                  const uint64_t* d_va, uint64_t* d_pa, uint32_t* d_flags,
+                                                  size_t n, void* cuda_stream);
+
 /* ---- statistics (EngineStatistics, cache_engine.h:65-72) --------------------- */
 typedef struct {
     uint64_t total_compressions;     /* groups compressed   */

@@ -323,3 +323,51 @@ def test_full_size_properties_llama70b_layer():
         s, p = check_group_against_oracle(c, g, xs[g].cpu().numpy().astype(np.float32))
         want = Port.decompress(s, p, G).astype(np.float16)
         assert np.array_equal(out_bits(y[g]), want.view(np.uint16))
+
+
+def test_page_table_lookup_on_device(golden):
+    """speckv_ext_page_table_export + speckv_ext_page_lookup against the reference's recorded
+    speckv_access results (tests/golden, host C API with /dev/null) and the oracle formulas."""
+    import cxl_speckv_b200 as pkg
+    L = pkg.lib()
+    assert L.speckv_init(b"cuda:0") == 0
+    try:
+        sizes = (1 << 20, 1 << 20, 5000, 3 << 20, 1)
+        handles = []
+        for sz in sizes:
+            h = C.c_uint64()
+            assert L.speckv_alloc(sz, None, C.byref(h)) == 0
+            handles.append(h.value)
+        assert handles == [1, 2, 3, 4, 5]
+        ptr = C.c_void_p()
+        assert L.speckv_access(4, 8192 + 5, 4, C.byref(ptr)) == 0           # marks page 2 of handle 4 as L2
+        for h, sz in zip(handles, sizes):
+            npages = (sz + 4095) // 4096
+            pages = torch.zeros(npages * 3, dtype=torch.int64, device=DEV)   # 24-byte records
+            cnt = C.c_size_t()
+            assert L.speckv_ext_page_table_export(h, pages.data_ptr(), npages, C.byref(cnt), None) == 0
+            assert cnt.value == npages
+            rec = pages.cpu().numpy().view(np.uint64).reshape(npages, 3)
+            assert all(int(rec[i, 0]) == Port.lib().oracle_virt_page_id(h, i) for i in range(npages))
+            assert all(int(rec[i, 1]) == Port.lib().oracle_phys_page_id(h, i) for i in range(npages))
+            offs = np.array([a[2] for a in golden["meta"]["capi"]["accesses"] if a[0] == h], dtype=np.uint64)
+            rng = np.random.default_rng(h)
+            offs = np.concatenate([offs, rng.integers(0, npages * 4096 + 9000, 5000, dtype=np.uint64)])
+            va = torch.from_numpy(((np.uint64(h) << np.uint64(32)) + offs).view(np.int64)).to(DEV)
+            pa = torch.empty_like(va)
+            fl = torch.empty(va.numel(), dtype=torch.int32, device=DEV)
+            st = L.speckv_ext_page_lookup(pages.data_ptr(), npages, h << 32, va.data_ptr(), pa.data_ptr(), fl.data_ptr(),
+                                          va.numel(), None)
+            assert st == 0
+            want = np.array([Port.access_addr(h, sz, int(o)) for o in offs], dtype=np.uint64)
+            assert np.array_equal(pa.cpu().numpy().view(np.uint64), want)
+            flags = fl.cpu().numpy()
+            if h == 4:
+                assert (flags[(offs >= 8192) & (offs < 12288)] == 2).all() and (flags[offs < 8192] == 0).all()
+            else:
+                assert (flags == 0).all()
+        # golden: every recorded (handle, offset) -> address / failure
+        for h, sz, off, rc, addr in golden["meta"]["capi"]["accesses"]:
+            assert Port.access_addr(h, sz, off) == (addr if rc == 0 else 0)
+    finally:
+        L.speckv_finalize()

@@ -1,0 +1,64 @@
+"""CPU, world_size 2 over gloo: the N > 1 host logic of the codec path -- layer sharding and
+the per-step all-gather of page-table metadata (the only collective in the design)."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from cxl_speckv_b200 import sharding
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, n_layers, gpl, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        layers, n_groups = sharding.shard_groups(n_layers, gpl, world, rank)
+        # synthetic per-group compressed sizes that encode (rank, layer, block) so the gather can be checked
+        comp = torch.empty(n_groups, dtype=torch.int32)
+        for li, layer in enumerate(layers):
+            for b in range(gpl):
+                comp[li * gpl + b] = 1_000_000 * rank + 1000 * layer + b
+        # equal table lengths are required by all_gather_into_tensor: pad to the max over ranks
+        n_max = max(len(sharding.shard_layers(n_layers, world, r)) for r in range(world)) * gpl
+        padded = torch.full((n_max,), -1, dtype=torch.int32)
+        padded[:n_groups] = comp
+        table = sharding.gather_page_metadata(padded)
+        ok = table.shape == (world, n_max)
+        for layer in range(n_layers):
+            for b in (0, gpl - 1):
+                r, idx = sharding.global_block_location(layer, b, gpl, world)
+                ok &= int(table[r, idx]) == 1_000_000 * r + 1000 * layer + b
+        ok &= sorted(sum((sharding.shard_layers(n_layers, world, r) for r in range(world)), [])) == list(range(n_layers))
+        ret[rank] = bool(ok)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_layers,gpl", [(80, 128), (5, 3)])
+def test_layer_sharding_and_metadata_allgather(n_layers, gpl):
+    world = 2
+    port = _free_port()
+    with mp.Manager() as mgr:
+        ret = mgr.dict()
+        mp.spawn(_worker, args=(world, port, n_layers, gpl, ret), nprocs=world, join=True)
+        assert dict(ret) == {0: True, 1: True}
+
+
+def test_single_process_paths():
+    assert sharding.shard_layers(80, 8, 3) == list(range(3, 80, 8))
+    assert sharding.owner_of(17, 4) == 1
+    assert sharding.global_block_location(17, 5, 128, 4) == (1, 4 * 128 + 5)
+    t = torch.arange(6, dtype=torch.int32)
+    assert torch.equal(sharding.gather_page_metadata(t), t.view(1, 6))
+    with pytest.raises(ValueError):
+        sharding.shard_layers(4, 2, 2)
