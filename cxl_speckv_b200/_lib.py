@@ -62,6 +62,8 @@ def lib() -> C.CDLL:
     L.speckv_ext_compress.restype = C.c_int
     L.speckv_ext_decompress.argtypes = [vp, sz, vp, vp, sz, sz, C.c_int, vp, vp, C.c_int, vp]
     L.speckv_ext_decompress.restype = C.c_int
+    L.speckv_ext_decompress_indexed.argtypes = [vp, sz, vp, vp, vp, sz, sz, C.c_int, vp, vp, C.c_int, vp]
+    L.speckv_ext_decompress_indexed.restype = C.c_int
     L.speckv_ext_compress_host.argtypes = [vp, C.c_int, sz, sz, vp, sz, vp, vp, C.c_int]
     L.speckv_ext_compress_host.restype = C.c_int
     L.speckv_ext_decompress_host.argtypes = [vp, sz, vp, vp, sz, sz, C.c_int, vp, vp, C.c_int]
@@ -73,6 +75,11 @@ def lib() -> C.CDLL:
     L.speckv_ext_page_table_export.restype = C.c_int
     L.speckv_ext_page_lookup.argtypes = [vp, sz, C.c_uint64, vp, vp, vp, sz, vp]
     L.speckv_ext_page_lookup.restype = C.c_int
+    L.speckv_ext_predictor_load.argtypes = [vp, vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32]
+    L.speckv_ext_predictor_load.restype = C.c_int
+    L.speckv_ext_predictor_unload.argtypes = []; L.speckv_ext_predictor_unload.restype = None
+    L.speckv_ext_prefetch_score.argtypes = [vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, vp, vp, vp, vp]
+    L.speckv_ext_prefetch_score.restype = C.c_int
     L.speckv_ext_get_stats.argtypes = [C.POINTER(Stats)]; L.speckv_ext_get_stats.restype = None
     L.speckv_ext_reset_stats.argtypes = []; L.speckv_ext_reset_stats.restype = None
     _LIB = L

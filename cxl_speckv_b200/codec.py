@@ -78,6 +78,22 @@ def decompress(c: CompressedKV, out: Optional[torch.Tensor] = None, out_elems: O
     return out
 
 
+def decompress_indexed(c: CompressedKV, block_index: torch.Tensor, out: Optional[torch.Tensor] = None,
+                       dtype: Optional[torch.dtype] = None) -> torch.Tensor:
+    """Decompress only the stored blocks listed in block_index (int32 CUDA tensor)."""
+    dtype = dtype or c.dtype
+    block_index = block_index.to(torch.int32).contiguous()
+    n = block_index.numel()
+    if out is None:
+        out = torch.empty((n, c.group_elems), dtype=dtype, device=c.payload.device)
+    with torch.cuda.device(c.payload.device):
+        st = lib().speckv_ext_decompress_indexed(c.payload.data_ptr(), c.payload.shape[1], c.scales.data_ptr(),
+                                                 c.comp_bytes.data_ptr(), block_index.data_ptr(), n, c.group_elems,
+                                                 _DTYPES[dtype], out.data_ptr(), None, c.scheme, _stream())
+    check(st, "speckv_ext_decompress_indexed")
+    return out
+
+
 def translate(va: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Batched FPGACacheEngine::translate_address over an int64 tensor of (uint64) addresses."""
     if va.dtype != torch.int64 or not va.is_cuda:

@@ -14,6 +14,7 @@ struct CodecArgs {
     float* scales = nullptr;
     uint32_t* comp_bytes = nullptr;
     uint32_t* out_elems = nullptr;   // decompress, optional
+    const uint32_t* src_index = nullptr;  // decompress, optional: output group i decodes payload group src_index[i]
     size_t slot_bytes = 0;
     uint32_t group_elems = 0;
     uint32_t n_groups = 0;

@@ -506,7 +506,8 @@ template <typename T, int R>
 __global__ void __launch_bounds__(kThreadsF, 3)
 decompress_fast_kernel(const uint8_t* __restrict__ payload, size_t slot_bytes, const float* __restrict__ scales,
                        const uint32_t* __restrict__ comp_bytes, uint32_t n_groups, T* __restrict__ out,
-                       uint32_t* __restrict__ out_elems, uint32_t* __restrict__ needs_generic) {
+                       uint32_t* __restrict__ out_elems, uint32_t* __restrict__ needs_generic,
+                       const uint32_t* __restrict__ src_index) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     FastSmem& sm = *reinterpret_cast<FastSmem*>(smem_raw);
     constexpr int C = R > kW ? R / kW : 1;
@@ -534,17 +535,19 @@ decompress_fast_kernel(const uint8_t* __restrict__ payload, size_t slot_bytes, c
     uint32_t np = 0;
     float s = 1.0f;
     bool cplx = false;
+    uint32_t gi = g;   // stored block decoded by output group g
     if (active) {
-        const uint32_t cb = comp_bytes[g];
+        if (src_index) gi = src_index[g];
+        const uint32_t cb = comp_bytes[gi];
         uint32_t npairs = cb >> 1;                            // a trailing odd byte is ignored (:245-247)
         if ((size_t)cb > slot_bytes) cplx = true;             // malformed: leave it to the generic kernel's clamping
         npairs = min(npairs, (uint32_t)(R * kRegion));
         const uint32_t first = (uint32_t)ridx * kRegion;
         np = npairs > first ? min(npairs - first, (uint32_t)kRegion) : 0u;
-        s = scales[g];
+        s = scales[gi];
         cplx |= scale_is_special(s);
     }
-    const uint8_t* rp = payload + (size_t)g * slot_bytes + (size_t)ridx * kRegionBytes;
+    const uint8_t* rp = payload + (size_t)gi * slot_bytes + (size_t)ridx * kRegionBytes;
 
     if (lane == 0) {
         mbar_init(mb, 1);
@@ -737,7 +740,8 @@ cudaError_t decompress_fast_t(int R, const CodecArgs& a, uint32_t* flags, cudaSt
     uint32_t n = a.n_groups;
     T* out = static_cast<T*>(a.out);
     uint32_t* oe = a.out_elems;
-    void* args[] = {&pay, &sb, &sc, &cb, &n, &out, &oe, &flags};
+    const uint32_t* si = a.src_index;
+    void* args[] = {&pay, &sb, &sc, &cb, &n, &out, &oe, &flags, &si};
     switch (R) {
 #define SPECKV_CASE(RR) case RR: return launch_clustered(decompress_fast_kernel<T, RR>, RR, n, st, args);
         SPECKV_CASE(1) SPECKV_CASE(2) SPECKV_CASE(4) SPECKV_CASE(8) SPECKV_CASE(16) SPECKV_CASE(32) SPECKV_CASE(64) SPECKV_CASE(128)

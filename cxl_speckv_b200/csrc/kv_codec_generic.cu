@@ -278,7 +278,8 @@ __global__ void __launch_bounds__(kThreads)
 decompress_rle_generic_kernel(const uint8_t* __restrict__ payload, size_t slot_bytes,
                               const float* __restrict__ scales, const uint32_t* __restrict__ comp_bytes,
                               uint32_t G, uint32_t n_groups, T* __restrict__ out,
-                              uint32_t* __restrict__ out_elems, const uint32_t* __restrict__ only_flagged) {
+                              uint32_t* __restrict__ out_elems, const uint32_t* __restrict__ only_flagged,
+                              const uint32_t* __restrict__ src_index) {
     constexpr int V = 16 / sizeof(T);
     __shared__ __align__(16) T stage[kWindow + V];
     __shared__ int wbuf[kWarps];
@@ -286,10 +287,11 @@ decompress_rle_generic_kernel(const uint8_t* __restrict__ payload, size_t slot_b
 
     for (uint32_t g = blockIdx.x; g < n_groups; g += gridDim.x) {
         if (only_flagged && !only_flagged[g]) continue;   // second pass after the tuned kernel
-        const uint8_t* gp = payload + (size_t)g * slot_bytes;
-        uint32_t npairs = comp_bytes[g] >> 1;  // a trailing odd byte is ignored (:245-247)
+        const uint32_t gi = src_index ? src_index[g] : g; // which stored block this output group decodes
+        const uint8_t* gp = payload + (size_t)gi * slot_bytes;
+        uint32_t npairs = comp_bytes[gi] >> 1;  // a trailing odd byte is ignored (:245-247)
         npairs = min(npairs, (uint32_t)(slot_bytes >> 1));
-        const float s = scales[g];
+        const float s = scales[gi];
         const bool special = scale_is_special(s);
         T* gout = out + (size_t)g * G;
         const bool vec_ok = (reinterpret_cast<uintptr_t>(gout) & 15) == 0;
@@ -413,12 +415,13 @@ __global__ void __launch_bounds__(kThreads)
 decompress_int8_generic_kernel(const uint8_t* __restrict__ payload, size_t slot_bytes,
                                const float* __restrict__ scales, const uint32_t* __restrict__ comp_bytes,
                                uint32_t G, uint32_t n_groups, T* __restrict__ out,
-                               uint32_t* __restrict__ out_elems) {
+                               uint32_t* __restrict__ out_elems, const uint32_t* __restrict__ src_index) {
     const int tid = threadIdx.x;
     for (uint32_t g = blockIdx.x; g < n_groups; g += gridDim.x) {
-        const uint8_t* gp = payload + (size_t)g * slot_bytes;
-        const uint32_t n = min(min(comp_bytes[g], G), (uint32_t)slot_bytes);
-        const float s = scales[g];
+        const uint32_t gi = src_index ? src_index[g] : g;
+        const uint8_t* gp = payload + (size_t)gi * slot_bytes;
+        const uint32_t n = min(min(comp_bytes[gi], G), (uint32_t)slot_bytes);
+        const float s = scales[gi];
         T* gout = out + (size_t)g * G;
         const bool special = scale_is_special(s);
         for (uint32_t i = tid; i < n; i += kThreads)
@@ -441,10 +444,12 @@ passthrough_meta_kernel(uint32_t n_groups, uint32_t bytes, float* __restrict__ s
 __global__ void __launch_bounds__(kThreads)
 passthrough_out_kernel(const uint8_t* __restrict__ payload, size_t slot_bytes,
                        const uint32_t* __restrict__ comp_bytes, uint32_t G, uint32_t n_groups,
-                       uint16_t* __restrict__ out, uint32_t* __restrict__ out_elems) {
+                       uint16_t* __restrict__ out, uint32_t* __restrict__ out_elems,
+                       const uint32_t* __restrict__ src_index) {
     for (uint32_t g = blockIdx.x; g < n_groups; g += gridDim.x) {
-        const uint16_t* gp = reinterpret_cast<const uint16_t*>(payload + (size_t)g * slot_bytes);
-        const uint32_t n = min(min(comp_bytes[g] >> 1, G), (uint32_t)(slot_bytes >> 1));
+        const uint32_t gi = src_index ? src_index[g] : g;
+        const uint16_t* gp = reinterpret_cast<const uint16_t*>(payload + (size_t)gi * slot_bytes);
+        const uint32_t n = min(min(comp_bytes[gi] >> 1, G), (uint32_t)(slot_bytes >> 1));
         for (uint32_t i = threadIdx.x; i < n; i += kThreads) out[(size_t)g * G + i] = gp[i];
         if (threadIdx.x == 0 && out_elems) out_elems[g] = n;
     }
@@ -480,10 +485,11 @@ static cudaError_t launch_decompress_t(const CodecArgs& a, cudaStream_t st, cons
     const int grid = grid_for(a.n_groups, a.sm_count, 8);
     if (a.scheme == 2) {
         decompress_rle_generic_kernel<T><<<grid, kThreads, 0, st>>>(pay, a.slot_bytes, a.scales, a.comp_bytes,
-                                                                    a.group_elems, a.n_groups, out, a.out_elems, only_flagged);
+                                                                    a.group_elems, a.n_groups, out, a.out_elems, only_flagged, a.src_index);
     } else {
         decompress_int8_generic_kernel<T><<<grid, kThreads, 0, st>>>(pay, a.slot_bytes, a.scales, a.comp_bytes,
-                                                                     a.group_elems, a.n_groups, out, a.out_elems);
+                                                                     a.group_elems, a.n_groups, out, a.out_elems,
+                                                                     a.src_index);
     }
     count_launch();
     return cudaGetLastError();
@@ -513,7 +519,7 @@ cudaError_t launch_decompress_generic(const CodecArgs& a, cudaStream_t st, const
     if (a.scheme == 0) {
         passthrough_out_kernel<<<grid_for(a.n_groups, a.sm_count, 8), kThreads, 0, st>>>(
             static_cast<const uint8_t*>(a.payload), a.slot_bytes, a.comp_bytes, a.group_elems, a.n_groups,
-            static_cast<uint16_t*>(a.out), a.out_elems);
+            static_cast<uint16_t*>(a.out), a.out_elems, a.src_index);
         count_launch();
         return cudaGetLastError();
     }

@@ -76,6 +76,16 @@ SPECKV_API speckv_status_t speckv_ext_decompress(const void* d_payload, size_t s
                                       speckv_dtype_t dtype, void* d_out, uint32_t* d_out_elems,
                                       speckv_comp_scheme_t scheme, void* cuda_stream);
 
+/* Decompress a selection of stored blocks: output group i (at d_out + i*group_elems) decodes the
+ * stored block d_block_index[i] of the container.  This is how prefetch requests for predicted
+ * blocks (speckv_ext_prefetch_score) and page fetches are served.  n_requests output groups. */
+SPECKV_API speckv_status_t speckv_ext_decompress_indexed(const void* d_payload, size_t slot_bytes,
+                                              const float* d_scales, const uint32_t* d_comp_bytes,
+                                              const uint32_t* d_block_index, size_t n_requests,
+                                              size_t group_elems, speckv_dtype_t dtype, void* d_out,
+                                              uint32_t* d_out_elems, speckv_comp_scheme_t scheme,
+                                              void* cuda_stream);
+
 /* Same two operations on HOST buffers: chunks are staged through device
  * buffers on internal streams (H2D, kernel, D2H overlapped) and the call
  * returns when the results are in host memory.  Pinned host memory
@@ -127,6 +137,27 @@ SPECKV_API speckv_status_t speckv_ext_page_table_export(speckv_handle_t handle, 
 SPECKV_API speckv_status_t speckv_ext_page_lookup(const speckv_page_t* d_pages, size_t num_pages, uint64_t va_base,
                                                   const uint64_t* d_va, uint64_t* d_pa, uint32_t* d_flags,
                                                   size_t n, void* cuda_stream);
+
+/* ---- speculative prefetch scoring ---------------------------------------------------- */
+/* Installs the predictor's weights on the current device: embedding [vocab][emb_dim] and
+ * output projection [vocab][hidden], fp32, row-major -- the two tables
+ * LSTMPredictor::predict_top_k actually reads (lstm_predictor.cpp:149-188; its per-layer "LSTM"
+ * weights are never used, :116-147).  The reference draws them from rand() (:27-35) and its
+ * load_model() is a stub (:96-99); here they are an explicit input. */
+SPECKV_API speckv_status_t speckv_ext_predictor_load(const float* h_embedding, const float* h_output,
+                                                     uint32_t vocab, uint32_t emb_dim, uint32_t hidden,
+                                                     uint32_t layers, uint32_t history_len);
+SPECKV_API void speckv_ext_predictor_unload(void);
+
+/* LSTMPredictor::predict_top_k + SpeculativePrefetcher::prefetch's request emission for `batch`
+ * sequences at once.  d_tokens: [batch][history_len] token ids, already windowed the way the
+ * reference does it (last history_len tokens, left-padded with 0, lstm_predictor.cpp:46-51).
+ * Outputs, [batch][k] each: predicted token ids, their softmax confidence, and the request
+ * address (req_id << 32) | (layer_id << 16) | (i + 1) (speculative_prefetcher.cpp:153-160; the
+ * reference always passes req_id 0).  k <= 16. */
+SPECKV_API speckv_status_t speckv_ext_prefetch_score(const uint32_t* d_tokens, uint32_t batch, uint32_t k,
+                                                     uint32_t req_id, uint32_t layer_id, uint32_t* d_ids,
+                                                     float* d_conf, uint64_t* d_va, void* cuda_stream);
 
 /* ---- statistics (EngineStatistics, cache_engine.h:65-72) --------------------- */
 typedef struct {
