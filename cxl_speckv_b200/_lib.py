@@ -26,6 +26,13 @@ class Stats(C.Structure):
                 ("bytes_out_decompress", C.c_uint64), ("kernel_launches", C.c_uint64)]
 
 
+class TierStats(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in ("pool_bytes", "used_bytes", "blocks", "bytes_offloaded_raw",
+                                          "bytes_offloaded_stored", "bytes_restored_raw", "bytes_restored_stored",
+                                          "last_offload_stored_bytes", "last_restore_stored_bytes")] + \
+               [("last_offload_ms", C.c_double), ("last_restore_ms", C.c_double)]
+
+
 def lib_path() -> str:
     return os.environ.get("SPECKV_LIB", os.path.join(PKG, "libcxlspeckv.so"))
 
@@ -80,6 +87,12 @@ def lib() -> C.CDLL:
     L.speckv_ext_predictor_unload.argtypes = []; L.speckv_ext_predictor_unload.restype = None
     L.speckv_ext_prefetch_score.argtypes = [vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, vp, vp, vp, vp]
     L.speckv_ext_prefetch_score.restype = C.c_int
+    L.speckv_ext_tier_create.argtypes = [sz, C.POINTER(vp)]; L.speckv_ext_tier_create.restype = C.c_int
+    L.speckv_ext_tier_destroy.argtypes = [vp]; L.speckv_ext_tier_destroy.restype = None
+    L.speckv_ext_tier_offload.argtypes = [vp, vp, C.c_int, sz, sz, vp, vp]; L.speckv_ext_tier_offload.restype = C.c_int
+    L.speckv_ext_tier_restore.argtypes = [vp, vp, sz, sz, C.c_int, vp, vp]; L.speckv_ext_tier_restore.restype = C.c_int
+    L.speckv_ext_tier_drop.argtypes = [vp, vp, sz]; L.speckv_ext_tier_drop.restype = C.c_int
+    L.speckv_ext_tier_get_stats.argtypes = [vp, C.POINTER(TierStats)]; L.speckv_ext_tier_get_stats.restype = None
     L.speckv_ext_get_stats.argtypes = [C.POINTER(Stats)]; L.speckv_ext_get_stats.restype = None
     L.speckv_ext_reset_stats.argtypes = []; L.speckv_ext_reset_stats.restype = None
     _LIB = L

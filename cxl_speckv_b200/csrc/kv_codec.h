@@ -15,6 +15,8 @@ struct CodecArgs {
     uint32_t* comp_bytes = nullptr;
     uint32_t* out_elems = nullptr;   // decompress, optional
     const uint32_t* src_index = nullptr;  // decompress, optional: output group i decodes payload group src_index[i]
+    const uint64_t* slot_offsets = nullptr;  // decompress, optional: block b starts at payload + slot_offsets[b]
+                                             // (16 B aligned, packed container) instead of b * slot_bytes
     size_t slot_bytes = 0;
     uint32_t group_elems = 0;
     uint32_t n_groups = 0;

@@ -507,7 +507,7 @@ __global__ void __launch_bounds__(kThreadsF, 3)
 decompress_fast_kernel(const uint8_t* __restrict__ payload, size_t slot_bytes, const float* __restrict__ scales,
                        const uint32_t* __restrict__ comp_bytes, uint32_t n_groups, T* __restrict__ out,
                        uint32_t* __restrict__ out_elems, uint32_t* __restrict__ needs_generic,
-                       const uint32_t* __restrict__ src_index) {
+                       const uint32_t* __restrict__ src_index, const uint64_t* __restrict__ slot_offsets) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     FastSmem& sm = *reinterpret_cast<FastSmem*>(smem_raw);
     constexpr int C = R > kW ? R / kW : 1;
@@ -547,7 +547,8 @@ decompress_fast_kernel(const uint8_t* __restrict__ payload, size_t slot_bytes, c
         s = scales[gi];
         cplx |= scale_is_special(s);
     }
-    const uint8_t* rp = payload + (size_t)gi * slot_bytes + (size_t)ridx * kRegionBytes;
+    const uint8_t* rp = payload + ((slot_offsets && active) ? (size_t)slot_offsets[gi] : (size_t)gi * slot_bytes) +
+                        (size_t)ridx * kRegionBytes;
 
     if (lane == 0) {
         mbar_init(mb, 1);
@@ -741,7 +742,8 @@ cudaError_t decompress_fast_t(int R, const CodecArgs& a, uint32_t* flags, cudaSt
     T* out = static_cast<T*>(a.out);
     uint32_t* oe = a.out_elems;
     const uint32_t* si = a.src_index;
-    void* args[] = {&pay, &sb, &sc, &cb, &n, &out, &oe, &flags, &si};
+    const uint64_t* so = a.slot_offsets;
+    void* args[] = {&pay, &sb, &sc, &cb, &n, &out, &oe, &flags, &si, &so};
     switch (R) {
 #define SPECKV_CASE(RR) case RR: return launch_clustered(decompress_fast_kernel<T, RR>, RR, n, st, args);
         SPECKV_CASE(1) SPECKV_CASE(2) SPECKV_CASE(4) SPECKV_CASE(8) SPECKV_CASE(16) SPECKV_CASE(32) SPECKV_CASE(64) SPECKV_CASE(128)

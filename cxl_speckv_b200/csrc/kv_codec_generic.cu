@@ -279,7 +279,7 @@ decompress_rle_generic_kernel(const uint8_t* __restrict__ payload, size_t slot_b
                               const float* __restrict__ scales, const uint32_t* __restrict__ comp_bytes,
                               uint32_t G, uint32_t n_groups, T* __restrict__ out,
                               uint32_t* __restrict__ out_elems, const uint32_t* __restrict__ only_flagged,
-                              const uint32_t* __restrict__ src_index) {
+                              const uint32_t* __restrict__ src_index, const uint64_t* __restrict__ slot_offsets) {
     constexpr int V = 16 / sizeof(T);
     __shared__ __align__(16) T stage[kWindow + V];
     __shared__ int wbuf[kWarps];
@@ -288,7 +288,7 @@ decompress_rle_generic_kernel(const uint8_t* __restrict__ payload, size_t slot_b
     for (uint32_t g = blockIdx.x; g < n_groups; g += gridDim.x) {
         if (only_flagged && !only_flagged[g]) continue;   // second pass after the tuned kernel
         const uint32_t gi = src_index ? src_index[g] : g; // which stored block this output group decodes
-        const uint8_t* gp = payload + (size_t)gi * slot_bytes;
+        const uint8_t* gp = payload + (slot_offsets ? (size_t)slot_offsets[gi] : (size_t)gi * slot_bytes);
         uint32_t npairs = comp_bytes[gi] >> 1;  // a trailing odd byte is ignored (:245-247)
         npairs = min(npairs, (uint32_t)(slot_bytes >> 1));
         const float s = scales[gi];
@@ -485,7 +485,8 @@ static cudaError_t launch_decompress_t(const CodecArgs& a, cudaStream_t st, cons
     const int grid = grid_for(a.n_groups, a.sm_count, 8);
     if (a.scheme == 2) {
         decompress_rle_generic_kernel<T><<<grid, kThreads, 0, st>>>(pay, a.slot_bytes, a.scales, a.comp_bytes,
-                                                                    a.group_elems, a.n_groups, out, a.out_elems, only_flagged, a.src_index);
+                                                                    a.group_elems, a.n_groups, out, a.out_elems, only_flagged, a.src_index,
+                                                                    a.slot_offsets);
     } else {
         decompress_int8_generic_kernel<T><<<grid, kThreads, 0, st>>>(pay, a.slot_bytes, a.scales, a.comp_bytes,
                                                                      a.group_elems, a.n_groups, out, a.out_elems,

@@ -1,0 +1,440 @@
+// tier.cu -- the host-DRAM tier standing in for the CXL memory pool (L3 of the reference).
+//
+// Reference behaviour being replaced: a KV page that is in neither L1 nor L2 is fetched from the
+// CXL/FPGA side by one DMA descriptor per 4 KiB page with the COMPRESSED flag (descriptor flags
+// bit1, driver/uapi/speckv_ioctl.h:14; SpeckvAllocator::sync_fetch_page,
+// host/src/speckv_allocator.cpp:115-138; CXLMemoryManager::demote_to_l3 / promote_to_l1,
+// src/cxl_memory/cxl_memory_manager.cpp:130-194) -- in the reference the transfer itself is a
+// simulated ioctl.  Here it is real: offload = compress kernel -> pack kernel (payload bytes of all
+// blocks back to back, 16 B aligned) -> ONE device-to-host copy into a pinned pool on a side
+// stream; restore = ONE host-to-device copy per contiguous pool extent -> decompress straight from
+// the packed stream (per-block byte offsets, no unpack pass).  Chunks are double-buffered so the
+// PCIe copy of chunk i overlaps the codec kernels of chunk i+1.
+#include <algorithm>
+#include <chrono>
+#include <cstring>
+#include <mutex>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/speckv_ext.h"
+#include "device_ctx.h"
+#include "kv_codec.h"
+
+namespace speckv {
+
+namespace {
+
+constexpr int kPackThreads = 256;
+
+// exclusive scan of the 16-byte-rounded payload sizes: one CTA, sequential over tiles of 1024
+__global__ void __launch_bounds__(1024)
+pack_offsets_kernel(const uint32_t* __restrict__ comp_bytes, uint32_t n, uint64_t* __restrict__ offsets,
+                    uint64_t* __restrict__ total) {
+    __shared__ uint64_t warp_sum[32];
+    __shared__ uint64_t carry;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (tid == 0) carry = 0;
+    __syncthreads();
+    for (uint32_t base = 0; base < n; base += 1024) {
+        const uint32_t i = base + tid;
+        const uint64_t v = i < n ? (((uint64_t)comp_bytes[i] + 15u) & ~15ull) : 0ull;
+        uint64_t inc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint64_t t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += t;
+        }
+        if (lane == 31) warp_sum[wid] = inc;
+        __syncthreads();
+        uint64_t before = carry;
+        for (int w = 0; w < wid; ++w) before += warp_sum[w];
+        if (i < n) offsets[i] = before + inc - v;
+        __syncthreads();
+        if (tid == 1023) carry = before + inc;
+        __syncthreads();
+    }
+    if (tid == 0) *total = carry;
+}
+
+// one warp per block: copy its payload (rounded up to 16 B) from the slot into the packed stream
+__global__ void __launch_bounds__(kPackThreads)
+pack_kernel(const uint8_t* __restrict__ slots, size_t slot_bytes, const uint32_t* __restrict__ comp_bytes,
+            const uint64_t* __restrict__ offsets, uint32_t n, uint8_t* __restrict__ packed) {
+    const uint32_t warps_per_cta = kPackThreads / 32;
+    const int lane = threadIdx.x & 31;
+    for (uint32_t g = blockIdx.x * warps_per_cta + (threadIdx.x >> 5); g < n; g += gridDim.x * warps_per_cta) {
+        const uint32_t nvec = (comp_bytes[g] + 15u) >> 4;
+        const uint4* src = reinterpret_cast<const uint4*>(slots + (size_t)g * slot_bytes);
+        uint4* dst = reinterpret_cast<uint4*>(packed + offsets[g]);
+        for (uint32_t v = lane; v < nvec; v += 32) dst[v] = __ldg(src + v);
+    }
+}
+
+struct BlockRec {
+    uint64_t pool_off;
+    uint32_t comp_bytes;
+    float scale;
+    uint32_t group_elems;
+    int dtype;
+};
+
+struct Extent {
+    uint64_t off, len;
+};
+
+}  // namespace
+
+struct Tier {
+    std::mutex mu;
+    int device = -1;
+    uint8_t* pool = nullptr;      // pinned host memory
+    size_t pool_bytes = 0, bump = 0;
+    std::vector<Extent> free_list;                       // sorted by offset, coalesced
+    std::unordered_map<uint64_t, BlockRec> blocks;
+    // device staging, two buffers for chunk double-buffering
+    static constexpr int kBuf = 2;
+    cudaStream_t copy_st[kBuf] = {};
+    cudaEvent_t ev_kernel[kBuf] = {}, ev_copy[kBuf] = {};
+    uint8_t* d_slots[kBuf] = {};
+    uint8_t* d_packed[kBuf] = {};
+    float* d_scales[kBuf] = {};
+    uint32_t* d_comp[kBuf] = {};
+    uint64_t* d_offsets[kBuf] = {};
+    uint64_t* d_total[kBuf] = {};
+    // pinned host mirrors of the small per-chunk metadata
+    float* h_scales[kBuf] = {};
+    uint32_t* h_comp[kBuf] = {};
+    uint64_t* h_offsets[kBuf] = {};
+    uint64_t* h_total[kBuf] = {};
+    size_t cap_groups = 0, cap_slot_bytes = 0;           // per buffer
+    speckv_tier_stats_t stats = {};
+
+    size_t alloc_pool(size_t len) {   // first fit in the free list, else bump; returns SIZE_MAX when full
+        for (size_t i = 0; i < free_list.size(); ++i) {
+            if (free_list[i].len >= len) {
+                const size_t off = free_list[i].off;
+                free_list[i].off += len;
+                free_list[i].len -= len;
+                if (free_list[i].len == 0) free_list.erase(free_list.begin() + i);
+                return off;
+            }
+        }
+        if (bump + len > pool_bytes) return SIZE_MAX;
+        const size_t off = bump;
+        bump += len;
+        return off;
+    }
+    void free_pool(uint64_t off, uint64_t len) {
+        if (len == 0) return;
+        auto it = std::lower_bound(free_list.begin(), free_list.end(), off,
+                                   [](const Extent& e, uint64_t o) { return e.off < o; });
+        it = free_list.insert(it, Extent{off, len});
+        if (it + 1 != free_list.end() && it->off + it->len == (it + 1)->off) {   // merge with the next extent
+            it->len += (it + 1)->len;
+            free_list.erase(it + 1);
+        }
+        if (it != free_list.begin() && (it - 1)->off + (it - 1)->len == it->off) {   // and with the previous one
+            (it - 1)->len += it->len;
+            it = free_list.erase(it) - 1;
+        }
+        if (it->off + it->len == bump) {   // give the tail back to the bump pointer
+            bump = it->off;
+            free_list.erase(it);
+        }
+    }
+    void release_staging() {
+        for (int b = 0; b < kBuf; ++b) {
+            cudaFree(d_slots[b]); cudaFree(d_packed[b]); cudaFree(d_scales[b]); cudaFree(d_comp[b]);
+            cudaFree(d_offsets[b]); cudaFree(d_total[b]);
+            cudaFreeHost(h_scales[b]); cudaFreeHost(h_comp[b]); cudaFreeHost(h_offsets[b]); cudaFreeHost(h_total[b]);
+            d_slots[b] = d_packed[b] = nullptr; d_scales[b] = nullptr; d_comp[b] = nullptr;
+            d_offsets[b] = d_total[b] = nullptr; h_scales[b] = nullptr; h_comp[b] = nullptr;
+            h_offsets[b] = h_total[b] = nullptr;
+        }
+        cap_groups = cap_slot_bytes = 0;
+    }
+    cudaError_t ensure_staging(size_t groups, size_t slot_bytes) {
+        if (groups <= cap_groups && groups * slot_bytes <= cap_slot_bytes) return cudaSuccess;
+        release_staging();
+        cudaError_t e = cudaSuccess;
+        for (int b = 0; b < kBuf && e == cudaSuccess; ++b) {
+            if ((e = cudaMalloc((void**)&d_slots[b], groups * slot_bytes)) != cudaSuccess) break;
+            if ((e = cudaMalloc((void**)&d_packed[b], groups * slot_bytes)) != cudaSuccess) break;
+            if ((e = cudaMalloc((void**)&d_scales[b], groups * 4)) != cudaSuccess) break;
+            if ((e = cudaMalloc((void**)&d_comp[b], groups * 4)) != cudaSuccess) break;
+            if ((e = cudaMalloc((void**)&d_offsets[b], groups * 8)) != cudaSuccess) break;
+            if ((e = cudaMalloc((void**)&d_total[b], 8)) != cudaSuccess) break;
+            if ((e = cudaHostAlloc((void**)&h_scales[b], groups * 4, cudaHostAllocDefault)) != cudaSuccess) break;
+            if ((e = cudaHostAlloc((void**)&h_comp[b], groups * 4, cudaHostAllocDefault)) != cudaSuccess) break;
+            if ((e = cudaHostAlloc((void**)&h_offsets[b], groups * 8, cudaHostAllocDefault)) != cudaSuccess) break;
+            if ((e = cudaHostAlloc((void**)&h_total[b], 8, cudaHostAllocDefault)) != cudaSuccess) break;
+        }
+        if (e != cudaSuccess) {
+            release_staging();
+            return e;
+        }
+        cap_groups = groups;
+        cap_slot_bytes = groups * slot_bytes;
+        return cudaSuccess;
+    }
+};
+
+}  // namespace speckv
+
+using namespace speckv;
+
+struct speckv_tier {
+    Tier t;
+};
+
+static size_t tier_chunk_groups(size_t slot_bytes, size_t n_groups) {
+    const size_t target = 128ull << 20;   // ~128 MiB of payload per chunk
+    size_t c = slot_bytes ? target / slot_bytes : n_groups;
+    if (c < 1) c = 1;
+    return c < n_groups ? c : n_groups;
+}
+
+extern "C" {
+
+speckv_status_t speckv_ext_tier_create(size_t pool_bytes, speckv_tier_t** out_tier) {
+    if (device_count() <= 0) return SPECKV_ERR_DRIVER;
+    if (!out_tier || pool_bytes == 0) return SPECKV_ERR_INVAL;
+    speckv_tier* h = new speckv_tier();
+    Tier& t = h->t;
+    cudaError_t e = cudaGetDevice(&t.device);
+    if (e == cudaSuccess) e = cudaHostAlloc((void**)&t.pool, pool_bytes, cudaHostAllocPortable);
+    for (int b = 0; b < Tier::kBuf && e == cudaSuccess; ++b) {
+        e = cudaStreamCreateWithFlags(&t.copy_st[b], cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&t.ev_kernel[b], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&t.ev_copy[b], cudaEventDisableTiming);
+    }
+    if (e != cudaSuccess) {
+        speckv_ext_tier_destroy(h);
+        return status_of(e);
+    }
+    t.pool_bytes = pool_bytes;
+    t.stats.pool_bytes = pool_bytes;
+    *out_tier = h;
+    return SPECKV_OK;
+}
+
+void speckv_ext_tier_destroy(speckv_tier_t* tier) {
+    if (!tier) return;
+    Tier& t = tier->t;
+    t.release_staging();
+    for (int b = 0; b < Tier::kBuf; ++b) {
+        if (t.copy_st[b]) cudaStreamDestroy(t.copy_st[b]);
+        if (t.ev_kernel[b]) cudaEventDestroy(t.ev_kernel[b]);
+        if (t.ev_copy[b]) cudaEventDestroy(t.ev_copy[b]);
+    }
+    if (t.pool) cudaFreeHost(t.pool);
+    cudaGetLastError();
+    delete tier;
+}
+
+speckv_status_t speckv_ext_tier_offload(speckv_tier_t* tier, const void* d_in, speckv_dtype_t dtype, size_t group_elems,
+                                        size_t n_groups, const uint64_t* h_block_ids, void* cuda_stream) {
+    if (device_count() <= 0) return SPECKV_ERR_DRIVER;
+    if (!tier || !h_block_ids || (!d_in && n_groups) || dtype < 0 || dtype > 2 || group_elems == 0 ||
+        group_elems >= (1ull << 31))
+        return SPECKV_ERR_INVAL;
+    if (n_groups == 0) return SPECKV_OK;
+    Tier& t = tier->t;
+    std::lock_guard<std::mutex> lk(t.mu);
+    const size_t slot = speckv_ext_slot_bytes(group_elems, SPECKV_COMP_INT8_DELTA_RLE);
+    const size_t esz = dtype == SPECKV_DTYPE_F32 ? 4 : 2;
+    const size_t cg = tier_chunk_groups(slot, n_groups);
+    cudaError_t e = t.ensure_staging(cg, slot);
+    if (e != cudaSuccess) return status_of(e);
+    cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+    const auto t0 = std::chrono::steady_clock::now();
+    uint64_t stored = 0;
+    speckv_status_t rc = SPECKV_OK;
+
+    // finish chunk `c` that was staged in buffer b: wait for its metadata, place it in the pool,
+    // start the payload copy and record the blocks
+    auto finish = [&](size_t g0, size_t ng, int b) -> speckv_status_t {
+        cudaError_t e2 = cudaStreamSynchronize(t.copy_st[b]);   // metadata (offsets, sizes, scales, total) on the host
+        if (e2 != cudaSuccess) return status_of(e2);
+        const uint64_t total = *t.h_total[b];
+        // re-offloading a block id replaces its previous copy
+        for (size_t i = 0; i < ng; ++i) {
+            auto it = t.blocks.find(h_block_ids[g0 + i]);
+            if (it != t.blocks.end()) {
+                t.free_pool(it->second.pool_off, ((uint64_t)it->second.comp_bytes + 15u) & ~15ull);
+                t.stats.used_bytes -= ((uint64_t)it->second.comp_bytes + 15u) & ~15ull;
+                t.blocks.erase(it);
+            }
+        }
+        const size_t off = t.alloc_pool(total);
+        if (off == SIZE_MAX) return SPECKV_ERR_NOMEM;
+        e2 = cudaMemcpyAsync(t.pool + off, t.d_packed[b], total, cudaMemcpyDeviceToHost, t.copy_st[b]);
+        if (e2 != cudaSuccess) return status_of(e2);
+        cudaEventRecord(t.ev_copy[b], t.copy_st[b]);
+        for (size_t i = 0; i < ng; ++i) {
+            BlockRec r;
+            r.pool_off = off + t.h_offsets[b][i];
+            r.comp_bytes = t.h_comp[b][i];
+            r.scale = t.h_scales[b][i];
+            r.group_elems = (uint32_t)group_elems;
+            r.dtype = dtype;
+            t.blocks[h_block_ids[g0 + i]] = r;
+        }
+        stored += total;
+        t.stats.used_bytes += total;
+        return SPECKV_OK;
+    };
+
+    size_t chunk = 0, prev_g0 = 0, prev_ng = 0;
+    int prev_b = -1;
+    for (size_t g0 = 0; g0 < n_groups && rc == SPECKV_OK; g0 += cg, ++chunk) {
+        const size_t ng = std::min(cg, n_groups - g0);
+        const int b = (int)(chunk % Tier::kBuf);
+        // buffer b is free once the payload copy of chunk - 2 has completed
+        cudaStreamWaitEvent(st, t.ev_copy[b], 0);
+        CodecArgs a;
+        a.in = (const char*)d_in + g0 * group_elems * esz;
+        a.payload = t.d_slots[b];
+        a.scales = t.d_scales[b];
+        a.comp_bytes = t.d_comp[b];
+        a.slot_bytes = slot;
+        a.group_elems = (uint32_t)group_elems;
+        a.n_groups = (uint32_t)ng;
+        a.dtype = dtype;
+        a.scheme = SPECKV_COMP_INT8_DELTA_RLE;
+        a.sm_count = current_sm_count();
+        if ((e = launch_compress(a, st)) != cudaSuccess) { rc = status_of(e); break; }
+        pack_offsets_kernel<<<1, 1024, 0, st>>>(t.d_comp[b], (uint32_t)ng, t.d_offsets[b], t.d_total[b]);
+        const int grid = (int)std::min<size_t>((ng + 7) / 8, (size_t)current_sm_count() * 8);
+        pack_kernel<<<grid, kPackThreads, 0, st>>>(t.d_slots[b], slot, t.d_comp[b], t.d_offsets[b], (uint32_t)ng, t.d_packed[b]);
+        count_launch(2);
+        cudaEventRecord(t.ev_kernel[b], st);
+        cudaStreamWaitEvent(t.copy_st[b], t.ev_kernel[b], 0);
+        cudaMemcpyAsync(t.h_total[b], t.d_total[b], 8, cudaMemcpyDeviceToHost, t.copy_st[b]);
+        cudaMemcpyAsync(t.h_offsets[b], t.d_offsets[b], ng * 8, cudaMemcpyDeviceToHost, t.copy_st[b]);
+        cudaMemcpyAsync(t.h_comp[b], t.d_comp[b], ng * 4, cudaMemcpyDeviceToHost, t.copy_st[b]);
+        cudaMemcpyAsync(t.h_scales[b], t.d_scales[b], ng * 4, cudaMemcpyDeviceToHost, t.copy_st[b]);
+        if (prev_b >= 0) rc = finish(prev_g0, prev_ng, prev_b);   // overlaps with this chunk's kernels
+        prev_g0 = g0;
+        prev_ng = ng;
+        prev_b = b;
+    }
+    if (rc == SPECKV_OK && prev_b >= 0) rc = finish(prev_g0, prev_ng, prev_b);
+    for (int b = 0; b < Tier::kBuf; ++b) {
+        cudaError_t e2 = cudaStreamSynchronize(t.copy_st[b]);
+        if (rc == SPECKV_OK && e2 != cudaSuccess) rc = status_of(e2);
+    }
+    if ((e = cudaGetLastError()) != cudaSuccess && rc == SPECKV_OK) rc = status_of(e);
+    const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    if (rc == SPECKV_OK) {
+        t.stats.blocks = t.blocks.size();
+        t.stats.bytes_offloaded_raw += (uint64_t)n_groups * group_elems * esz;
+        t.stats.bytes_offloaded_stored += stored;
+        t.stats.last_offload_ms = ms;
+        t.stats.last_offload_stored_bytes = stored;
+    }
+    return rc;
+}
+
+speckv_status_t speckv_ext_tier_restore(speckv_tier_t* tier, const uint64_t* h_block_ids, size_t n_groups,
+                                        size_t group_elems, speckv_dtype_t dtype, void* d_out, void* cuda_stream) {
+    if (device_count() <= 0) return SPECKV_ERR_DRIVER;
+    if (!tier || !h_block_ids || (!d_out && n_groups) || dtype < 0 || dtype > 2 || group_elems == 0) return SPECKV_ERR_INVAL;
+    if (n_groups == 0) return SPECKV_OK;
+    Tier& t = tier->t;
+    std::lock_guard<std::mutex> lk(t.mu);
+    const size_t slot = speckv_ext_slot_bytes(group_elems, SPECKV_COMP_INT8_DELTA_RLE);
+    const size_t esz = dtype == SPECKV_DTYPE_F32 ? 4 : 2;
+    const size_t cg = tier_chunk_groups(slot, n_groups);
+    cudaError_t e = t.ensure_staging(cg, slot);
+    if (e != cudaSuccess) return status_of(e);
+    cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+    const auto t0 = std::chrono::steady_clock::now();
+    uint64_t moved = 0;
+    size_t chunk = 0;
+    for (size_t g0 = 0; g0 < n_groups; g0 += cg, ++chunk) {
+        const size_t ng = std::min(cg, n_groups - g0);
+        const int b = (int)(chunk % Tier::kBuf);
+        // the pinned metadata mirrors and the staging of buffer b are reusable once its previous
+        // H2D copies and decompress have completed
+        if ((e = cudaStreamSynchronize(t.copy_st[b])) != cudaSuccess) return status_of(e);
+        cudaEventSynchronize(t.ev_kernel[b]);
+        // host: look the blocks up, lay them out back to back in the staging buffer (in request order)
+        // and merge copies whose pool ranges are contiguous
+        uint64_t dst = 0;
+        uint64_t run_src = 0, run_dst = 0, run_len = 0;
+        for (size_t i = 0; i < ng; ++i) {
+            auto it = t.blocks.find(h_block_ids[g0 + i]);
+            if (it == t.blocks.end() || it->second.group_elems != group_elems) return SPECKV_ERR_GENERAL;
+            const BlockRec& r = it->second;
+            const uint64_t len = ((uint64_t)r.comp_bytes + 15u) & ~15ull;
+            t.h_offsets[b][i] = dst;
+            t.h_comp[b][i] = r.comp_bytes;
+            t.h_scales[b][i] = r.scale;
+            if (run_len && r.pool_off == run_src + run_len) {
+                run_len += len;
+            } else {
+                if (run_len) cudaMemcpyAsync(t.d_packed[b] + run_dst, t.pool + run_src, run_len, cudaMemcpyHostToDevice, t.copy_st[b]);
+                run_src = r.pool_off;
+                run_dst = dst;
+                run_len = len;
+            }
+            dst += len;
+        }
+        if (run_len) cudaMemcpyAsync(t.d_packed[b] + run_dst, t.pool + run_src, run_len, cudaMemcpyHostToDevice, t.copy_st[b]);
+        moved += dst;
+        cudaMemcpyAsync(t.d_offsets[b], t.h_offsets[b], ng * 8, cudaMemcpyHostToDevice, t.copy_st[b]);
+        cudaMemcpyAsync(t.d_comp[b], t.h_comp[b], ng * 4, cudaMemcpyHostToDevice, t.copy_st[b]);
+        cudaMemcpyAsync(t.d_scales[b], t.h_scales[b], ng * 4, cudaMemcpyHostToDevice, t.copy_st[b]);
+        cudaEventRecord(t.ev_copy[b], t.copy_st[b]);
+        cudaStreamWaitEvent(st, t.ev_copy[b], 0);
+        CodecArgs a;
+        a.out = (char*)d_out + g0 * group_elems * esz;
+        a.payload = t.d_packed[b];
+        a.scales = t.d_scales[b];
+        a.comp_bytes = t.d_comp[b];
+        a.slot_offsets = t.d_offsets[b];
+        a.slot_bytes = slot;
+        a.group_elems = (uint32_t)group_elems;
+        a.n_groups = (uint32_t)ng;
+        a.dtype = dtype;
+        a.scheme = SPECKV_COMP_INT8_DELTA_RLE;
+        a.sm_count = current_sm_count();
+        if ((e = launch_decompress(a, st)) != cudaSuccess) return status_of(e);
+        cudaEventRecord(t.ev_kernel[b], st);
+    }
+    e = cudaStreamSynchronize(st);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e != cudaSuccess) return status_of(e);
+    const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    t.stats.bytes_restored_raw += (uint64_t)n_groups * group_elems * esz;
+    t.stats.bytes_restored_stored += moved;
+    t.stats.last_restore_ms = ms;
+    t.stats.last_restore_stored_bytes = moved;
+    return SPECKV_OK;
+}
+
+speckv_status_t speckv_ext_tier_drop(speckv_tier_t* tier, const uint64_t* h_block_ids, size_t n) {
+    if (!tier || (!h_block_ids && n)) return SPECKV_ERR_INVAL;
+    Tier& t = tier->t;
+    std::lock_guard<std::mutex> lk(t.mu);
+    for (size_t i = 0; i < n; ++i) {
+        auto it = t.blocks.find(h_block_ids[i]);
+        if (it == t.blocks.end()) continue;   // like speckv_free: dropping an unknown block is not an error
+        const uint64_t len = ((uint64_t)it->second.comp_bytes + 15u) & ~15ull;
+        t.free_pool(it->second.pool_off, len);
+        t.stats.used_bytes -= len;
+        t.blocks.erase(it);
+    }
+    t.stats.blocks = t.blocks.size();
+    return SPECKV_OK;
+}
+
+void speckv_ext_tier_get_stats(speckv_tier_t* tier, speckv_tier_stats_t* out) {
+    if (!tier || !out) return;
+    std::lock_guard<std::mutex> lk(tier->t.mu);
+    *out = tier->t.stats;
+}
+
+}  // extern "C"

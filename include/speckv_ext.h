@@ -138,6 +138,38 @@ SPECKV_API speckv_status_t speckv_ext_page_lookup(const speckv_page_t* d_pages, 
                                                   const uint64_t* d_va, uint64_t* d_pa, uint32_t* d_flags,
                                                   size_t n, void* cuda_stream);
 
+/* ---- host tier (pinned-DRAM pool standing in for the CXL memory pool) ------------------- */
+/* Replaces the simulated DMA of SpeckvAllocator::sync_fetch_page (speckv_allocator.cpp:115-138,
+ * descriptor flag bit1 = COMPRESSED, driver/uapi/speckv_ioctl.h:14) and CXLMemoryManager's
+ * demote_to_l3 / promote_to_l1 data movement (cxl_memory_manager.cpp:130-194) with real transfers:
+ * offload = compress + pack on the GPU, one device-to-host copy per chunk on a side stream into a
+ * pinned pool; restore = host-to-device copies of the packed blocks + decompress.  Blocks are
+ * named by caller-chosen 64-bit ids (e.g. virt_page_id).  Scheme: INT8_DELTA_RLE. */
+typedef struct speckv_tier speckv_tier_t;
+typedef struct {
+    uint64_t pool_bytes, used_bytes, blocks;
+    uint64_t bytes_offloaded_raw, bytes_offloaded_stored;   /* uncompressed KV bytes / bytes placed in the pool */
+    uint64_t bytes_restored_raw, bytes_restored_stored;
+    uint64_t last_offload_stored_bytes, last_restore_stored_bytes;
+    double   last_offload_ms, last_restore_ms;              /* wall time of the last call, copies included */
+} speckv_tier_stats_t;
+
+SPECKV_API speckv_status_t speckv_ext_tier_create(size_t pool_bytes, speckv_tier_t** out_tier);
+SPECKV_API void speckv_ext_tier_destroy(speckv_tier_t* tier);
+/* Compress n_groups groups of d_in and move their payload into the pool under h_block_ids[i].
+ * Returns when the bytes are in host memory.  SPECKV_ERR_NOMEM when the pool is full. */
+SPECKV_API speckv_status_t speckv_ext_tier_offload(speckv_tier_t* tier, const void* d_in, speckv_dtype_t dtype,
+                                                   size_t group_elems, size_t n_groups,
+                                                   const uint64_t* h_block_ids, void* cuda_stream);
+/* Bring blocks back: output group i (d_out + i*group_elems) = decompressed block h_block_ids[i].
+ * Unknown id -> SPECKV_ERR_GENERAL.  Returns when d_out is complete. */
+SPECKV_API speckv_status_t speckv_ext_tier_restore(speckv_tier_t* tier, const uint64_t* h_block_ids, size_t n_groups,
+                                                   size_t group_elems, speckv_dtype_t dtype, void* d_out,
+                                                   void* cuda_stream);
+/* Release pool space of blocks (unknown ids are ignored, like speckv_free). */
+SPECKV_API speckv_status_t speckv_ext_tier_drop(speckv_tier_t* tier, const uint64_t* h_block_ids, size_t n);
+SPECKV_API void speckv_ext_tier_get_stats(speckv_tier_t* tier, speckv_tier_stats_t* out);
+
 /* ---- speculative prefetch scoring ---------------------------------------------------- */
 /* Installs the predictor's weights on the current device: embedding [vocab][emb_dim] and
  * output projection [vocab][hidden], fp32, row-major -- the two tables
