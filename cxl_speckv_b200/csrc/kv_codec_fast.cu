@@ -272,7 +272,15 @@ __device__ __forceinline__ void flush_region(uint32_t sbase, uint8_t* gout, int 
     const int nv = (hi_al - lo_al) >> 3;
     uint32_t sa = sbase + 2u * (uint32_t)lo_al + 16u * (uint32_t)lane;
     uint8_t* ga = gout + 2 * (size_t)lo_al + 16 * (size_t)lane;
-    for (int v = lane; v < nv; v += 32, sa += 512u, ga += 512) stg128(ga, lds128s(sa));
+    int v = lane;
+    for (; v + 96 < nv; v += 128, sa += 2048u, ga += 2048) {   // 4 vectors per lane per trip
+        const uint4 a0 = lds128s(sa), a1 = lds128s(sa + 512u), a2 = lds128s(sa + 1024u), a3 = lds128s(sa + 1536u);
+        stg128(ga, a0);
+        stg128(ga + 512, a1);
+        stg128(ga + 1024, a2);
+        stg128(ga + 1536, a3);
+    }
+    for (; v < nv; v += 32, sa += 512u, ga += 512) stg128(ga, lds128s(sa));
 }
 
 // ===================================================================================
@@ -582,12 +590,16 @@ decompress_fast_kernel(const uint8_t* __restrict__ payload, size_t slot_bytes, c
             }
             const uint32_t va = __byte_perm(w.x, w.y, 0x6420), ca = __byte_perm(w.x, w.y, 0x7531);
             const uint32_t vb = __byte_perm(w.z, w.w, 0x6420), cb = __byte_perm(w.z, w.w, 0x7531);
-            csum = __dp4a(ca, 0x01010101u, csum);
-            csum = __dp4a(cb, 0x01010101u, csum);
-            ssum = __dp4a(va, ca, ssum);
-            ssum = __dp4a(vb, cb, ssum);
-            nnz += __popc((((ca & 0x7f7f7f7fu) + 0x7f7f7f7fu) | ca) & 0x80808080u) +
-                   __popc((((cb & 0x7f7f7f7fu) + 0x7f7f7f7fu) | cb) & 0x80808080u);
+            if (__all_sync(kFull, ca == 0x01010101u && cb == 0x01010101u)) {   // one element per pair
+                csum += 8u;
+                nnz += 8u;
+                ssum = __dp4a(vb, 0x01010101u, __dp4a(va, 0x01010101u, ssum));
+            } else {
+                csum = __dp4a(cb, 0x01010101u, __dp4a(ca, 0x01010101u, csum));
+                ssum = __dp4a(vb, cb, __dp4a(va, ca, ssum));
+                nnz += __popc((((ca & 0x7f7f7f7fu) + 0x7f7f7f7fu) | ca) & 0x80808080u) +
+                       __popc((((cb & 0x7f7f7f7fu) + 0x7f7f7f7fu) | cb) & 0x80808080u);
+            }
         }
         csum = __reduce_add_sync(kFull, csum);
         ssum = __reduce_add_sync(kFull, ssum) & 0xffu;
@@ -649,12 +661,19 @@ decompress_fast_kernel(const uint8_t* __restrict__ payload, size_t slot_bytes, c
                 v0 = __byte_perm(va, va, sel.x);
                 v1 = __byte_perm(va, vb, sel.y);
             }
+            // codes = running byte sums: dp4a against 0x01, 0x0101, ... adds the first 1..4 bytes
             float y[9];
-#pragma unroll
-            for (int j = 0; j < 9; ++j) {
-                qb += (j < 4 ? v0 >> (8 * j) : (j < 8 ? v1 >> (8 * (j - 4)) : v2)) & 0xffu;
-                y[j] = dequantize(qb & 0xffu, s);
-            }
+            const uint32_t q4 = __dp4a(v0, 0x01010101u, qb);
+            y[0] = dequantize(__dp4a(v0, 0x00000001u, qb) & 0xffu, s);
+            y[1] = dequantize(__dp4a(v0, 0x00000101u, qb) & 0xffu, s);
+            y[2] = dequantize(__dp4a(v0, 0x00010101u, qb) & 0xffu, s);
+            y[3] = dequantize(q4 & 0xffu, s);
+            y[4] = dequantize(__dp4a(v1, 0x00000001u, q4) & 0xffu, s);
+            y[5] = dequantize(__dp4a(v1, 0x00000101u, q4) & 0xffu, s);
+            y[6] = dequantize(__dp4a(v1, 0x00010101u, q4) & 0xffu, s);
+            const uint32_t q8 = __dp4a(v1, 0x01010101u, q4);
+            y[7] = dequantize(q8 & 0xffu, s);
+            y[8] = dequantize((q8 + (v2 & 0xffu)) & 0xffu, s);
             store_units9(sbase + 2u * idx, pack2_out<T>(y[0], y[1]), pack2_out<T>(y[2], y[3]), pack2_out<T>(y[4], y[5]),
                          pack2_out<T>(y[6], y[7]), pack2_out<T>(y[8], 0.0f), 8 + ntwo);
             ecur += 256u + __popc(bal);
