@@ -390,13 +390,120 @@ def run_cuda(args, rank, world, local_rank):
         dist.destroy_process_group()
 
 
+# --------------------------------------------------------------------------------------
+# auxiliary reports (not the driver's bench line): BASELINE configs 4 and 5
+# --------------------------------------------------------------------------------------
+def run_cfg4(args, local_rank):
+    """Llama-3-8B 32K-context paged KV: translate every page address, page-table lookup, then
+    offload -> restore through the pinned host pool (PCIe GB/s of stored bytes), verify bytes."""
+    import ctypes as C
+
+    import numpy as np
+    import torch
+
+    import cxl_speckv_b200 as pkg
+    from cxl_speckv_b200 import codec
+    from cxl_speckv_b200.tier import HostTier
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    L = pkg.lib()
+    layers = max(1, int(round(32 * args.scale)))
+    G, pages = 2048, layers * 2 * 8 * 32768 * 128 // 2048
+    x = torch.empty(pages * G, dtype=torch.float16, device=dev)
+    gen = torch.Generator(device=dev); gen.manual_seed(1234)
+    x.normal_(generator=gen)
+
+    def timed(fn, reps=3):
+        fn(); torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            fn()
+        b.record(); torch.cuda.synchronize()
+        return a.elapsed_time(b) / reps
+
+    # address translation of every page + page-table lookup through the exported table
+    assert L.speckv_init(f"cuda:{local_rank}".encode()) == 0
+    h = C.c_uint64(); assert L.speckv_alloc(pages * 4096, None, C.byref(h)) == 0
+    tbl = torch.empty(pages * 3, dtype=torch.int64, device=dev); cnt = C.c_size_t()
+    assert L.speckv_ext_page_table_export(h.value, tbl.data_ptr(), pages, C.byref(cnt), None) == 0
+    va = (torch.arange(pages, dtype=torch.int64, device=dev) << 12) + (h.value << 32) + 0x123
+    pa = torch.empty_like(va); fl = torch.empty(pages, dtype=torch.int32, device=dev)
+    t_tr = timed(lambda: codec.translate(va, out=pa))
+    t_lk = timed(lambda: L.speckv_ext_page_lookup(tbl.data_ptr(), pages, h.value << 32, va.data_ptr(), pa.data_ptr(), fl.data_ptr(), pages, None))
+    assert int(pa[5].item()) == 0x4000000000 + (h.value << 20) + (5 << 12) + 0x123
+    L.speckv_finalize()
+
+    tier = HostTier(int(pages * G * 2 * 1.02) + (64 << 20))
+    ids = np.arange(pages, dtype=np.uint64) << np.uint64(12)
+    tier.offload(x[:65536 * G], G, ids[:65536]); tier.drop(ids[:65536])      # warm-up: staging buffers, pinned mirrors
+    t0 = time.perf_counter(); tier.offload(x, G, ids); torch.cuda.synchronize(); t_off = time.perf_counter() - t0
+    out = torch.empty((pages, G), dtype=torch.float16, device=dev)
+    t0 = time.perf_counter(); tier.restore(ids, G, torch.float16, out=out); torch.cuda.synchronize(); t_res = time.perf_counter() - t0
+    st = tier.stats()
+    want = codec.decompress(codec.compress(x[:4096 * G], G))
+    assert torch.equal(out[:4096].view(torch.int16), want.view(torch.int16))
+    tier.close()
+    print(json.dumps({"report": "cfg4", "workload": f"Llama-3-8B 32K ctx paged KV, {layers} layers, {pages} pages of 4 KiB",
+                      "translate_Gaddr_per_s": pages / t_tr / 1e6, "translate_GB/s": pages * 16 / t_tr / 1e6,
+                      "page_lookup_Gaddr_per_s": pages / t_lk / 1e6,
+                      "offload": {"s": t_off, "stored_bytes": st["bytes_offloaded_stored"], "pcie_GB/s": st["bytes_offloaded_stored"] / t_off / 1e9,
+                                  "kv_GB/s": pages * G * 2 / t_off / 1e9},
+                      "restore": {"s": t_res, "pcie_GB/s": st["bytes_restored_stored"] / t_res / 1e9, "kv_GB/s": pages * G * 2 / t_res / 1e9},
+                      "verified": "restored pages == device compress->decompress, bit for bit"}), flush=True)
+
+
+def run_cfg5(args, local_rank):
+    """Batch-256 decode step: LSTM prefetch scoring (k = 4) + decompress of the predicted blocks."""
+    import numpy as np
+    import torch
+
+    from cxl_speckv_b200 import codec, prefetch
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    rng = np.random.default_rng(1)
+    emb = ((rng.random((32000, 64), dtype=np.float32) - 0.5) * 0.1).astype(np.float32)
+    wout = ((rng.random((32000, 128), dtype=np.float32) - 0.5) * 0.1).astype(np.float32)
+    prefetch.load_predictor(emb, wout)
+    toks = torch.from_numpy(np.random.default_rng(7).integers(0, 32000, (256, 16)).astype(np.int32)).to(dev)
+    G, n_blocks = 131072, 4096                                    # 1 GiB of stored blocks to pick from
+    x = torch.randn(n_blocks * G, device=dev).half()
+    c = codec.compress(x, G)
+    out = torch.empty((1024, G), dtype=torch.float16, device=dev)
+
+    def step():
+        ids, conf, va = prefetch.score(toks, k=4, layer_id=0)
+        codec.decompress_indexed(c, (ids.view(-1) % n_blocks).to(torch.int32), out=out)
+
+    for _ in range(3):
+        step()
+    torch.cuda.synchronize()
+    a, b, m = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+    reps = 10
+    a.record()
+    for _ in range(reps):
+        ids, conf, va = prefetch.score(toks, k=4, layer_id=0)
+    m.record()
+    for _ in range(reps):
+        step()
+    b.record(); torch.cuda.synchronize()
+    t_score = a.elapsed_time(m) / reps
+    t_step = m.elapsed_time(b) / reps
+    print(json.dumps({"report": "cfg5", "workload": "256 sequences x 16-token history, vocab 32000, k=4 -> 1024 predicted blocks of 1024x128 fp16",
+                      "score_ms": t_score, "score_seq_per_s": 256 / t_score * 1e3, "reference_cpu_ms_per_sequence": 17.8,
+                      "step_ms(score+decompress 1024 blocks)": t_step,
+                      "decompress_kv_GB/s": 1024 * G * 2 / ((t_step - t_score) * 1e-3) / 1e9}), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
-    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg3", "cfg4p"])
+    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg3", "cfg4p", "cfg4", "cfg5"])
     ap.add_argument("--scale", type=float, default=1.0, help="fraction of the workload's layers (debug only; 1.0 = the named config)")
     ap.add_argument("--e2e-mib", type=float, default=2048.0, help="host-buffer sample per e2e step (MiB of fp16 KV)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
@@ -406,7 +513,11 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if args.impl == "reference":
+    if args.workload == "cfg4":
+        run_cfg4(args, local_rank)
+    elif args.workload == "cfg5":
+        run_cfg5(args, local_rank)
+    elif args.impl == "reference":
         run_reference(args, rank, world)
     else:
         run_cuda(args, rank, world, local_rank)
