@@ -95,15 +95,16 @@ template <> __device__ __forceinline__ bool fast_quant_ok<__nv_bfloat16>(float m
 template <> __device__ __forceinline__ bool fast_quant_ok<float>(float) { return false; }
 
 // ---- dequantiser -------------------------------------------------------------------
-// (float) q / 127.0f * s with q the signed code.  q/127 is an IEEE division by a
-// constant; oracle/verify_fastdiv.c checks all 256 codes against the identity
-//     y0 = RN(q*r127);  y = RN(y0 + RN(q - y0*127)*r127),  r127 = RN(1/127)
-__device__ __forceinline__ float dequantize(uint32_t code_u8, float s) {
-    float qf = (float)(int)(int8_t)code_u8;
-    const float r127 = 0.007874015718698502f;  // RN(1/127) = 0x3c010204
-    float y0 = __fmul_rn(qf, r127);
-    float e = __fmaf_rn(-y0, 127.0f, qf);
-    float y = __fmaf_rn(e, r127, y0);
+// (float) q / 127.0f * s with q the signed code (the LOW BYTE of code; upper bits are ignored).
+// q/127 is an IEEE division by a constant: with r127 = RN(1/127) and d127 = RN(1/127 - r127),
+//     RN(q/127) == RN(q*r127 + RN(q*d127))        (one FMUL + one FMA)
+// holds for all 256 codes (oracle/verify_fastdiv.c checks them: q/127 has a 7-bit periodic
+// expansion, so it is never within the tiny error of a rounding boundary).
+__device__ __forceinline__ float dequantize(uint32_t code, float s) {
+    const float qf = (float)(int)(int8_t)code;
+    const float r127 = __uint_as_float(0x3c010204u);   // RN(1/127)
+    const float d127 = __uint_as_float(0x2e010204u);   // RN(1/127 - r127)
+    const float y = __fmaf_rn(qf, r127, __fmul_rn(qf, d127));
     return __fmul_rn(y, s);
 }
 

@@ -431,7 +431,7 @@ compress_fast_kernel(const T* __restrict__ in, uint32_t n_groups, uint8_t* __res
     // pair closes a run of that length (+ its own offset)
     uint32_t carry_tail = halo_nz1 ? ((uint32_t)__clz((int)halo_nz1) >> 3) + 1u : ((uint32_t)__clz((int)halo_nz0) >> 3) + 5u;
     const int src_lane = (lane + 31) & 31;
-#pragma unroll 1
+#pragma unroll 2
     for (int k = 0; k < kIters; ++k) {
         const uint4 st = lds128(reg + k * 512 + lane * 16);
         __syncwarp();   // every lane has read its slot before any pair of this iteration lands on it
@@ -634,11 +634,10 @@ decompress_fast_kernel(const uint8_t* __restrict__ payload, size_t slot_bytes, c
         __syncwarp();
         const uint32_t va = __byte_perm(w.x, w.y, 0x6420), ca = __byte_perm(w.x, w.y, 0x7531);
         const uint32_t vb = __byte_perm(w.z, w.w, 0x6420), cb = __byte_perm(w.z, w.w, 0x7531);
-        // counts: z = c ^ 1 is 0 for a count of 1 and 3 for a count of 2
-        const uint32_t za = ca ^ 0x01010101u, zb = cb ^ 0x01010101u;
-        const bool small = (((za | zb) & 0xfcfcfcfcu) == 0) && (((za ^ (za >> 1)) & 0x01010101u) == 0) &&
-                           (((zb ^ (zb >> 1)) & 0x01010101u) == 0);
-        const uint32_t ta = za & 0x01010101u, tb = zb & 0x01010101u;   // byte j = 1 iff count j is 2
+        // counts: c - 1 is 0 for a count of 1 and 1 for a count of 2; a count of 0 borrows and any
+        // other count leaves higher bits, so "every count is 1 or 2" is one mask test
+        const uint32_t ta = ca - 0x01010101u, tb = cb - 0x01010101u;   // byte j = 1 iff count j is 2
+        const bool small = ((ta | tb) & 0xfefefefeu) == 0;
         const int ntwo = __popc(ta) + __popc(tb);
         const bool slow = __any_sync(kFull, !small || ntwo > 1);
         const uint32_t sl = __dp4a(vb, cb, __dp4a(va, ca, 0u));
@@ -654,7 +653,8 @@ decompress_fast_kernel(const uint8_t* __restrict__ payload, size_t slot_bytes, c
             }
             const uint32_t tot = __shfl_sync(kFull, inc, 31);
             uint32_t qb = qcur + inc - sl;
-            uint32_t v0 = va, v1 = vb, v2 = vb >> 24;
+            uint32_t v0 = va, v1 = vb;
+            const uint32_t v2 = vb >> 24;
             if (ntwo) {
                 const int h = ta ? (__ffs((int)ta) >> 3) : (__ffs((int)tb) >> 3) + 4;
                 const uint2 sel = *reinterpret_cast<const uint2*>(c_dup_sel[h]);
@@ -664,16 +664,16 @@ decompress_fast_kernel(const uint8_t* __restrict__ payload, size_t slot_bytes, c
             // codes = running byte sums: dp4a against 0x01, 0x0101, ... adds the first 1..4 bytes
             float y[9];
             const uint32_t q4 = __dp4a(v0, 0x01010101u, qb);
-            y[0] = dequantize(__dp4a(v0, 0x00000001u, qb) & 0xffu, s);
-            y[1] = dequantize(__dp4a(v0, 0x00000101u, qb) & 0xffu, s);
-            y[2] = dequantize(__dp4a(v0, 0x00010101u, qb) & 0xffu, s);
-            y[3] = dequantize(q4 & 0xffu, s);
-            y[4] = dequantize(__dp4a(v1, 0x00000001u, q4) & 0xffu, s);
-            y[5] = dequantize(__dp4a(v1, 0x00000101u, q4) & 0xffu, s);
-            y[6] = dequantize(__dp4a(v1, 0x00010101u, q4) & 0xffu, s);
+            y[0] = dequantize(__dp4a(v0, 0x00000001u, qb), s);
+            y[1] = dequantize(__dp4a(v0, 0x00000101u, qb), s);
+            y[2] = dequantize(__dp4a(v0, 0x00010101u, qb), s);
+            y[3] = dequantize(q4, s);
+            y[4] = dequantize(__dp4a(v1, 0x00000001u, q4), s);
+            y[5] = dequantize(__dp4a(v1, 0x00000101u, q4), s);
+            y[6] = dequantize(__dp4a(v1, 0x00010101u, q4), s);
             const uint32_t q8 = __dp4a(v1, 0x01010101u, q4);
-            y[7] = dequantize(q8 & 0xffu, s);
-            y[8] = dequantize((q8 + (v2 & 0xffu)) & 0xffu, s);
+            y[7] = dequantize(q8, s);
+            y[8] = dequantize(q8 + v2, s);
             store_units9(sbase + 2u * idx, pack2_out<T>(y[0], y[1]), pack2_out<T>(y[2], y[3]), pack2_out<T>(y[4], y[5]),
                          pack2_out<T>(y[6], y[7]), pack2_out<T>(y[8], 0.0f), 8 + ntwo);
             ecur += 256u + __popc(bal);

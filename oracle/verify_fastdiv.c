@@ -82,8 +82,16 @@ int main(int argc, char** argv) {
         float y0 = qf * r127, e = fmaf(-y0, 127.0f, qf), y = fmaf(e, r127, y0);
         if (memcmp(&y, &t, 4)) dbad++;
     }
-    printf("dequant: r127 bits=0x%08x (%.18g) mismatches=%d\n", rb, r127, dbad);
-    fail += dbad + (rb != 0x3c010204u);
+    /* two-operation form used by the kernels: RN(q*r127 + RN(q*d127)), d127 = RN(1/127 - r127) */
+    float d127 = (float)(1.0 / 127.0 - (double)r127);
+    uint32_t db; memcpy(&db, &d127, 4);
+    for (int q = -128; q < 128; ++q) {
+        float qf = (float)q, t = qf / 127.0f;
+        float y = fmaf(qf, r127, qf * d127);
+        if (memcmp(&y, &t, 4)) dbad++;
+    }
+    printf("dequant: r127 bits=0x%08x (%.18g) d127 bits=0x%08x mismatches=%d\n", rb, r127, db, dbad);
+    fail += dbad + (rb != 0x3c010204u) + (db != 0x2e010204u);
     /* rounding identity: kernel rounding == roundf on a dense sweep incl. ties and 0.49999997 */
     long rbad = 0;
     for (int i = -3300000; i <= 3300000; ++i) {

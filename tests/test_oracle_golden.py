@@ -162,3 +162,16 @@ def test_port_vs_reference_random():
         s = np.float32(rng.uniform(0.001, 3))
         a, b = Port.decompress(s, p, 200000), Ref.decompress(s, p, 200000)
         assert np.array_equal(f32_bits(a), f32_bits(b))
+
+
+def test_division_identities_quick():
+    """oracle/verify_fastdiv: the FMA-residual quantiser, the q/127 identities and the rounding
+    trick used by the CUDA kernels equal the reference arithmetic (every 16th fp16/bf16 max value
+    here; the full exhaustive run is `./oracle/verify_fastdiv`, ~15 s on 8 cores)."""
+    import os
+    import subprocess
+
+    here = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle")
+    subprocess.check_call(["make", "-s", "-C", here, "verify"])
+    out = subprocess.run([os.path.join(here, "verify_fastdiv"), "quick"], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and out.stdout.strip().endswith("OK"), out.stdout
