@@ -36,8 +36,12 @@ namespace speckv {
 
 namespace {
 
-constexpr int kW = 16;                  // warps (= regions) per CTA
+#ifndef SPECKV_KW
+#define SPECKV_KW 16
+#endif
+constexpr int kW = SPECKV_KW;           // warps (= regions) per CTA
 constexpr int kThreadsF = kW * 32;
+constexpr int kCtasPerSm = 48 / kW;     // 48 warps per SM: 40 registers per thread, <= 227 KiB of tiles
 constexpr int kRegion = 2048;           // elements / pairs per region
 constexpr int kIters = 8;               // 256 per warp iteration, 8 per lane
 constexpr int kRegionBytes = 4096;
@@ -287,7 +291,7 @@ __device__ __forceinline__ void flush_region(uint32_t sbase, uint8_t* gout, int 
 // compress
 // ===================================================================================
 template <typename T, int R>
-__global__ void __launch_bounds__(kThreadsF, 3)
+__global__ void __launch_bounds__(kThreadsF, kCtasPerSm)
 compress_fast_kernel(const T* __restrict__ in, uint32_t n_groups, uint8_t* __restrict__ payload, size_t slot_bytes,
                      float* __restrict__ scales, uint32_t* __restrict__ comp_bytes,
                      uint32_t* __restrict__ needs_generic) {
@@ -511,7 +515,7 @@ compress_fast_kernel(const T* __restrict__ in, uint32_t n_groups, uint8_t* __res
 // decompress
 // ===================================================================================
 template <typename T, int R>
-__global__ void __launch_bounds__(kThreadsF, 3)
+__global__ void __launch_bounds__(kThreadsF, kCtasPerSm)
 decompress_fast_kernel(const uint8_t* __restrict__ payload, size_t slot_bytes, const float* __restrict__ scales,
                        const uint32_t* __restrict__ comp_bytes, uint32_t n_groups, T* __restrict__ out,
                        uint32_t* __restrict__ out_elems, uint32_t* __restrict__ needs_generic,
@@ -779,6 +783,7 @@ int fast_regions(const CodecArgs& a, bool decompress) {
     if (a.group_elems == 0 || a.group_elems % kRegion) return 0;
     const uint32_t R = a.group_elems / kRegion;
     if (R > 128 || (R & (R - 1))) return 0;
+    if (R > (uint32_t)kW * 8) return 0;   // portable cluster size limit (8 CTAs)
     const void* elems = decompress ? a.out : a.in;
     if ((reinterpret_cast<uintptr_t>(elems) | reinterpret_cast<uintptr_t>(a.payload)) & 15) return 0;
     if (a.slot_bytes < (size_t)R * kRegionBytes) return 0;
