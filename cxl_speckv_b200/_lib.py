@@ -93,6 +93,13 @@ def lib() -> C.CDLL:
     L.speckv_ext_tier_restore.argtypes = [vp, vp, sz, sz, C.c_int, vp, vp]; L.speckv_ext_tier_restore.restype = C.c_int
     L.speckv_ext_tier_drop.argtypes = [vp, vp, sz]; L.speckv_ext_tier_drop.restype = C.c_int
     L.speckv_ext_tier_get_stats.argtypes = [vp, C.POINTER(TierStats)]; L.speckv_ext_tier_get_stats.restype = None
+    L.speckv_ext_atu_create.argtypes = [C.c_uint32, C.POINTER(vp)]; L.speckv_ext_atu_create.restype = C.c_int
+    L.speckv_ext_atu_destroy.argtypes = [vp]; L.speckv_ext_atu_destroy.restype = None
+    L.speckv_ext_atu_translate.argtypes = [vp, vp, vp, sz, vp]; L.speckv_ext_atu_translate.restype = C.c_int
+    L.speckv_ext_atu_invalidate.argtypes = [vp, C.c_uint64, C.c_int, vp]; L.speckv_ext_atu_invalidate.restype = C.c_int
+    L.speckv_ext_atu_get_stats.argtypes = [vp, u64p, u64p, C.c_int]; L.speckv_ext_atu_get_stats.restype = C.c_int
+    L.speckv_ext_ratio_stats.argtypes = [vp, sz, sz, C.POINTER(C.c_double), C.POINTER(C.c_double), vp]
+    L.speckv_ext_ratio_stats.restype = C.c_int
     L.speckv_ext_get_stats.argtypes = [C.POINTER(Stats)]; L.speckv_ext_get_stats.restype = None
     L.speckv_ext_reset_stats.argtypes = []; L.speckv_ext_reset_stats.restype = None
     _LIB = L

@@ -146,11 +146,56 @@ static size_t chunk_groups(size_t group_bytes, size_t n_groups) {
     return c ? c : 1;
 }
 
+// sum of payload sizes and sum of the per-group ratios original_size / compressed_size, where
+// original_size = n * sizeof(float) exactly as the reference accounts it (cache_engine.cpp:49,72)
+__global__ void __launch_bounds__(256)
+ratio_kernel(const uint32_t* __restrict__ comp_bytes, size_t n_groups, double original_bytes, double* __restrict__ acc) {
+    double c = 0.0, r = 0.0;
+    for (size_t g = (size_t)blockIdx.x * 256 + threadIdx.x; g < n_groups; g += (size_t)gridDim.x * 256) {
+        const double cb = (double)comp_bytes[g];
+        c += cb;
+        if (cb > 0.0) r += original_bytes / cb;
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        c += __shfl_xor_sync(0xffffffffu, c, o);
+        r += __shfl_xor_sync(0xffffffffu, r, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(&acc[0], c);
+        atomicAdd(&acc[1], r);
+    }
+}
+
 }  // namespace speckv
 
 using namespace speckv;
 
 extern "C" {
+
+speckv_status_t speckv_ext_ratio_stats(const uint32_t* d_comp_bytes, size_t n_groups, size_t group_elems,
+                                       double* out_total_comp_bytes, double* out_mean_ratio, void* cuda_stream) {
+    if (device_count() <= 0) return SPECKV_ERR_DRIVER;
+    if (!d_comp_bytes || !out_total_comp_bytes || !out_mean_ratio) return SPECKV_ERR_INVAL;
+    *out_total_comp_bytes = 0.0;
+    *out_mean_ratio = 0.0;
+    if (n_groups == 0) return SPECKV_OK;
+    cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+    double* d_acc = nullptr;
+    cudaError_t e = cudaMallocAsync((void**)&d_acc, 16, st);
+    if (e != cudaSuccess) return status_of(e);
+    cudaMemsetAsync(d_acc, 0, 16, st);
+    size_t blocks = (n_groups + 255) / 256;
+    if (blocks > 1024) blocks = 1024;
+    ratio_kernel<<<(unsigned)blocks, 256, 0, st>>>(d_comp_bytes, n_groups, (double)group_elems * 4.0, d_acc);
+    count_launch();
+    double h[2] = {0.0, 0.0};
+    e = cudaMemcpyAsync(h, d_acc, 16, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    cudaFreeAsync(d_acc, st);
+    *out_total_comp_bytes = h[0];
+    *out_mean_ratio = h[1] / (double)n_groups;
+    return status_of(e);
+}
 
 int speckv_ext_device_count(void) { return device_count(); }
 

@@ -111,6 +111,20 @@ SPECKV_API void speckv_ext_host_free(void* p);
  * the value, only hit/miss counts. */
 SPECKV_API speckv_status_t speckv_ext_translate(const uint64_t* d_va, uint64_t* d_pa, size_t n, void* cuda_stream);
 
+/* Stateful model of the reference's AddressTranslationUnit (src/utils/address_translation.cpp):
+ * a direct-mapped TLB whose translate() returns entry.ppage + offset on a hit and
+ * page_walk(va) + offset -- the offset counted twice -- on a miss (:19-46, :85-90), with hit/miss
+ * counters (:23-27).  The batch is processed with exact sequential semantics (results depend on
+ * the order of d_va).  `all` != 0 in _invalidate = invalidate_all (:60-66), else invalidate(va)
+ * (:48-58).  _get_stats synchronises the device. */
+typedef struct speckv_atu speckv_atu_t;
+SPECKV_API speckv_status_t speckv_ext_atu_create(uint32_t tlb_size, speckv_atu_t** out_atu);
+SPECKV_API void speckv_ext_atu_destroy(speckv_atu_t* atu);
+SPECKV_API speckv_status_t speckv_ext_atu_translate(speckv_atu_t* atu, const uint64_t* d_va, uint64_t* d_pa, size_t n,
+                                                    void* cuda_stream);
+SPECKV_API speckv_status_t speckv_ext_atu_invalidate(speckv_atu_t* atu, uint64_t va, int all, void* cuda_stream);
+SPECKV_API speckv_status_t speckv_ext_atu_get_stats(speckv_atu_t* atu, uint64_t* hits, uint64_t* misses, int reset);
+
 /* ---- page table --------------------------------------------------------------- */
 /* One page-table entry: identical to the reference's KvPageHandle
  * (host/include/speckv_allocator.hpp:22-27): flags bit0 = in L1, bit1 = in L2, bit2 = compressed. */
@@ -201,6 +215,12 @@ typedef struct {
     uint64_t kernel_launches;        /* CUDA kernels this library launched */
 } speckv_ext_stats_t;
 SPECKV_API void speckv_ext_get_stats(speckv_ext_stats_t* out);
+/* EngineStatistics::avg_compression_ratio (cache_engine.cpp:69-75): the mean over groups of
+ * original_size / compressed_size with original_size = group_elems * sizeof(float), the reference's
+ * own accounting (:49); plus the total payload bytes.  Blocking (returns host values). */
+SPECKV_API speckv_status_t speckv_ext_ratio_stats(const uint32_t* d_comp_bytes, size_t n_groups, size_t group_elems,
+                                                  double* out_total_comp_bytes, double* out_mean_ratio,
+                                                  void* cuda_stream);
 SPECKV_API void speckv_ext_reset_stats(void);
 
 #ifdef __cplusplus

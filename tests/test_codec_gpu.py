@@ -371,3 +371,73 @@ def test_page_table_lookup_on_device(golden):
             assert Port.access_addr(h, sz, off) == (addr if rc == 0 else 0)
     finally:
         L.speckv_finalize()
+
+
+def test_stateful_atu_matches_reference_sequence(golden):
+    """AddressTranslationUnit with its TLB state: per-address results (offset counted twice on a
+    miss), hit/miss counters and invalidation, against the reference's recorded sequence and the
+    oracle's model on a longer random sequence."""
+    import cxl_speckv_b200 as pkg
+    L = pkg.lib()
+    tr, meta = golden["translate"], golden["meta"]["translate"]
+    atu = C.c_void_p()
+    assert L.speckv_ext_atu_create(1024, C.byref(atu)) == 0
+    try:
+        va = torch.from_numpy(tr["va"].view(np.int64)).to(DEV)
+        pa = torch.empty_like(va)
+        assert L.speckv_ext_atu_translate(atu, va.data_ptr(), pa.data_ptr(), va.numel(), None) == 0
+        assert np.array_equal(pa.cpu().numpy().view(np.uint64), tr["atu_pa"])
+        h, m = C.c_uint64(), C.c_uint64()
+        assert L.speckv_ext_atu_get_stats(atu, C.byref(h), C.byref(m), 1) == 0
+        assert (h.value, m.value) == (meta["atu_hits"], meta["atu_misses"])
+        # longer sequence with reuse, continuing from the TLB state left by the first batch
+        rng = np.random.default_rng(3)
+        seq = (np.uint64(0x100000000) + rng.integers(0, 3000, 20000, dtype=np.uint64) * np.uint64(4096)
+               + rng.integers(0, 4096, 20000, dtype=np.uint64))
+        Lp = Port.lib()
+        ref = Lp.oracle_atu_new(1024)
+        ref = C.c_void_p(ref)
+        for v in tr["va"]:
+            Lp.oracle_atu_translate(ref, int(v))
+        want = np.array([Lp.oracle_atu_translate(ref, int(v)) for v in seq], dtype=np.uint64)
+        va2 = torch.from_numpy(seq.view(np.int64)).to(DEV)
+        pa2 = torch.empty_like(va2)
+        assert L.speckv_ext_atu_translate(atu, va2.data_ptr(), pa2.data_ptr(), va2.numel(), None) == 0
+        assert np.array_equal(pa2.cpu().numpy().view(np.uint64), want)
+        # invalidate one page, then everything
+        Lp.oracle_atu_invalidate(ref, int(seq[-1]))
+        assert L.speckv_ext_atu_invalidate(atu, int(seq[-1]), 0, None) == 0
+        probe = np.array([seq[-1], seq[-2], seq[-1]], dtype=np.uint64)
+        want = np.array([Lp.oracle_atu_translate(ref, int(v)) for v in probe], dtype=np.uint64)
+        vp_ = torch.from_numpy(probe.view(np.int64)).to(DEV); pp_ = torch.empty_like(vp_)
+        assert L.speckv_ext_atu_translate(atu, vp_.data_ptr(), pp_.data_ptr(), 3, None) == 0
+        assert np.array_equal(pp_.cpu().numpy().view(np.uint64), want)
+        Lp.oracle_atu_invalidate_all(ref)
+        assert L.speckv_ext_atu_invalidate(atu, 0, 1, None) == 0
+        want = np.array([Lp.oracle_atu_translate(ref, int(v)) for v in probe], dtype=np.uint64)
+        assert L.speckv_ext_atu_translate(atu, vp_.data_ptr(), pp_.data_ptr(), 3, None) == 0
+        assert np.array_equal(pp_.cpu().numpy().view(np.uint64), want)
+        hh, mm = C.c_uint64(), C.c_uint64()
+        Lp.oracle_atu_stats(ref, C.byref(hh), C.byref(mm))
+        assert L.speckv_ext_atu_get_stats(atu, C.byref(h), C.byref(m), 0) == 0
+        assert h.value + meta["atu_hits"] == hh.value and m.value + meta["atu_misses"] == mm.value
+        Lp.oracle_atu_free(ref)
+    finally:
+        L.speckv_ext_atu_destroy(atu)
+
+
+def test_ratio_stats_match_reference_accounting():
+    """avg_compression_ratio the way the reference accounts it (fp32 original size, mean of ratios)."""
+    import cxl_speckv_b200 as pkg
+    L = pkg.lib()
+    G, n = 2048, 500
+    x = torch.randn(n * G, device=DEV).half()
+    x[: 100 * G] = 0
+    c = codec.compress(x, G)
+    tot, mean = C.c_double(), C.c_double()
+    assert L.speckv_ext_ratio_stats(c.comp_bytes.data_ptr(), n, G, C.byref(tot), C.byref(mean), None) == 0
+    comp = c.comp_bytes.cpu().numpy().view(np.uint32).astype(np.float64)
+    assert tot.value == comp.sum()
+    assert abs(mean.value - (G * 4.0 / comp).mean()) < 1e-9 * mean.value
+    # zeros: 2048 elements -> 9 pairs (255 cap) -> ratio 8192 / 18; N(0,1): ~2.0 (SURVEY.md section 6)
+    assert comp[0] == 18 and 1.99 < (G * 4.0 / comp[200:]).mean() < 2.03
