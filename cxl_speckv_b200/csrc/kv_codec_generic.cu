@@ -26,7 +26,6 @@ constexpr int kEPT = 16;                     // elements per thread per tile (co
 constexpr int kTile = kThreads * kEPT;       // 4096 elements
 constexpr int kPPT = 8;                      // pairs per thread per chunk (decompress)
 constexpr int kChunk = kThreads * kPPT;      // 2048 pairs
-constexpr int kWindow = 4096;                // decompress staging window (elements)
 
 __device__ __forceinline__ uint4 ldg_stream(const uint4* p) {
     uint4 r;
@@ -280,8 +279,15 @@ decompress_rle_generic_kernel(const uint8_t* __restrict__ payload, size_t slot_b
                               uint32_t G, uint32_t n_groups, T* __restrict__ out,
                               uint32_t* __restrict__ out_elems, const uint32_t* __restrict__ only_flagged,
                               const uint32_t* __restrict__ src_index, const uint64_t* __restrict__ slot_offsets) {
+    // Output-stationary expansion: a chunk of 2048 pairs is scanned once (start position and
+    // starting code of every pair go to shared memory); then every thread produces 16 consecutive
+    // output elements at a time -- binary search for the pair covering its first element, then a
+    // walk -- so the cost per element does not depend on the run lengths (a block of zeros is 515
+    // pairs of 255 elements each) and the stores are whole 16-byte vectors.
     constexpr int V = 16 / sizeof(T);
-    __shared__ __align__(16) T stage[kWindow + V];
+    constexpr int kOut = 16;                         // elements per thread per window
+    // per pair: x = output position where it starts, y = code before it | value << 8 | count << 16
+    __shared__ uint2 s_ent[kChunk + 1];              // (+ end sentinel)
     __shared__ int wbuf[kWarps];
     const int tid = threadIdx.x;
 
@@ -297,7 +303,7 @@ decompress_rle_generic_kernel(const uint8_t* __restrict__ payload, size_t slot_b
         const bool vec_ok = (reinterpret_cast<uintptr_t>(gout) & 15) == 0;
         const bool in_vec_ok = (reinterpret_cast<uintptr_t>(gp) & 15) == 0;
 
-        uint32_t out_pos = 0, acc = 0, stage_base = 0;
+        uint32_t out_pos = 0, acc = 0;
         for (uint32_t c0 = 0; c0 < npairs && out_pos < G; c0 += kChunk) {
             const uint32_t pbase = c0 + tid * kPPT;
             const int np = pbase < npairs ? min((uint32_t)kPPT, npairs - pbase) : 0;
@@ -309,63 +315,67 @@ decompress_rle_generic_kernel(const uint8_t* __restrict__ payload, size_t slot_b
                 const uint16_t* p16 = reinterpret_cast<const uint16_t*>(gp) + pbase;
                 for (int k = 0; k < np; ++k) w[k >> 1] |= (uint32_t)p16[k] << (16 * (k & 1));
             }
-            uint32_t val[kPPT], cntv[kPPT];
             uint32_t C = 0, S = 0;
 #pragma unroll
             for (int k = 0; k < kPPT; ++k) {
                 const uint32_t pr = (w[k >> 1] >> (16 * (k & 1))) & 0xffffu;
-                val[k] = pr & 0xffu;
-                cntv[k] = pr >> 8;
-                C += cntv[k];
-                S += val[k] * cntv[k];
+                C += pr >> 8;
+                S += (pr & 0xffu) * (pr >> 8);
             }
             int totC, totS;
-            const uint32_t exclC = (uint32_t)block_excl_sum((int)C, totC, wbuf);
-            const uint32_t exclS = (uint32_t)block_excl_sum((int)S, totS, wbuf);
-            const uint32_t chunk_end = (uint32_t)min((uint64_t)out_pos + (uint64_t)totC, (uint64_t)G);
-            const uint32_t my_start = out_pos + exclC;
-            const uint32_t qbase = acc + exclS;
-
-            uint32_t cur = out_pos;
-            while (true) {
-                const uint32_t hi = min(chunk_end, stage_base + (uint32_t)kWindow);
-                uint32_t p = my_start, qb = qbase;
+            uint32_t p = out_pos + (uint32_t)block_excl_sum((int)C, totC, wbuf);
+            uint32_t qb = acc + (uint32_t)block_excl_sum((int)S, totS, wbuf);
 #pragma unroll
-                for (int k = 0; k < kPPT; ++k) {
-                    const uint32_t lo = max(p, cur), e = min(p + cntv[k], hi);
-                    for (uint32_t pos = lo; pos < e; ++pos) {
-                        const uint32_t code = (qb + val[k] * (pos - p + 1)) & 0xffu;
-                        stage[pos - stage_base] = narrow<T>(special ? dequantize_special(code, s) : dequantize(code, s));
-                    }
-                    p += cntv[k];
-                    qb += val[k] * cntv[k];
-                }
-                __syncthreads();
-                const uint32_t flushable = hi - stage_base;
-                const uint32_t nvec = flushable / V;
-                if (vec_ok) {
-                    uint4* dst = reinterpret_cast<uint4*>(gout + stage_base);
-                    const uint4* src = reinterpret_cast<const uint4*>(stage);
-                    for (uint32_t v = tid; v < nvec; v += kThreads) dst[v] = src[v];
-                } else {
-                    for (uint32_t i = tid; i < nvec * V; i += kThreads) gout[stage_base + i] = stage[i];
-                }
-                const uint32_t rem = flushable - nvec * V;
-                T keep = stage[0];
-                if ((uint32_t)tid < rem) keep = stage[nvec * V + tid];
-                __syncthreads();
-                if ((uint32_t)tid < rem) stage[tid] = keep;
-                stage_base += nvec * V;
-                cur = hi;
-                __syncthreads();
-                if (cur >= chunk_end) break;
+            for (int k = 0; k < kPPT; ++k) {
+                const uint32_t pr = (w[k >> 1] >> (16 * (k & 1))) & 0xffffu;
+                s_ent[tid * kPPT + k] = make_uint2(p, (qb & 0xffu) | (pr << 8));
+                p += pr >> 8;
+                qb += (pr & 0xffu) * (pr >> 8);
             }
+            if (tid == kThreads - 1) s_ent[kChunk] = make_uint2(p, 0u);   // == out_pos + totC
+            __syncthreads();
+            const uint32_t chunk_end = (uint32_t)min((uint64_t)out_pos + (uint64_t)totC, (uint64_t)G);
+            // windows of kThreads * kOut elements aligned to the group start
+            for (uint32_t w0 = (out_pos / (kThreads * kOut)) * (kThreads * kOut); w0 < chunk_end; w0 += kThreads * kOut) {
+                const uint32_t e0 = w0 + tid * kOut;
+                const uint32_t lo = max(e0, out_pos), hi = min(e0 + kOut, chunk_end);
+                if (lo >= hi) continue;
+                // last pair whose start is <= lo (pairs with count 0 share their start with the next one)
+                uint32_t a = 0, b = kChunk;   // invariant: pos[a] <= lo < pos[b]
+                while (b - a > 1) {
+                    const uint32_t mid = (a + b) >> 1;
+                    if (s_ent[mid].x <= lo) a = mid; else b = mid;
+                }
+                uint32_t j = a;
+                uint2 en = s_ent[j];          // en.y: code before | value << 8 | count << 16
+                T vals[kOut];
+#pragma unroll
+                for (int i = 0; i < kOut; ++i) {
+                    const uint32_t e = e0 + i;
+                    if (e >= lo && e < hi) {
+                        while (e >= en.x + (en.y >> 16)) en = s_ent[++j];   // next pair (skips empty ones)
+                        const uint32_t code = en.y + ((en.y >> 8) & 0xffu) * (e - en.x + 1u);
+                        vals[i] = narrow<T>(special ? dequantize_special(code & 0xffu, s) : dequantize(code, s));
+                    } else {
+                        vals[i] = narrow<T>(0.0f);
+                    }
+                }
+                if (vec_ok && lo == e0 && hi == e0 + kOut) {
+                    uint4* dst = reinterpret_cast<uint4*>(gout + e0);
+                    const uint4* src = reinterpret_cast<const uint4*>(vals);
+#pragma unroll
+                    for (int v = 0; v < kOut / V; ++v) dst[v] = src[v];
+                } else {
+#pragma unroll
+                    for (int i = 0; i < kOut; ++i)
+                        if (e0 + i >= lo && e0 + i < hi) gout[e0 + i] = vals[i];
+                }
+            }
+            __syncthreads();   // the chunk tables are rewritten by the next chunk
             out_pos = chunk_end;
             acc = (acc + (uint32_t)totS) & 0xffu;
         }
-        if ((uint32_t)tid < out_pos - stage_base) gout[stage_base + tid] = stage[tid];
         if (tid == 0 && out_elems) out_elems[g] = out_pos;
-        __syncthreads();
     }
 }
 

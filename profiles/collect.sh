@@ -21,4 +21,5 @@ python bench.py --workload cfg3 --steps 10 --no-cpu > gpurun_out/bench_cfg3.json
 python bench.py --workload cfg4p --steps 5 --no-cpu > gpurun_out/bench_cfg4p.json 2>&1
 python bench.py --workload cfg4 > gpurun_out/bench_cfg4.json 2>&1
 python bench.py --workload cfg5 > gpurun_out/bench_cfg5.json 2>&1
+python bench.py --workload ratios > gpurun_out/bench_ratios.json 2>&1
 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_reference.json 2>&1
