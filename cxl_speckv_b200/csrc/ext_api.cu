@@ -139,7 +139,11 @@ void release_host_pipe() {
 
 // groups per chunk: aim at ~32 MiB of elements so H2D, kernel and D2H of neighbouring chunks overlap
 static size_t chunk_groups(size_t group_bytes, size_t n_groups) {
-    const size_t target = 32ull << 20;
+    static const size_t target = [] {
+        const char* e = std::getenv("SPECKV_HOST_CHUNK_MIB");
+        const long v = e ? std::atol(e) : 0;
+        return (size_t)(v > 0 ? v : 64) << 20;
+    }();
     size_t c = group_bytes ? target / group_bytes : n_groups;
     if (c < 1) c = 1;
     if (c > n_groups) c = n_groups;
