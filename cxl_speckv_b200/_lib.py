@@ -100,6 +100,11 @@ def lib() -> C.CDLL:
     L.speckv_ext_atu_get_stats.argtypes = [vp, u64p, u64p, C.c_int]; L.speckv_ext_atu_get_stats.restype = C.c_int
     L.speckv_ext_ratio_stats.argtypes = [vp, sz, sz, C.POINTER(C.c_double), C.POINTER(C.c_double), vp]
     L.speckv_ext_ratio_stats.restype = C.c_int
+    L.speckv_ext_bind_pool.argtypes = [C.c_uint64, vp, sz, vp]; L.speckv_ext_bind_pool.restype = C.c_int
+    L.speckv_ext_set_kv_layout.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32]
+    L.speckv_ext_set_kv_layout.restype = C.c_int
+    L.speckv_ext_offload_pages.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, vp]; L.speckv_ext_offload_pages.restype = C.c_int
+    L.speckv_ext_fetch_pages.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, vp]; L.speckv_ext_fetch_pages.restype = C.c_int
     L.speckv_ext_get_stats.argtypes = [C.POINTER(Stats)]; L.speckv_ext_get_stats.restype = None
     L.speckv_ext_reset_stats.argtypes = []; L.speckv_ext_reset_stats.restype = None
     _LIB = L

@@ -12,7 +12,10 @@
 #include <deque>
 #include <memory>
 #include <mutex>
+#include <algorithm>
 #include <string>
+#include <unordered_map>
+#include <vector>
 
 #include "../../include/speckv_ext.h"
 #include "device_ctx.h"
@@ -28,8 +31,17 @@ struct PrefetchRecord {            // == SpeckvPrefetchReq + tokens, speckv_driv
     std::vector<int32_t> tokens;
 };
 
+struct PoolBinding {               // device memory behind a handle + the host tier its pages spill to
+    uint8_t* d_base = nullptr;
+    size_t bytes = 0;
+    speckv_tier_t* tier = nullptr;
+    // KV layout of the region, [req][layer][kind][pos][head] x entry_bytes (vllm_speckv_backend.py:95-100)
+    uint32_t num_layers = 0, num_tokens = 0, num_heads = 0, entry_bytes = 0;
+};
+
 struct Runtime {
     PageTable table;
+    std::unordered_map<uint64_t, PoolBinding> pools;
     int fd = -1;                   // the opened dev_path, when it is a filesystem path
     int cuda_device = -1;          // -1: no CUDA device (host bookkeeping only; setters fail like a dead ioctl)
     uint32_t prefetch_depth = 4;   // SpeculativePrefetcher default, speculative_prefetcher.h:36
@@ -40,6 +52,40 @@ struct Runtime {
 
 static std::mutex g_mutex;
 static std::unique_ptr<Runtime> g_rt;
+
+constexpr size_t kPageElems = kPageSize / 2;   // one 4 KiB page = one group of 2048 fp16 values
+
+// make pages [p0, p1) of `a` resident in the bound pool: pages whose only copy is the compressed one
+// in the host tier (flag bit2 set, bits 0-1 clear) are restored, then marked L2 (the reference's
+// sync_fetch_page, speckv_allocator.cpp:115-138, with a real transfer behind it)
+static speckv_status_t fetch_pages_locked(Runtime& rt, uint64_t handle, KvAllocation& a, const PoolBinding& pb,
+                                          uint64_t p0, uint64_t p1, cudaStream_t st) {
+    (void)rt;
+    (void)handle;
+    std::vector<uint64_t> ids;
+    uint64_t run_start = p0;
+    auto flush = [&](uint64_t end) -> speckv_status_t {
+        if (ids.empty()) return SPECKV_OK;
+        speckv_status_t rc = speckv_ext_tier_restore(pb.tier, ids.data(), ids.size(), kPageElems, SPECKV_DTYPE_F16,
+                                                     pb.d_base + run_start * kPageSize, st);
+        (void)end;
+        ids.clear();
+        return rc;
+    };
+    for (uint64_t p = p0; p < p1; ++p) {
+        KvPage& pg = a.pages[p];
+        const bool resident = (pg.flags & (kFlagL1 | kFlagL2)) != 0;
+        if (!resident && (pg.flags & kFlagCompressed) && pb.tier) {
+            if (ids.empty()) run_start = p;
+            ids.push_back(pg.virt_page_id);
+        } else {
+            speckv_status_t rc = flush(p);
+            if (rc != SPECKV_OK) return rc;
+        }
+        pg.flags |= kFlagL2;
+    }
+    return flush(p1);
+}
 
 Runtime* runtime_locked() { return g_rt.get(); }
 std::mutex& runtime_mutex() { return g_mutex; }
@@ -103,6 +149,17 @@ speckv_status_t speckv_alloc(size_t bytes, const speckv_alloc_hint_t* hint, spec
 speckv_status_t speckv_free(speckv_handle_t handle) {
     std::lock_guard<std::mutex> lock(g_mutex);
     if (!g_rt) return SPECKV_ERR_INVAL;
+    auto pit = g_rt->pools.find(handle);
+    if (pit != g_rt->pools.end()) {                  // drop the handle's blocks from the host tier
+        KvAllocation* a = g_rt->table.find(handle);
+        if (a && pit->second.tier) {
+            std::vector<uint64_t> ids;
+            for (const KvPage& pg : a->pages)
+                if (pg.flags & kFlagCompressed) ids.push_back(pg.virt_page_id);
+            if (!ids.empty()) speckv_ext_tier_drop(pit->second.tier, ids.data(), ids.size());
+        }
+        g_rt->pools.erase(pit);
+    }
     g_rt->table.free(handle);                        // unknown handle: OK, speckv_allocator.cpp:42
     return SPECKV_OK;
 }
@@ -110,6 +167,21 @@ speckv_status_t speckv_free(speckv_handle_t handle) {
 speckv_status_t speckv_access(speckv_handle_t handle, uint64_t offset_bytes, size_t length_bytes, void** out_gpu_ptr) {
     std::lock_guard<std::mutex> lock(g_mutex);
     if (!g_rt || !out_gpu_ptr) return SPECKV_ERR_INVAL;
+    auto pit = g_rt->pools.find(handle);
+    if (pit != g_rt->pools.end()) {
+        // a device pool is bound: return a dereferenceable pointer, restoring the pages from the host
+        // tier first when their only copy is the compressed one
+        KvAllocation* a = g_rt->table.find(handle);
+        if (!a) return SPECKV_ERR_GENERAL;
+        const uint64_t p0 = offset_bytes / kPageSize;
+        if (p0 >= a->pages.size()) return SPECKV_ERR_GENERAL;
+        uint64_t p1 = (offset_bytes + (length_bytes ? length_bytes : 1) + kPageSize - 1) / kPageSize;
+        if (p1 > a->pages.size()) p1 = a->pages.size();
+        speckv_status_t rc = fetch_pages_locked(*g_rt, handle, *a, pit->second, p0, p1, nullptr);
+        if (rc != SPECKV_OK) return rc;
+        *out_gpu_ptr = pit->second.d_base + offset_bytes;
+        return SPECKV_OK;
+    }
     bool fetched = false;
     const uint64_t addr = g_rt->table.access(handle, offset_bytes, length_bytes, &fetched);
     if (!addr) return SPECKV_ERR_GENERAL;            // *out_gpu_ptr untouched, speckv_c_api.cpp:76-79
@@ -130,6 +202,28 @@ speckv_status_t speckv_prefetch(uint32_t req_id, uint16_t layer, uint32_t cur_po
     g_rt->prefetch_log.push_back(std::move(r));
     if (g_rt->prefetch_log.size() > 16) g_rt->prefetch_log.pop_front();
     ++g_rt->prefetch_total;
+    // With a pool + KV layout bound, make the KV entries of the next depth_k positions of this
+    // (request, layer) resident: the reference's prefetcher requests positions cur+1 .. cur+k
+    // (compute_kv_address(req, layer, i + 1), speculative_prefetcher.cpp:48,153-160).
+    for (auto& kv : g_rt->pools) {
+        PoolBinding& pb = kv.second;
+        if (!pb.num_tokens || !pb.tier) continue;
+        KvAllocation* a = g_rt->table.find(kv.first);
+        if (!a || layer >= pb.num_layers) continue;
+        for (uint32_t kind = 0; kind < 2; ++kind) {
+            const uint64_t first_pos = (uint64_t)cur_pos + 1;
+            if (first_pos >= pb.num_tokens) continue;
+            const uint64_t last_pos = std::min<uint64_t>((uint64_t)cur_pos + depth_k, pb.num_tokens - 1);
+            const uint64_t row = (((uint64_t)req_id * pb.num_layers + layer) * 2 + kind) * pb.num_tokens;
+            const uint64_t off0 = (row + first_pos) * pb.num_heads * pb.entry_bytes;
+            const uint64_t off1 = (row + last_pos + 1) * pb.num_heads * pb.entry_bytes;
+            const uint64_t p0 = off0 / kPageSize;
+            uint64_t p1 = (off1 + kPageSize - 1) / kPageSize;
+            if (p0 >= a->pages.size()) continue;
+            if (p1 > a->pages.size()) p1 = a->pages.size();
+            fetch_pages_locked(*g_rt, kv.first, *a, pb, p0, p1, nullptr);   // status discarded like the reference
+        }
+    }
     return SPECKV_OK;                                // the reference discards the driver's status, speckv_allocator.cpp:89
 }
 
@@ -148,6 +242,89 @@ speckv_status_t speckv_set_compression_scheme(speckv_comp_scheme_t scheme) {
     if ((int)scheme < 0 || (int)scheme > 2) return SPECKV_ERR_DRIVER;  // the device has no such mode
     g_rt->scheme = (int)scheme;
     return SPECKV_OK;
+}
+
+speckv_status_t speckv_ext_bind_pool(speckv_handle_t handle, void* d_base, size_t bytes, speckv_tier_t* tier) {
+    std::lock_guard<std::mutex> lock(g_mutex);
+    if (!g_rt) return SPECKV_ERR_INVAL;
+    if (g_rt->cuda_device < 0) return SPECKV_ERR_DRIVER;
+    KvAllocation* a = g_rt->table.find(handle);
+    if (!a) return SPECKV_ERR_GENERAL;
+    if (!d_base || (reinterpret_cast<uintptr_t>(d_base) & 15) || bytes < a->pages.size() * kPageSize) return SPECKV_ERR_INVAL;
+    PoolBinding pb;
+    pb.d_base = static_cast<uint8_t*>(d_base);
+    pb.bytes = bytes;
+    pb.tier = tier;
+    auto it = g_rt->pools.find(handle);
+    if (it != g_rt->pools.end()) {   // keep a layout that was set before re-binding
+        pb.num_layers = it->second.num_layers;
+        pb.num_tokens = it->second.num_tokens;
+        pb.num_heads = it->second.num_heads;
+        pb.entry_bytes = it->second.entry_bytes;
+    }
+    g_rt->pools[handle] = pb;
+    for (KvPage& pg : a->pages) pg.flags |= kFlagL1;   // the pool's current contents are the resident copy
+    return SPECKV_OK;
+}
+
+speckv_status_t speckv_ext_set_kv_layout(speckv_handle_t handle, uint32_t num_layers, uint32_t num_tokens,
+                                         uint32_t num_heads, uint32_t entry_bytes) {
+    std::lock_guard<std::mutex> lock(g_mutex);
+    if (!g_rt) return SPECKV_ERR_INVAL;
+    auto it = g_rt->pools.find(handle);
+    if (it == g_rt->pools.end()) return SPECKV_ERR_GENERAL;
+    if (!num_layers || !num_tokens || !num_heads || !entry_bytes) return SPECKV_ERR_INVAL;
+    it->second.num_layers = num_layers;
+    it->second.num_tokens = num_tokens;
+    it->second.num_heads = num_heads;
+    it->second.entry_bytes = entry_bytes;
+    return SPECKV_OK;
+}
+
+speckv_status_t speckv_ext_offload_pages(speckv_handle_t handle, uint64_t first_page, uint64_t n_pages, void* cuda_stream) {
+    std::lock_guard<std::mutex> lock(g_mutex);
+    if (!g_rt) return SPECKV_ERR_INVAL;
+    auto it = g_rt->pools.find(handle);
+    KvAllocation* a = g_rt->table.find(handle);
+    if (it == g_rt->pools.end() || !a) return SPECKV_ERR_GENERAL;
+    const PoolBinding& pb = it->second;
+    if (!pb.tier) return SPECKV_ERR_INVAL;
+    if (first_page >= a->pages.size()) return SPECKV_ERR_GENERAL;
+    const uint64_t last = std::min<uint64_t>(first_page + n_pages, a->pages.size());
+    // only pages whose resident copy is current are worth offloading; runs of them go in one call
+    std::vector<uint64_t> ids;
+    uint64_t run_start = first_page;
+    auto flush = [&]() -> speckv_status_t {
+        if (ids.empty()) return SPECKV_OK;
+        speckv_status_t rc = speckv_ext_tier_offload(pb.tier, pb.d_base + run_start * kPageSize, SPECKV_DTYPE_F16, kPageElems,
+                                                     ids.size(), ids.data(), cuda_stream);
+        if (rc == SPECKV_OK)
+            for (uint64_t p = run_start; p < run_start + ids.size(); ++p)
+                a->pages[p].flags = (a->pages[p].flags & ~(kFlagL1 | kFlagL2)) | kFlagCompressed;
+        ids.clear();
+        return rc;
+    };
+    for (uint64_t p = first_page; p < last; ++p) {
+        if (a->pages[p].flags & (kFlagL1 | kFlagL2)) {
+            if (ids.empty()) run_start = p;
+            ids.push_back(a->pages[p].virt_page_id);
+        } else {
+            speckv_status_t rc = flush();
+            if (rc != SPECKV_OK) return rc;
+        }
+    }
+    return flush();
+}
+
+speckv_status_t speckv_ext_fetch_pages(speckv_handle_t handle, uint64_t first_page, uint64_t n_pages, void* cuda_stream) {
+    std::lock_guard<std::mutex> lock(g_mutex);
+    if (!g_rt) return SPECKV_ERR_INVAL;
+    auto it = g_rt->pools.find(handle);
+    KvAllocation* a = g_rt->table.find(handle);
+    if (it == g_rt->pools.end() || !a) return SPECKV_ERR_GENERAL;
+    if (first_page >= a->pages.size()) return SPECKV_ERR_GENERAL;
+    const uint64_t last = std::min<uint64_t>(first_page + n_pages, a->pages.size());
+    return fetch_pages_locked(*g_rt, handle, *a, it->second, first_page, last, static_cast<cudaStream_t>(cuda_stream));
 }
 
 speckv_status_t speckv_ext_page_table_export(speckv_handle_t handle, speckv_page_t* d_pages, size_t capacity,

@@ -57,6 +57,34 @@ class CxlSpeckvKVAllocator:
         if ret != 0:
             raise RuntimeError(f"speckv_prefetch failed: {ret}")
 
+    # ---- additive: serve real device pointers (not in the reference) ----
+    def bind_pool(self, pool, tier=None):
+        """Back the allocated region with a CUDA tensor (`pool`, >= the region's bytes).  After this
+        get_kv_ptr() returns addresses inside `pool`; with a HostTier, pages can be demoted with
+        offload_pages() and come back on access / prefetch_step()."""
+        lib = self._speckv.lib
+        lib.speckv_ext_bind_pool.argtypes = [ctypes.c_uint64, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]
+        lib.speckv_ext_bind_pool.restype = ctypes.c_int
+        lib.speckv_ext_set_kv_layout.argtypes = [ctypes.c_uint64] + [ctypes.c_uint32] * 4
+        lib.speckv_ext_set_kv_layout.restype = ctypes.c_int
+        ret = lib.speckv_ext_bind_pool(self._handle, pool.data_ptr(), pool.numel() * pool.element_size(),
+                                       tier._h if tier is not None else None)
+        if ret != 0:
+            raise RuntimeError(f"speckv_ext_bind_pool failed: {ret}")
+        ret = lib.speckv_ext_set_kv_layout(self._handle, self._num_layers, self._num_tokens, self._num_heads,
+                                           self._head_dim * self._bytes_per_element)
+        if ret != 0:
+            raise RuntimeError(f"speckv_ext_set_kv_layout failed: {ret}")
+        self._pool = pool
+
+    def offload_pages(self, first_page: int, n_pages: int):
+        lib = self._speckv.lib
+        lib.speckv_ext_offload_pages.argtypes = [ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_void_p]
+        lib.speckv_ext_offload_pages.restype = ctypes.c_int
+        ret = lib.speckv_ext_offload_pages(self._handle, first_page, n_pages, None)
+        if ret != 0:
+            raise RuntimeError(f"speckv_ext_offload_pages failed: {ret}")
+
     def _calc_offset(self, req_id: int, layer: int, head: int, pos: int, kind: int, entry_bytes: int) -> int:
         # [req][layer][kind][pos][head] * entry_bytes  (reference :95-100)
         return ((((req_id * self._num_layers + layer) * 2 + kind) * self._num_tokens + pos)

@@ -184,6 +184,27 @@ SPECKV_API speckv_status_t speckv_ext_tier_restore(speckv_tier_t* tier, const ui
 SPECKV_API speckv_status_t speckv_ext_tier_drop(speckv_tier_t* tier, const uint64_t* h_block_ids, size_t n);
 SPECKV_API void speckv_ext_tier_get_stats(speckv_tier_t* tier, speckv_tier_stats_t* out);
 
+/* ---- serving real pointers through the frozen ABI ----------------------------------------- */
+/* Binds device memory to a speckv_alloc handle.  From then on
+ * speckv_access(handle, offset, len, &ptr) returns d_base + offset -- a dereferenceable device
+ * pointer instead of the reference's synthetic 0x40..-address -- after making the touched pages
+ * resident: a page whose only copy is the compressed one in `tier` is restored first (the
+ * reference's sync_fetch_page with a real transfer).  `tier` may be NULL (no spilling).
+ * bytes >= pages * 4096; the pool's current contents count as resident. */
+SPECKV_API speckv_status_t speckv_ext_bind_pool(speckv_handle_t handle, void* d_base, size_t bytes,
+                                                speckv_tier_t* tier);
+/* KV layout of the bound region, [req][layer][kind][pos][head] x entry_bytes
+ * (host/python/vllm_speckv_backend.py:95-100); lets speckv_prefetch() turn (req, layer, cur_pos,
+ * depth_k) into the pages of positions cur_pos+1 .. cur_pos+depth_k and make them resident. */
+SPECKV_API speckv_status_t speckv_ext_set_kv_layout(speckv_handle_t handle, uint32_t num_layers, uint32_t num_tokens,
+                                                    uint32_t num_heads, uint32_t entry_bytes);
+/* Demote pages to the host tier (compress + move; flags: L1/L2 cleared, compressed set) /
+ * promote them back (restore; flags: L2 set).  Pages are fp16 groups of 2048 elements. */
+SPECKV_API speckv_status_t speckv_ext_offload_pages(speckv_handle_t handle, uint64_t first_page, uint64_t n_pages,
+                                                    void* cuda_stream);
+SPECKV_API speckv_status_t speckv_ext_fetch_pages(speckv_handle_t handle, uint64_t first_page, uint64_t n_pages,
+                                                  void* cuda_stream);
+
 /* ---- speculative prefetch scoring ---------------------------------------------------- */
 /* Installs the predictor's weights on the current device: embedding [vocab][emb_dim] and
  * output projection [vocab][hidden], fp32, row-major -- the two tables

@@ -68,3 +68,68 @@ def test_pool_exhaustion_is_reported():
         assert ei.value.status == -3                       # SPECKV_ERR_NOMEM
     finally:
         tier.close()
+
+
+def test_frozen_api_serves_real_pointers_with_page_faults():
+    """speckv_alloc/access/prefetch over a bound HBM pool + host tier: get_kv_ptr returns addresses
+    inside the pool, demoted pages come back (decompressed) on access and on prefetch_step."""
+    import ctypes as C
+
+    import cxl_speckv_b200 as pkg
+    from cxl_speckv_b200 import CxlSpeckvKVAllocator
+
+    alloc = CxlSpeckvKVAllocator(pkg.lib_path(), "cuda:0")
+    L = pkg.lib()
+    tier = HostTier(16 << 20)
+    try:
+        tokens, layers, heads, hd = 256, 2, 8, 128
+        h = alloc.allocate(tokens, layers, heads, hd, 2)
+        total = tokens * layers * heads * hd * 2 * 2                   # bytes (K+V)
+        n_pages = total // 4096
+        torch.manual_seed(5)
+        pool = torch.randn(total // 2, device=DEV).half()
+        want = codec.decompress(codec.compress(pool, 2048)).clone()    # what a page looks like after a round trip
+        orig = pool.clone()
+        alloc.bind_pool(pool, tier)
+        entry = hd * 2
+        off = alloc._calc_offset(0, 1, 3, 7, 1, entry)
+        assert alloc.get_kv_ptr(0, 1, 3, 7, 1, entry) == pool.data_ptr() + off      # a real device pointer
+        assert torch.equal(pool, orig)                                               # resident pages are untouched
+
+        alloc.offload_pages(0, n_pages)                                              # demote everything
+        assert tier.stats()["blocks"] == n_pages
+        pool.zero_()                                                                 # the HBM copy is gone
+        p = alloc.get_kv_ptr(0, 1, 3, 7, 1, entry)                                   # page fault -> restore
+        page = off // 4096
+        assert p == pool.data_ptr() + off
+        got = pool.view(n_pages, 2048)
+        assert torch.equal(got[page].view(torch.int16), want[page].view(torch.int16))
+        others = torch.ones(n_pages, dtype=torch.bool, device=DEV)
+        others[page] = False
+        assert (got[others] == 0).all()                                              # only that page came back
+
+        # prefetch_step makes positions cur+1 .. cur+k of (req, layer) resident for K and V
+        alloc.prefetch_step(req_id=0, layer=0, cur_pos=10, recent_tokens=list(range(16)), depth_k=4)
+        for kind in (0, 1):
+            o0 = alloc._calc_offset(0, 0, 0, 11, kind, entry)
+            o1 = alloc._calc_offset(0, 0, 0, 15, kind, entry)
+            for pg in range(o0 // 4096, (o1 + 4095) // 4096):
+                assert torch.equal(got[pg].view(torch.int16), want[pg].view(torch.int16)), (kind, pg)
+        # page-table flags: demoted = compressed only (4); restored = L2 | compressed (6)
+        tbl = torch.zeros(n_pages * 3, dtype=torch.int64, device=DEV)
+        cnt = C.c_size_t()
+        assert L.speckv_ext_page_table_export(h, tbl.data_ptr(), n_pages, C.byref(cnt), None) == 0
+        flags = (tbl.cpu().numpy().view(np.uint64).reshape(n_pages, 3)[:, 2] >> np.uint64(32)).astype(np.int64)
+        assert flags[page] == 6 and set(np.unique(flags).tolist()) == {4, 6}
+        # explicit promote of a range, then a span crossing pages
+        assert L.speckv_ext_fetch_pages(h, 100, 8, None) == 0
+        assert torch.equal(got[100:108].view(torch.int16), want[100:108].view(torch.int16))
+        ptr = C.c_void_p()
+        assert L.speckv_access(h, 200 * 4096 + 4000, 5000, C.byref(ptr)) == 0        # touches pages 200..202
+        assert torch.equal(got[200:203].view(torch.int16), want[200:203].view(torch.int16))
+        assert L.speckv_access(h, total, 1, C.byref(ptr)) == -1                       # past the end: as the reference
+        assert L.speckv_free(h) == 0
+        assert tier.stats()["blocks"] == 0                                            # the handle's blocks left the tier
+    finally:
+        alloc._speckv.finalize()
+        tier.close()
