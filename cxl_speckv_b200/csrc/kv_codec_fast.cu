@@ -164,6 +164,12 @@ template <typename T> __device__ __forceinline__ uint16_t out_bits(float a) {
     return *reinterpret_cast<uint16_t*>(&h);
 }
 
+// Split cluster barrier: every CTA arrives when it starts and waits just before its first
+// distributed-shared-memory store, which may only target a CTA that has begun executing.
+// By then the peers have long arrived, so the wait costs nothing.
+__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+
 // synchronise the warps (CTAs) that share a group
 template <int R>
 __device__ __forceinline__ void group_sync() {
@@ -318,6 +324,7 @@ compress_fast_kernel(const T* __restrict__ in, uint32_t n_groups, uint8_t* __res
     uint8_t* reg = sm.tile[warp] + kPadBytes;
     const uint32_t reg_s = smem_u32(reg);
     const uint32_t mb = smem_u32(&sm.mbar[warp]);
+    if (C > 1) cluster_arrive();
 
     // ---- 0. one bulk-TMA copy per region -------------------------------------------------------
     if (lane == 0) {
@@ -341,6 +348,7 @@ compress_fast_kernel(const T* __restrict__ in, uint32_t n_groups, uint8_t* __res
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(kFull, m, o));
     }
+    if (C > 1) cluster_wait();   // all CTAs of the cluster are running: their shared memory may be written
     group_publish<R>(sm.xa, warp, lane, ridx, __float_as_uint(m));   // non-negative floats order like their bits
     group_sync<R>();
     uint32_t t0, t1, gmax_bits;
@@ -542,6 +550,7 @@ decompress_fast_kernel(const uint8_t* __restrict__ payload, size_t slot_bytes, c
     uint8_t* reg = sm.tile[warp] + kPadBytes;
     const uint32_t reg_s = smem_u32(reg);
     const uint32_t mb = smem_u32(&sm.mbar[warp]);
+    if (C > 1) cluster_arrive();
 
     // pairs of this region: [ridx * 2048, ridx * 2048 + np)
     uint32_t np = 0;
@@ -611,6 +620,7 @@ decompress_fast_kernel(const uint8_t* __restrict__ payload, size_t slot_bytes, c
         // in-place staging needs the output stream to stay within kPadBytes of the read position
         if (csum - nnz > (uint32_t)(kPadBytes / 2 - 8)) cplx = true;
     }
+    if (C > 1) cluster_wait();   // all CTAs of the cluster are running: their shared memory may be written
     group_publish<R>(sm.xa, warp, lane, ridx, min(csum, G + 1u));   // saturated: sums stay < 2^32, "> G" still shows
     group_publish<R>(sm.xb, warp, lane, ridx, ssum | (cplx ? (1u << 24) : 0u));
     group_sync<R>();
