@@ -46,6 +46,7 @@ struct Runtime {
     int cuda_device = -1;          // -1: no CUDA device (host bookkeeping only; setters fail like a dead ioctl)
     uint32_t prefetch_depth = 4;   // SpeculativePrefetcher default, speculative_prefetcher.h:36
     int scheme = SPECKV_COMP_INT8_DELTA_RLE;
+    std::deque<uint8_t> accuracy;  // last 100 prediction outcomes (speculative_prefetcher.cpp:99-104)
     std::deque<PrefetchRecord> prefetch_log;   // bounded: 16 outstanding, speculative_prefetcher.cpp:168-171
     uint64_t prefetch_total = 0;
 };
@@ -241,6 +242,33 @@ speckv_status_t speckv_set_compression_scheme(speckv_comp_scheme_t scheme) {
     if (g_rt->cuda_device < 0) return SPECKV_ERR_DRIVER;
     if ((int)scheme < 0 || (int)scheme > 2) return SPECKV_ERR_DRIVER;  // the device has no such mode
     g_rt->scheme = (int)scheme;
+    return SPECKV_OK;
+}
+
+// SpeculativePrefetcher::update_prediction_accuracy (speculative_prefetcher.cpp:99-120): window of
+// 100 outcomes; after every outcome, once 10 are known: mean of the last 10 > 0.95 and depth < 8 ->
+// depth + 1; < 0.85 and depth > 2 -> depth - 1.
+speckv_status_t speckv_ext_prefetch_feedback(int was_correct, uint32_t* out_depth) {
+    std::lock_guard<std::mutex> lock(g_mutex);
+    if (!g_rt) return SPECKV_ERR_INVAL;
+    Runtime& rt = *g_rt;
+    rt.accuracy.push_back(was_correct ? 1 : 0);
+    if (rt.accuracy.size() > 100) rt.accuracy.pop_front();
+    if (rt.accuracy.size() >= 10) {
+        double acc = 0.0;
+        for (size_t i = rt.accuracy.size() - 10; i < rt.accuracy.size(); ++i) acc += rt.accuracy[i];
+        acc /= 10.0;
+        if (acc > 0.95 && rt.prefetch_depth < 8) ++rt.prefetch_depth;
+        else if (acc < 0.85 && rt.prefetch_depth > 2) --rt.prefetch_depth;
+    }
+    if (out_depth) *out_depth = rt.prefetch_depth;
+    return SPECKV_OK;
+}
+
+speckv_status_t speckv_ext_get_prefetch_depth(uint32_t* out_depth) {
+    std::lock_guard<std::mutex> lock(g_mutex);
+    if (!g_rt || !out_depth) return SPECKV_ERR_INVAL;
+    *out_depth = g_rt->prefetch_depth;
     return SPECKV_OK;
 }
 

@@ -226,6 +226,13 @@ SPECKV_API speckv_status_t speckv_ext_prefetch_score(const uint32_t* d_tokens, u
                                                      uint32_t req_id, uint32_t layer_id, uint32_t* d_ids,
                                                      float* d_conf, uint64_t* d_va, void* cuda_stream);
 
+/* Adaptive prefetch depth (SpeculativePrefetcher::update_prediction_accuracy / get_adaptive_depth,
+ * speculative_prefetcher.cpp:99-124): report whether the last prediction was correct; the depth
+ * used by the prefetcher moves between 2 and 8 exactly as in the reference.  Host logic: works
+ * without a GPU.  speckv_set_prefetch_depth() overrides the current depth (:144-147). */
+SPECKV_API speckv_status_t speckv_ext_prefetch_feedback(int was_correct, uint32_t* out_depth);
+SPECKV_API speckv_status_t speckv_ext_get_prefetch_depth(uint32_t* out_depth);
+
 /* ---- statistics (EngineStatistics, cache_engine.h:65-72) --------------------- */
 typedef struct {
     uint64_t total_compressions;     /* groups compressed   */

@@ -114,7 +114,7 @@ def main():
     assert Ref.available(), "build oracle/_ref first: make -C oracle ref"
     os.makedirs(OUT, exist_ok=True)
     meta = {"generator": "oracle/make_golden.py", "source": "oracle/_ref (reference C++ model, unmodified)",
-            "codec": {}, "bulk": {}, "translate": {}, "capi": {}, "lstm": {}}
+            "codec": {}, "bulk": {}, "translate": {}, "capi": {}, "lstm": {}, "adaptive_depth": {}}
 
     # ---- codec fixtures ------------------------------------------------------------
     arrays = {}
@@ -239,6 +239,18 @@ def main():
     meta["lstm"]["prefetch"] = {"hist": hists[0], "layer": 5, "depth": 4, "va": va[:n].tolist(),
                                 "layer_out": lay[:n].tolist(), "tok": tok[:n].tolist(),
                                 "conf_bits": f32_bits(cf[:n]).tolist()}
+    # adaptive depth trace (update_prediction_accuracy / get_adaptive_depth)
+    lib.ref_prefetcher_feedback.argtypes = [C.c_void_p, C.c_int]
+    lib.ref_prefetcher_adaptive_depth.restype = C.c_size_t
+    lib.ref_prefetcher_adaptive_depth.argtypes = [C.c_void_p]
+    rng = np.random.default_rng(5)
+    outcomes = np.concatenate([rng.random(150) < 0.99, rng.random(150) < 0.5, rng.random(200) < 0.9,
+                               np.ones(60, bool)]).astype(int).tolist()
+    trace = []
+    for o in outcomes:
+        lib.ref_prefetcher_feedback(pf, int(o))
+        trace.append(int(lib.ref_prefetcher_adaptive_depth(pf)))
+    meta["adaptive_depth"] = {"initial": 4, "outcomes": outcomes, "depth_trace": trace}
     lib.ref_prefetcher_free(pf)
 
     with open(os.path.join(OUT, "golden.json"), "w") as f:

@@ -212,6 +212,12 @@ size_t ref_prefetcher_prefetch(void* p, const uint32_t* hist, size_t n_hist, uin
     }
     return r.size();
 }
+// adaptive depth: update_prediction_accuracy :99-120, get_adaptive_depth :122-124, set_prefetch_depth :144-147
+void ref_prefetcher_feedback(void* p, int was_correct) {
+    static_cast<RefPrefetcher*>(p)->pf.update_prediction_accuracy(0, was_correct != 0);
+}
+size_t ref_prefetcher_adaptive_depth(void* p) { return static_cast<RefPrefetcher*>(p)->pf.get_adaptive_depth(); }
+void ref_prefetcher_set_depth(void* p, size_t d) { static_cast<RefPrefetcher*>(p)->pf.set_prefetch_depth(d); }
 uint64_t ref_kv_address(void* p, uint32_t req, uint32_t layer, uint32_t pos) {
     return static_cast<RefPrefetcher*>(p)->pf.compute_kv_address(req, layer, pos);
 }

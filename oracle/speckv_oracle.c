@@ -448,6 +448,28 @@ uint64_t oracle_kv_address(uint32_t req_id, uint32_t layer_id, uint32_t position
     return ((uint64_t)req_id << 32) | ((uint64_t)layer_id << 16) | (uint64_t)position;
 }
 
+void oracle_depth_init(oracle_depth_t* d, unsigned depth) {
+    memset(d, 0, sizeof(*d));
+    d->depth = depth;
+}
+
+/* update_prediction_accuracy, speculative_prefetcher.cpp:99-120 */
+unsigned oracle_depth_feedback(oracle_depth_t* d, int was_correct) {
+    if (d->n == 100) {                      /* erase(begin()) once the window holds 100 */
+        memmove(d->hist, d->hist + 1, 99 * sizeof(int));
+        d->n = 99;
+    }
+    d->hist[d->n++] = was_correct ? 1 : 0;
+    if (d->n >= 10) {
+        double acc = 0.0;
+        for (int i = d->n - 10; i < d->n; ++i) acc += d->hist[i];
+        acc /= 10.0;
+        if (acc > 0.95 && d->depth < 8) d->depth++;
+        else if (acc < 0.85 && d->depth > 2) d->depth--;
+    }
+    return d->depth;
+}
+
 uint64_t oracle_fnv1a64(const void* p, size_t n) {
     const uint8_t* b = (const uint8_t*)p;
     uint64_t h = 0xcbf29ce484222325ULL;

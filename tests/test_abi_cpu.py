@@ -155,3 +155,35 @@ def test_python_mirror_classes(L):
             alloc.get_kv_ptr(5, 1, 3, 7, 1, entry)           # past the end of the region
     finally:
         alloc._speckv.finalize()
+
+
+def test_adaptive_prefetch_depth_matches_reference_trace(L, golden):
+    """speckv_ext_prefetch_feedback against the depth trace recorded from the reference's
+    SpeculativePrefetcher::update_prediction_accuracy (host logic, no GPU needed) and the oracle."""
+    import ctypes as C
+
+    from oracle.oracle import Port
+
+    ad = golden["meta"]["adaptive_depth"]
+    assert L.speckv_ext_prefetch_feedback(1, None) == pkg.SPECKV_ERR_INVAL       # before init
+    assert L.speckv_init(b"/dev/null") == 0
+    try:
+        d = C.c_uint32()
+        assert L.speckv_ext_get_prefetch_depth(C.byref(d)) == 0 and d.value == ad["initial"]
+        trace = []
+        for o in ad["outcomes"]:
+            assert L.speckv_ext_prefetch_feedback(int(o), C.byref(d)) == 0
+            trace.append(d.value)
+        assert trace == ad["depth_trace"]
+        assert min(trace) == 2 and max(trace) == 8
+    finally:
+        L.speckv_finalize()
+
+    class D(C.Structure):
+        _fields_ = [("hist", C.c_int * 100), ("n", C.c_int), ("depth", C.c_uint)]
+
+    P = Port.lib()
+    P.oracle_depth_feedback.restype = C.c_uint
+    st = D()
+    P.oracle_depth_init(C.byref(st), ad["initial"])
+    assert [int(P.oracle_depth_feedback(C.byref(st), int(o))) for o in ad["outcomes"]] == ad["depth_trace"]
