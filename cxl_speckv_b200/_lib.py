@@ -107,6 +107,9 @@ def lib() -> C.CDLL:
     L.speckv_ext_fetch_pages.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, vp]; L.speckv_ext_fetch_pages.restype = C.c_int
     L.speckv_ext_prefetch_feedback.argtypes = [C.c_int, u32p]; L.speckv_ext_prefetch_feedback.restype = C.c_int
     L.speckv_ext_get_prefetch_depth.argtypes = [u32p]; L.speckv_ext_get_prefetch_depth.restype = C.c_int
+    L.speckv_ext_submit_dma_batch.argtypes = [vp, vp, C.c_uint32, vp]; L.speckv_ext_submit_dma_batch.restype = C.c_int
+    L.speckv_ext_poll_complete.argtypes = []; L.speckv_ext_poll_complete.restype = C.c_uint32
+    L.speckv_ext_set_param.argtypes = [C.c_uint32, C.c_uint32]; L.speckv_ext_set_param.restype = C.c_int
     L.speckv_ext_get_stats.argtypes = [C.POINTER(Stats)]; L.speckv_ext_get_stats.restype = None
     L.speckv_ext_reset_stats.argtypes = []; L.speckv_ext_reset_stats.restype = None
     _LIB = L

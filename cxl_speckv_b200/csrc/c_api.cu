@@ -265,6 +265,20 @@ speckv_status_t speckv_ext_prefetch_feedback(int was_correct, uint32_t* out_dept
     return SPECKV_OK;
 }
 
+// SPECKV_IOCTL_SET_PARAM (driver/uapi/speckv_ioctl.h:36-43, handle_set_param
+// speckv_kernel_module.c:169-191): key 1 = prefetch depth, key 2 = compression scheme, anything
+// else is rejected (-EINVAL there, SPECKV_ERR_INVAL here; tests/test_params.c:68-84).
+speckv_status_t speckv_ext_set_param(uint32_t key, uint32_t value) {
+    switch (key) {
+        case 1: return speckv_set_prefetch_depth(value);
+        case 2: return speckv_set_compression_scheme(static_cast<speckv_comp_scheme_t>(value));
+        default: {
+            std::lock_guard<std::mutex> lock(g_mutex);
+            return SPECKV_ERR_INVAL;
+        }
+    }
+}
+
 speckv_status_t speckv_ext_get_prefetch_depth(uint32_t* out_depth) {
     std::lock_guard<std::mutex> lock(g_mutex);
     if (!g_rt || !out_depth) return SPECKV_ERR_INVAL;

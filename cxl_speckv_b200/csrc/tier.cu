@@ -11,6 +11,7 @@
 // the packed stream (per-block byte offsets, no unpack pass).  Chunks are double-buffered so the
 // PCIe copy of chunk i overlaps the codec kernels of chunk i+1.
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cstring>
 #include <mutex>
@@ -26,6 +27,7 @@ namespace speckv {
 namespace {
 
 constexpr int kPackThreads = 256;
+constexpr uint32_t kTierPage = 4096;
 
 // exclusive scan of the 16-byte-rounded payload sizes: one CTA, sequential over tiles of 1024
 __global__ void __launch_bounds__(1024)
@@ -73,9 +75,9 @@ pack_kernel(const uint8_t* __restrict__ slots, size_t slot_bytes, const uint32_t
 
 struct BlockRec {
     uint64_t pool_off;
-    uint32_t comp_bytes;
+    uint32_t comp_bytes;   // bytes held in the pool (payload bytes, or the raw size for raw blocks)
     float scale;
-    uint32_t group_elems;
+    uint32_t group_elems;  // 0 for raw (uncompressed) blocks
     int dtype;
 };
 
@@ -366,7 +368,7 @@ speckv_status_t speckv_ext_tier_restore(speckv_tier_t* tier, const uint64_t* h_b
         uint64_t run_src = 0, run_dst = 0, run_len = 0;
         for (size_t i = 0; i < ng; ++i) {
             auto it = t.blocks.find(h_block_ids[g0 + i]);
-            if (it == t.blocks.end() || it->second.group_elems != group_elems) return SPECKV_ERR_GENERAL;
+            if (it == t.blocks.end() || it->second.group_elems != group_elems) return SPECKV_ERR_GENERAL;   // unknown, raw, or other geometry
             const BlockRec& r = it->second;
             const uint64_t len = ((uint64_t)r.comp_bytes + 15u) & ~15ull;
             t.h_offsets[b][i] = dst;
@@ -430,6 +432,68 @@ speckv_status_t speckv_ext_tier_drop(speckv_tier_t* tier, const uint64_t* h_bloc
     t.stats.blocks = t.blocks.size();
     return SPECKV_OK;
 }
+
+// ---- descriptor interface (driver/uapi/speckv_ioctl.h:10-15, host/src/speckv_driver.cpp:24-47) ----
+static std::atomic<uint32_t> g_dma_done{0};
+
+speckv_status_t speckv_ext_submit_dma_batch(speckv_tier_t* tier, const speckv_dma_desc_t* h_descs, uint32_t count,
+                                            void* cuda_stream) {
+    if (device_count() <= 0) return SPECKV_ERR_DRIVER;
+    if (!tier || (!h_descs && count)) return SPECKV_ERR_INVAL;
+    if (count > 4096) return SPECKV_ERR_INVAL;                  // handle_dma_batch: -EINVAL, speckv_kernel_module.c:65-66
+    cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+    for (uint32_t i = 0; i < count; ++i) {
+        const speckv_dma_desc_t& d = h_descs[i];
+        if (d.bytes == 0 || d.bytes % kTierPage || !d.gpu_addr) return SPECKV_ERR_INVAL;
+        const uint32_t pages = d.bytes / kTierPage;
+        std::vector<uint64_t> ids(pages);
+        for (uint32_t p = 0; p < pages; ++p) ids[p] = d.fpga_addr + (uint64_t)p * kTierPage;
+        void* gpu = reinterpret_cast<void*>(d.gpu_addr);
+        speckv_status_t rc;
+        if (d.flags & SPECKV_DMA_COMPRESSED) {
+            rc = (d.flags & SPECKV_DMA_WRITE)
+                     ? speckv_ext_tier_offload(tier, gpu, SPECKV_DTYPE_F16, kTierPage / 2, pages, ids.data(), st)
+                     : speckv_ext_tier_restore(tier, ids.data(), pages, kTierPage / 2, SPECKV_DTYPE_F16, gpu, st);
+        } else {
+            // uncompressed pages: straight copies between the device and the pool
+            Tier& t = tier->t;
+            std::lock_guard<std::mutex> lk(t.mu);
+            rc = SPECKV_OK;
+            for (uint32_t p = 0; p < pages && rc == SPECKV_OK; ++p) {
+                uint8_t* dev = static_cast<uint8_t*>(gpu) + (size_t)p * kTierPage;
+                auto it = t.blocks.find(ids[p]);
+                if (d.flags & SPECKV_DMA_WRITE) {
+                    if (it != t.blocks.end()) {
+                        t.free_pool(it->second.pool_off, ((uint64_t)it->second.comp_bytes + 15u) & ~15ull);
+                        t.stats.used_bytes -= ((uint64_t)it->second.comp_bytes + 15u) & ~15ull;
+                        t.blocks.erase(it);
+                    }
+                    const size_t off = t.alloc_pool(kTierPage);
+                    if (off == SIZE_MAX) { rc = SPECKV_ERR_NOMEM; break; }
+                    rc = status_of(cudaMemcpyAsync(t.pool + off, dev, kTierPage, cudaMemcpyDeviceToHost, st));
+                    BlockRec r;
+                    r.pool_off = off;
+                    r.comp_bytes = kTierPage;
+                    r.scale = 1.0f;
+                    r.group_elems = 0;
+                    r.dtype = SPECKV_DTYPE_F16;
+                    t.blocks[ids[p]] = r;
+                    t.stats.used_bytes += kTierPage;
+                } else {
+                    if (it == t.blocks.end() || it->second.group_elems != 0) { rc = SPECKV_ERR_GENERAL; break; }
+                    rc = status_of(cudaMemcpyAsync(dev, t.pool + it->second.pool_off, kTierPage, cudaMemcpyHostToDevice, st));
+                }
+            }
+            if (rc == SPECKV_OK) rc = status_of(cudaStreamSynchronize(st));
+            t.stats.blocks = t.blocks.size();
+        }
+        if (rc != SPECKV_OK) return rc;
+        g_dma_done.fetch_add(1);
+    }
+    return SPECKV_OK;
+}
+
+uint32_t speckv_ext_poll_complete(void) { return g_dma_done.exchange(0); }   // handle_poll_done, :194-213
 
 void speckv_ext_tier_get_stats(speckv_tier_t* tier, speckv_tier_stats_t* out) {
     if (!tier || !out) return;

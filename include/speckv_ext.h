@@ -184,6 +184,31 @@ SPECKV_API speckv_status_t speckv_ext_tier_restore(speckv_tier_t* tier, const ui
 SPECKV_API speckv_status_t speckv_ext_tier_drop(speckv_tier_t* tier, const uint64_t* h_block_ids, size_t n);
 SPECKV_API void speckv_ext_tier_get_stats(speckv_tier_t* tier, speckv_tier_stats_t* out);
 
+/* ---- descriptor-level interface (what the reference's ioctl client speaks) ------------------ */
+/* One transfer descriptor, identical to struct speckv_ioctl_dma_desc (driver/uapi/speckv_ioctl.h:
+ * 10-15) / SpeckvDmaDesc (host/include/speckv_driver.hpp:8-13): fpga_addr names the first 4 KiB
+ * page on the tier side (page i of the descriptor is fpga_addr + i*4096), gpu_addr is a device
+ * pointer, bytes a multiple of 4096, flags bit0 = write (GPU -> tier; clear = read, tier -> GPU),
+ * bit1 = run the page through the codec, bit2 = prefetch hint (no effect on the data). */
+typedef struct {
+    uint64_t fpga_addr;
+    uint64_t gpu_addr;
+    uint32_t bytes;
+    uint32_t flags;
+} speckv_dma_desc_t;
+#define SPECKV_DMA_WRITE      1u
+#define SPECKV_DMA_COMPRESSED 2u
+#define SPECKV_DMA_PREFETCH   4u
+/* SpeckvDriver::submit_dma_batch (speckv_driver.cpp:24-47): at most 4096 descriptors per batch
+ * (speckv_kernel_module.c:65-66 -> SPECKV_ERR_INVAL), executed in order, blocking. */
+SPECKV_API speckv_status_t speckv_ext_submit_dma_batch(speckv_tier_t* tier, const speckv_dma_desc_t* h_descs,
+                                                       uint32_t count, void* cuda_stream);
+/* SpeckvDriver::poll_complete (speckv_driver.cpp:65-72): descriptors completed since the last poll. */
+SPECKV_API uint32_t speckv_ext_poll_complete(void);
+/* SPECKV_IOCTL_SET_PARAM: key 1 = prefetch depth, key 2 = compression scheme; any other key is
+ * rejected with SPECKV_ERR_INVAL (speckv_kernel_module.c:179-188, tests/test_params.c:68-84). */
+SPECKV_API speckv_status_t speckv_ext_set_param(uint32_t key, uint32_t value);
+
 /* ---- serving real pointers through the frozen ABI ----------------------------------------- */
 /* Binds device memory to a speckv_alloc handle.  From then on
  * speckv_access(handle, offset, len, &ptr) returns d_base + offset -- a dereferenceable device

@@ -133,3 +133,55 @@ def test_frozen_api_serves_real_pointers_with_page_faults():
     finally:
         alloc._speckv.finalize()
         tier.close()
+
+
+def test_descriptor_interface_like_the_reference_ioctl_client():
+    """speckv_ioctl_dma_desc batches (tests/test_dma.c), SET_PARAM with an invalid key
+    (tests/test_params.c:68-84) and POLL_DONE against the CUDA backend."""
+    import ctypes as C
+
+    import cxl_speckv_b200 as pkg
+    L = pkg.lib()
+
+    class Desc(C.Structure):
+        _fields_ = [("fpga_addr", C.c_uint64), ("gpu_addr", C.c_uint64), ("bytes", C.c_uint32), ("flags", C.c_uint32)]
+
+    assert C.sizeof(Desc) == 24
+    tier = HostTier(8 << 20)
+    try:
+        src = torch.randn(6 * 2048, device=DEV).half()
+        dst = torch.zeros_like(src)
+        base = src.data_ptr()
+        # the shape of tests/test_dma.c: two single pages, one 2-page write, one compressed page
+        wr = (Desc * 4)(Desc(0x4000000000, base, 4096, 1), Desc(0x4000001000, base + 4096, 4096, 1),
+                        Desc(0x4000002000, base + 8192, 8192, 1), Desc(0x4000004000, base + 16384, 4096, 1 | 2))
+        assert L.speckv_ext_poll_complete() == 0
+        assert L.speckv_ext_submit_dma_batch(tier._h, wr, 4, None) == 0
+        assert L.speckv_ext_poll_complete() == 4 and L.speckv_ext_poll_complete() == 0
+        assert tier.stats()["blocks"] == 5
+        d0 = dst.data_ptr()
+        rd = (Desc * 4)(Desc(0x4000000000, d0, 4096, 0), Desc(0x4000001000, d0 + 4096, 4096, 0),
+                        Desc(0x4000002000, d0 + 8192, 8192, 0), Desc(0x4000004000, d0 + 16384, 4096, 2))
+        assert L.speckv_ext_submit_dma_batch(tier._h, rd, 4, None) == 0
+        torch.cuda.synchronize()
+        assert torch.equal(dst[:4 * 2048], src[:4 * 2048])                       # raw pages: bit copies
+        want = codec.decompress(codec.compress(src[4 * 2048:5 * 2048], 2048)).view(-1)
+        assert torch.equal(dst[4 * 2048:5 * 2048].view(torch.int16), want.view(torch.int16))   # codec page
+        # reading a raw page through the codec (or an unknown page) fails like a bad descriptor
+        bad = (Desc * 1)(Desc(0x4000000000, d0, 4096, 2))
+        assert L.speckv_ext_submit_dma_batch(tier._h, bad, 1, None) == -1
+        bad = (Desc * 1)(Desc(0x4999999000, d0, 4096, 0))
+        assert L.speckv_ext_submit_dma_batch(tier._h, bad, 1, None) == -1
+        assert L.speckv_ext_submit_dma_batch(tier._h, wr, 4097, None) == -4      # batch too large: -EINVAL
+        # parameters
+        assert L.speckv_ext_set_param(1, 6) == -4                                 # before speckv_init
+        assert L.speckv_init(b"cuda:0") == 0
+        try:
+            assert L.speckv_ext_set_param(1, 6) == 0 and L.speckv_ext_set_param(2, 1) == 0
+            d = C.c_uint32()
+            assert L.speckv_ext_get_prefetch_depth(C.byref(d)) == 0 and d.value == 6
+            assert L.speckv_ext_set_param(999, 123) == -4                         # invalid key is rejected
+        finally:
+            L.speckv_finalize()
+    finally:
+        tier.close()
