@@ -50,7 +50,7 @@ def workload_spec(name: str, world: int, rank: int, scale: float):
         layers, per_layer = 80, 2 * 8 * 8                # K|V x KV heads x (8192/1024)
         mine = [l for l in range(layers) if l % world == rank] if world > 1 else list(range(layers))
         return dict(label=f"cfg3: Llama-2-70B GQA KV, 80 L x 8 KVH x 8K ctx, layers sharded {layers}/{world}",
-                    group_elems=G_BLOCK, n_groups=len(mine) * per_layer, chunk_groups=per_layer * 8, scaling="strong",
+                    group_elems=G_BLOCK, n_groups=len(mine) * per_layer, chunk_groups=per_layer * 20, scaling="strong",
                     global_batch=1)
     if name == "cfg4p":
         layers, per_layer = 32, 2 * 8 * 32768 * 128 // 2048
