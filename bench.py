@@ -199,6 +199,24 @@ def run_reference(args, rank, world):
 # --------------------------------------------------------------------------------------
 # CUDA arm
 # --------------------------------------------------------------------------------------
+def bind_to_gpu_cpus(local_rank):
+    """Pin this rank to the host cores NVML lists as local to its GPU, so that the pinned host
+    buffers of the e2e leg are allocated on the GPU's own NUMA node (matters at 8 ranks per box).
+    Returns the previous affinity so that the CPU baseline can take all cores back."""
+    before = os.sched_getaffinity(0)
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (max(before) + 64) // 64)
+        cpus = {64 * w + b for w, m in enumerate(words) for b in range(64) if (int(m) >> b) & 1} & before
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+    except Exception:
+        pass
+    return before
+
+
 def run_cuda(args, rank, world, local_rank):
     import ctypes as C
 
@@ -212,6 +230,7 @@ def run_cuda(args, rank, world, local_rank):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the CUDA path has no CPU fallback "
                          "(use --impl reference for the CPU baseline)")
+    all_cpus = bind_to_gpu_cpus(local_rank)
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
@@ -370,6 +389,7 @@ def run_cuda(args, rank, world, local_rank):
     # ---- CPU baseline (rank 0, N = 1 only) ----------------------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
+        os.sched_setaffinity(0, all_cpus)
         cpu = cpu_roundtrip_rate(G, args.cpu_seconds, os.cpu_count() or 1)
         cpu.pop("seconds", None)
 

@@ -3,9 +3,10 @@
 // fp16/bf16 groups of R * 2048 elements (R a power of two up to 128) go to the tuned
 // TMA/cluster kernels; every group those flag (runs of 8+ equal deltas, non-finite or
 // tiny scales) and every other geometry goes to the generic kernel.  Both launches are
-// ordered on the caller's stream; the flag array comes from the stream-ordered pool.
+// ordered on the caller's stream; the flag array comes from the library's stream-ordered pool.
 #include <cstdlib>
 
+#include "device_ctx.h"
 #include "kv_codec.h"
 
 namespace speckv {
@@ -23,7 +24,7 @@ static cudaError_t two_pass(const CodecArgs& a, cudaStream_t st, bool decompress
     const int R = force_generic() ? 0 : fast_regions(a, decompress);
     if (R == 0) return generic(a, st, nullptr);
     uint32_t* flags = nullptr;
-    cudaError_t e = cudaMallocAsync(reinterpret_cast<void**>(&flags), (size_t)a.n_groups * sizeof(uint32_t), st);
+    cudaError_t e = scratch_alloc(reinterpret_cast<void**>(&flags), (size_t)a.n_groups * sizeof(uint32_t), st);
     if (e != cudaSuccess) return e;
     e = fast(R, a, flags, st);
     if (e == cudaSuccess) e = generic(a, st, flags);

@@ -55,6 +55,7 @@ constexpr int kBlockBytes = kPadBytes + kRegionBytes;
 struct FastSmem {
     alignas(128) uint8_t tile[kW][kBlockBytes];   // [pad][4 KiB region]; outputs are staged in place, 16 B..512 B behind the reads
     alignas(8) unsigned long long mbar[kW];
+    alignas(8) unsigned long long xmbar[2];   // cluster groups: one per exchange round, completed by the peers' st.async bytes
     // exchange words of ALL regions of the group (every region pushes its word into every CTA of the
     // cluster), indexed by region for cluster groups and by warp for groups inside one CTA
     uint32_t xa[kMaxR];   // region max bits | head count + flags | sum of counts
@@ -101,6 +102,42 @@ __device__ __forceinline__ void mbar_wait(uint32_t a, uint32_t parity) {
         "}" ::"r"(a),
         "r"(parity)
         : "memory");
+}
+// byte permute with a register selector (no "& 0x7777" as __byte_perm adds; callers pass clean selectors)
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
+    uint32_t r;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(sel));
+    return r;
+}
+// one step of an inclusive warp scan: v += (value of lane - o), for the lanes that have such a lane
+__device__ __forceinline__ uint32_t scan_step(uint32_t v, int o) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        ".reg .b32 t;\n"
+        "shfl.sync.up.b32 t|p, %0, %1, 0, 0xffffffff;\n"
+        "@p add.u32 %0, %0, t;\n"
+        "}"
+        : "+r"(v)
+        : "r"(o));
+    return v;
+}
+__device__ __forceinline__ uint32_t warp_scan_inclusive(uint32_t v) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) v = scan_step(v, o);
+    return v;
+}
+// address of the same shared-memory variable in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t a, uint32_t rank) {
+    uint32_t r;
+    asm("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(rank));
+    return r;
+}
+// asynchronous 4-byte store into a peer CTA's shared memory; the peer's mbarrier counts the bytes
+__device__ __forceinline__ void st_async_u32(uint32_t dst, uint32_t v, uint32_t mbar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.u32 [%0], %1, [%2];" ::"r"(dst), "r"(v),
+                 "r"(mbar)
+                 : "memory");
 }
 __device__ __forceinline__ uint4 lds128(const void* p) { return *reinterpret_cast<const uint4*>(p); }
 __device__ __forceinline__ void stg128(void* p, uint4 v) {
@@ -164,32 +201,51 @@ template <typename T> __device__ __forceinline__ uint16_t out_bits(float a) {
     return *reinterpret_cast<uint16_t*>(&h);
 }
 
-// Split cluster barrier: every CTA arrives when it starts and waits just before its first
-// distributed-shared-memory store, which may only target a CTA that has begun executing.
-// By then the peers have long arrived, so the wait costs nothing.
+// Cluster groups exchange their region words without cluster barriers: every region stores its word
+// into every CTA of the cluster with st.async, which also credits 4 bytes to an mbarrier in the
+// receiving CTA; a CTA's warps wait on their own mbarrier until all R words (R * 4 bytes per array)
+// have landed.  One split cluster barrier at kernel start (arrive after the mbarriers are armed,
+// wait just before the first remote store) makes sure a peer's shared memory is only written once
+// that CTA runs and has armed its mbarriers; by then the peers have long arrived.
 __device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
 __device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
 
-// synchronise the warps (CTAs) that share a group
+// arm the exchange mbarriers of this CTA (one thread), `words` arrays of R words in round 0
 template <int R>
-__device__ __forceinline__ void group_sync() {
-    if (R == 1) __syncwarp();
-    else if (R <= kW) __syncthreads();
-    else cg::this_cluster().sync();
+__device__ __forceinline__ void exchange_init(FastSmem& sm, int words0, int words1) {
+    if (R > kW) {
+        if (threadIdx.x == 0) {
+            mbar_init(smem_u32(&sm.xmbar[0]), 1);
+            mbar_init(smem_u32(&sm.xmbar[1]), 1);
+            mbar_expect_tx(smem_u32(&sm.xmbar[0]), (uint32_t)(R * 4 * words0));
+            if (words1) mbar_expect_tx(smem_u32(&sm.xmbar[1]), (uint32_t)(R * 4 * words1));
+        }
+        cluster_arrive();
+    }
 }
 
-// Exchange between the regions of a group.  publish(): the region's lane 0 (lanes 0..C-1 for a
-// cluster) stores its word into the array of every CTA of the group -- local shared memory, or
-// distributed shared memory through mapa/st.shared::cluster.  After group_sync() every warp reads
-// the words of its group locally: `before` = sum over lower-indexed regions, `total`, `mx` = max.
+// Exchange between the regions of a group.  publish(): the region's lane 0 stores its word into the
+// group's array (groups inside one CTA), or lanes 0..C-1 send it to the C CTAs of the cluster.
+// group_sync() then waits until every region's word is there; every warp reads the words locally:
+// `before` = sum over lower-indexed regions, `total`, `mx` = max.
 template <int R>
-__device__ __forceinline__ void group_publish(uint32_t* arr, int warp, int lane, int ridx, uint32_t v) {
+__device__ __forceinline__ void group_publish(FastSmem& sm, uint32_t* arr, int round, int warp, int lane, int ridx,
+                                              uint32_t v) {
     if (R <= kW) {
         if (lane == 0) arr[warp] = v;
     } else {
         constexpr int C = R / kW;
-        if (lane < C) cg::this_cluster().map_shared_rank(arr, lane)[ridx] = v;
+        if (lane < C)
+            st_async_u32(mapa_u32(smem_u32(arr + ridx), (uint32_t)lane), v,
+                         mapa_u32(smem_u32(&sm.xmbar[round]), (uint32_t)lane));
     }
+}
+
+template <int R>
+__device__ __forceinline__ void group_sync(FastSmem& sm, int round) {
+    if (R == 1) __syncwarp();
+    else if (R <= kW) __syncthreads();
+    else mbar_wait(smem_u32(&sm.xmbar[round]), 0);
 }
 
 template <int R>
@@ -280,17 +336,21 @@ __device__ __forceinline__ void flush_region(uint32_t sbase, uint8_t* gout, int 
     i = hi_al + lane;
     if (i < hi) *reinterpret_cast<uint16_t*>(gout + ((size_t)i << 1)) = (uint16_t)lds16s(sbase + ((uint32_t)i << 1));
     const int nv = (hi_al - lo_al) >> 3;
-    uint32_t sa = sbase + 2u * (uint32_t)lo_al + 16u * (uint32_t)lane;
+    const uint32_t sa = sbase + 2u * (uint32_t)lo_al + 16u * (uint32_t)lane;
     uint8_t* ga = gout + 2 * (size_t)lo_al + 16 * (size_t)lane;
-    int v = lane;
-    for (; v + 96 < nv; v += 128, sa += 2048u, ga += 2048) {   // 4 vectors per lane per trip
-        const uint4 a0 = lds128s(sa), a1 = lds128s(sa + 512u), a2 = lds128s(sa + 1024u), a3 = lds128s(sa + 1536u);
-        stg128(ga, a0);
-        stg128(ga + 512, a1);
-        stg128(ga + 1024, a2);
-        stg128(ga + 1536, a3);
+    // a region is 256 vectors (+- the ragged ends): two rounds of four guarded copies per lane, no loop
+    const int left = nv - lane;   // vectors lane, lane + 32, ... while < nv
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        uint4 a[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if (left > 32 * (4 * h + j)) a[j] = lds128s(sa + 512u * (uint32_t)(4 * h + j));
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if (left > 32 * (4 * h + j)) stg128(ga + 512 * (4 * h + j), a[j]);
     }
-    for (; v < nv; v += 32, sa += 512u, ga += 512) stg128(ga, lds128s(sa));
+    for (int v = 256; v < left; v += 32) stg128(ga + 16 * (size_t)v, lds128s(sa + 16u * (uint32_t)v));   // decode expansions
 }
 
 // ===================================================================================
@@ -324,7 +384,7 @@ compress_fast_kernel(const T* __restrict__ in, uint32_t n_groups, uint8_t* __res
     uint8_t* reg = sm.tile[warp] + kPadBytes;
     const uint32_t reg_s = smem_u32(reg);
     const uint32_t mb = smem_u32(&sm.mbar[warp]);
-    if (C > 1) cluster_arrive();
+    exchange_init<R>(sm, 1, 1);
 
     // ---- 0. one bulk-TMA copy per region -------------------------------------------------------
     if (lane == 0) {
@@ -349,8 +409,8 @@ compress_fast_kernel(const T* __restrict__ in, uint32_t n_groups, uint8_t* __res
         for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(kFull, m, o));
     }
     if (C > 1) cluster_wait();   // all CTAs of the cluster are running: their shared memory may be written
-    group_publish<R>(sm.xa, warp, lane, ridx, __float_as_uint(m));   // non-negative floats order like their bits
-    group_sync<R>();
+    group_publish<R>(sm, sm.xa, 0, warp, lane, ridx, __float_as_uint(m));   // non-negative floats order like their bits
+    group_sync<R>(sm, 0);
     uint32_t t0, t1, gmax_bits;
     group_reduce<R>(sm.xa, warp, lane, ridx, t0, t1, gmax_bits);
     const float gmax = __uint_as_float(gmax_bits);
@@ -420,8 +480,8 @@ compress_fast_kernel(const T* __restrict__ in, uint32_t n_groups, uint8_t* __res
     }
     cplx = __any_sync(kFull, cplx);
     // one word per region: head count (<= 2048) in the low 20 bits, "needs the generic kernel" above
-    group_publish<R>(sm.xc, warp, lane, ridx, active ? (heads | (cplx ? (1u << 20) : 0u)) : 0u);
-    group_sync<R>();
+    group_publish<R>(sm, sm.xc, 1, warp, lane, ridx, active ? (heads | (cplx ? (1u << 20) : 0u)) : 0u);
+    group_sync<R>(sm, 1);
     uint32_t h_before, h_total;
     group_reduce<R>(sm.xc, warp, lane, ridx, h_before, h_total, t0);
     const bool any_cplx = (h_total >> 20) != 0;
@@ -449,45 +509,38 @@ compress_fast_kernel(const T* __restrict__ in, uint32_t n_groups, uint8_t* __res
         __syncwarp();   // every lane has read its slot before any pair of this iteration lands on it
         const uint32_t dsh0 = st.x, dsh1 = st.y;
         const uint32_t nz0 = st.z, nz1 = st.w;
-        const uint32_t tail = nz1 ? ((uint32_t)__clz((int)nz1) >> 3) + 1u : ((uint32_t)__clz((int)nz0) >> 3) + 5u;
-        const uint32_t rt = __shfl_sync(kFull, tail, src_lane);
-        const uint32_t lf = lane == 0 ? carry_tail : rt;   // distance back to the previous head
-        carry_tail = rt;
-        const uint32_t hw0 = ~nz0 & 0x80808080u, hw1 = ~nz1 & 0x80808080u;
+        const uint32_t hw0 = ~nz0 & 0x80808080u, hw1 = ~nz1 & 0x80808080u;   // "holes": positions that continue a run
         const int nhole = __popc(hw0) + __popc(hw1);
         if (!__any_sync(kFull, nhole > 1)) {
             // ---- common case: every lane emits 8 pairs, or 7 (one position continues a run) ----
+            // with at most one hole the run open at the end of the chunk is 1 or 2 positions long
+            const uint32_t rt = __shfl_sync(kFull, 1u + (hw1 >> 31), src_lane);
+            const uint32_t lf = lane == 0 ? carry_tail : rt;   // distance back to the previous head
+            carry_tail = rt;
             const unsigned bal = __ballot_sync(kFull, nhole != 0);
             const int idx = pidx + 8 * lane - __popc(bal & lt_mask);
-            // counts: 1 everywhere, lf for the first unit; the unit after a hole inherits the hole's count
-            uint32_t c0 = 0x01010100u | lf, c1 = 0x01010101u;
-            int h = 8;
-            if (nhole) {
-                h = hw0 ? (__ffs((int)hw0) >> 3) - 1 : (__ffs((int)hw1) >> 3) + 3;
-                const uint32_t add = h == 0 ? lf : 1u;
-                if (h < 3) c0 += add << (8 * (h + 1));
-                else if (h < 7) c1 += add << (8 * (h - 3));
-            }
-            uint32_t w0 = __byte_perm(dsh0, c0, 0x5140), w1 = __byte_perm(dsh0, c0, 0x7362);
-            uint32_t w2 = __byte_perm(dsh1, c1, 0x5140), w3 = __byte_perm(dsh1, c1, 0x7362);
-            if (nhole) {
-                const uint4 sel = *reinterpret_cast<const uint4*>(c_del_sel[h]);
-                w0 = __byte_perm(w0, w1, sel.x);
-                w1 = __byte_perm(w1, w2, sel.y);
-                w2 = __byte_perm(w2, w3, sel.z);
-                w3 = __byte_perm(w3, 0u, sel.w);
-            }
+            // Branch-free hole deletion.  u = 1 << (8 * hole byte) in its word, 0 without a hole.
+            // counts: lf for the first unit, 1 elsewhere; once the hole unit is gone the unit that
+            // takes its index has absorbed the hole's position: +1 at that index (lf + 1 at index 0).
+            const uint32_t u0 = hw0 >> 7, u1 = hw1 >> 7;
+            const uint32_t c0 = (0x01010100u | lf) + u0, c1 = 0x01010101u + u1;
+            // values: bytes below the hole stay, bytes from the hole on move down by one
+            const uint32_t keep0 = u0 - 1u;                    // all ones when the hole is not in word 0
+            const uint32_t keep1 = u0 ? 0u : u1 - 1u;
+            const uint32_t sh0 = __funnelshift_r(dsh0, dsh1, 8), sh1 = dsh1 >> 8;
+            const uint32_t v0 = (dsh0 & keep0) | (sh0 & ~keep0), v1 = (dsh1 & keep1) | (sh1 & ~keep1);
+            const uint32_t w0 = __byte_perm(v0, c0, 0x5140), w1 = __byte_perm(v0, c0, 0x7362);
+            const uint32_t w2 = __byte_perm(v1, c1, 0x5140), w3 = __byte_perm(v1, c1, 0x7362);
             store_units8(sbase + 2u * (uint32_t)idx, w0, w1, w2, w3, 8 - nhole);
             pidx += 256 - __popc(bal);
         } else {
             // ---- some lane has two or more continuing positions: scan + one store per head ----
+            const uint32_t tail = nz1 ? ((uint32_t)__clz((int)nz1) >> 3) + 1u : ((uint32_t)__clz((int)nz0) >> 3) + 5u;
+            const uint32_t rt = __shfl_sync(kFull, tail, src_lane);
+            const uint32_t lf = lane == 0 ? carry_tail : rt;
+            carry_tail = rt;
             const int n = 8 - nhole;
-            int inc = n;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int t = __shfl_up_sync(kFull, inc, o);
-                if (lane >= o) inc += t;
-            }
+            const int inc = (int)warp_scan_inclusive((uint32_t)n);
             int idx = pidx + inc - n;
             uint32_t run = lf;
 #pragma unroll
@@ -550,7 +603,7 @@ decompress_fast_kernel(const uint8_t* __restrict__ payload, size_t slot_bytes, c
     uint8_t* reg = sm.tile[warp] + kPadBytes;
     const uint32_t reg_s = smem_u32(reg);
     const uint32_t mb = smem_u32(&sm.mbar[warp]);
-    if (C > 1) cluster_arrive();
+    exchange_init<R>(sm, 2, 0);
 
     // pairs of this region: [ridx * 2048, ridx * 2048 + np)
     uint32_t np = 0;
@@ -621,9 +674,9 @@ decompress_fast_kernel(const uint8_t* __restrict__ payload, size_t slot_bytes, c
         if (csum - nnz > (uint32_t)(kPadBytes / 2 - 8)) cplx = true;
     }
     if (C > 1) cluster_wait();   // all CTAs of the cluster are running: their shared memory may be written
-    group_publish<R>(sm.xa, warp, lane, ridx, min(csum, G + 1u));   // saturated: sums stay < 2^32, "> G" still shows
-    group_publish<R>(sm.xb, warp, lane, ridx, ssum | (cplx ? (1u << 24) : 0u));
-    group_sync<R>();
+    group_publish<R>(sm, sm.xa, 0, warp, lane, ridx, min(csum, G + 1u));   // saturated: sums stay < 2^32, "> G" still shows
+    group_publish<R>(sm, sm.xb, 0, warp, lane, ridx, ssum | (cplx ? (1u << 24) : 0u));
+    group_sync<R>(sm, 0);
     uint32_t e_before, e_total, q_before, xb_total, t0;
     group_reduce<R>(sm.xa, warp, lane, ridx, e_before, e_total, t0);
     group_reduce<R>(sm.xb, warp, lane, ridx, q_before, xb_total, t0);
@@ -641,10 +694,10 @@ decompress_fast_kernel(const uint8_t* __restrict__ payload, size_t slot_bytes, c
     uint32_t ecur = e0;                       // next element index to produce
     uint32_t qcur = q_before & 0xffu;         // code of element ecur - 1
     const uint32_t sbase = reg_s - (uint32_t)kPadBytes - 2u * (e0 & ~7u);   // element i is staged at sbase + 2*i
+    uint32_t rd_s = reg_s + 16u * (uint32_t)lane;   // this lane's slot of the current iteration
 #pragma unroll 1
-    for (int k = 0; k < kIters; ++k) {
-        if (k * 256 >= (int)np) break;
-        const uint4 w = lds128(reg + k * 512 + lane * 16);
+    for (uint32_t pk = 0; pk < np; pk += 256u, rd_s += 512u) {
+        const uint4 w = lds128s(rd_s);
         __syncwarp();
         const uint32_t va = __byte_perm(w.x, w.y, 0x6420), ca = __byte_perm(w.x, w.y, 0x7531);
         const uint32_t vb = __byte_perm(w.z, w.w, 0x6420), cb = __byte_perm(w.z, w.w, 0x7531);
@@ -659,22 +712,17 @@ decompress_fast_kernel(const uint8_t* __restrict__ payload, size_t slot_bytes, c
             // every lane: 8 pairs -> 8 or 9 elements
             const unsigned bal = __ballot_sync(kFull, ntwo != 0);
             const uint32_t idx = ecur + 8u * lane + __popc(bal & lt_mask);
-            uint32_t inc = sl;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const uint32_t t = __shfl_up_sync(kFull, inc, o);
-                if (lane >= o) inc += t;
-            }
+            const uint32_t inc = warp_scan_inclusive(sl);
             const uint32_t tot = __shfl_sync(kFull, inc, 31);
-            uint32_t qb = qcur + inc - sl;
-            uint32_t v0 = va, v1 = vb;
+            const uint32_t qb = qcur + inc - sl;
+            // Branch-free duplication of the value whose count is 2 (ta / tb hold 1 << (8 * its byte)):
+            // bytes up to and including it stay, the bytes above move up by one; the ninth value is
+            // byte 7 either way (it is only stored when there was a duplicate).
+            const uint32_t keep0 = (ta << 8) - 1u;                  // all ones when the pair is not in word a
+            const uint32_t keep1 = ta ? 0u : (tb << 8) - 1u;
+            const uint32_t up0 = va << 8, up1 = __funnelshift_l(va, vb, 8);
+            const uint32_t v0 = (va & keep0) | (up0 & ~keep0), v1 = (vb & keep1) | (up1 & ~keep1);
             const uint32_t v2 = vb >> 24;
-            if (ntwo) {
-                const int h = ta ? (__ffs((int)ta) >> 3) : (__ffs((int)tb) >> 3) + 4;
-                const uint2 sel = *reinterpret_cast<const uint2*>(c_dup_sel[h]);
-                v0 = __byte_perm(va, va, sel.x);
-                v1 = __byte_perm(va, vb, sel.y);
-            }
             // codes = running byte sums: dp4a against 0x01, 0x0101, ... adds the first 1..4 bytes
             float y[9];
             const uint32_t q4 = __dp4a(v0, 0x01010101u, qb);
@@ -695,12 +743,7 @@ decompress_fast_kernel(const uint8_t* __restrict__ payload, size_t slot_bytes, c
         } else {
             // any counts: exclusive scan of (elements, code advance), then per-pair loops
             const uint32_t cl = __dp4a(cb, 0x01010101u, __dp4a(ca, 0x01010101u, 0u));
-            uint32_t inc = cl | (sl << 24);
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const uint32_t t = __shfl_up_sync(kFull, inc, o);
-                if (lane >= o) inc += t;
-            }
+            const uint32_t inc = warp_scan_inclusive(cl | (sl << 24));
             const uint32_t tot = __shfl_sync(kFull, inc, 31);
             const uint32_t excl = inc - (cl | (sl << 24));
             uint32_t p = ecur + (excl & 0xffffffu);
