@@ -95,12 +95,12 @@ __device__ __forceinline__ void mbar_wait(uint32_t a, uint32_t parity) {
         "{\n"
         ".reg .pred P1;\n"
         "LAB_WAIT:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, %2;\n"   // suspends in hardware up to the hint (ns)
         "@P1 bra DONE;\n"
         "bra LAB_WAIT;\n"
         "DONE:\n"
         "}" ::"r"(a),
-        "r"(parity)
+        "r"(parity), "r"(0x989680u)
         : "memory");
 }
 // byte permute with a register selector (no "& 0x7777" as __byte_perm adds; callers pass clean selectors)
@@ -206,8 +206,9 @@ template <typename T> __device__ __forceinline__ uint16_t out_bits(float a) {
 // receiving CTA; a CTA's warps wait on their own mbarrier until all R words (R * 4 bytes per array)
 // have landed.  One split cluster barrier at kernel start (arrive after the mbarriers are armed,
 // wait just before the first remote store) makes sure a peer's shared memory is only written once
-// that CTA runs and has armed its mbarriers; by then the peers have long arrived.
-__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+// that CTA runs and has armed its mbarriers; by then the peers have long arrived.  The arrive is
+// relaxed: fence.mbarrier_init.release.cluster (in mbar_init) is what publishes the mbarriers.
+__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory"); }
 __device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
 
 // arm the exchange mbarriers of this CTA (one thread), `words` arrays of R words in round 0
@@ -395,6 +396,9 @@ compress_fast_kernel(const T* __restrict__ in, uint32_t n_groups, uint8_t* __res
         }
     }
     __syncwarp();
+    // halo: the 16 elements in front of the region, fetched now so that the latency hides behind phase 1
+    T halo_x = narrow<T>(0.0f);
+    if (active && ridx > 0 && lane < 16) halo_x = __ldg(rin + lane - 16);
 
     // ---- 1. region max-abs, then the group max over its R regions -------------------------------
     float m = 0.0f;
@@ -429,7 +433,7 @@ compress_fast_kernel(const T* __restrict__ in, uint32_t n_groups, uint8_t* __res
             // halo: the 16 elements before the region give the last code, the last delta and the
             // run boundaries among the last 4 positions before the region (all local, no neighbour needed)
             uint32_t qh = 0;
-            if (lane < 16) qh = quantize_fast(widen<T>(rin[lane - 16]), s, r);
+            if (lane < 16) qh = quantize_fast(widen<T>(halo_x), s, r);
             const uint32_t qp = __shfl_up_sync(kFull, qh, 1);
             const uint32_t dh = (qh - qp) & 0xffu;
             const uint32_t dp = __shfl_up_sync(kFull, dh, 1);
