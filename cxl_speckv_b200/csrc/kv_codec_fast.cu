@@ -408,9 +408,8 @@ compress_fast_kernel(const T* __restrict__ in, uint32_t n_groups, uint8_t* __res
         typename Pack2<T>::type pm = *reinterpret_cast<const typename Pack2<T>::type*>(&z);
 #pragma unroll
         for (int k = 0; k < kIters; ++k) pm = absmax8<T>(pm, lds128(reg + k * 512 + lane * 16));
-        m = pack_max_to_float(pm);
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(kFull, m, o));
+        // non-negative floats order like their bit patterns: one integer warp reduction
+        m = __uint_as_float(__reduce_max_sync(kFull, __float_as_uint(pack_max_to_float(pm))));
     }
     if (C > 1) cluster_wait();   // all CTAs of the cluster are running: their shared memory may be written
     group_publish<R>(sm, sm.xa, 0, warp, lane, ridx, __float_as_uint(m));   // non-negative floats order like their bits

@@ -35,6 +35,46 @@ __device__ __forceinline__ uint4 ldg_stream(const uint4* p) {
     return r;
 }
 
+// Groups a CTA works on: g = blockIdx.x + t * gridDim.x, t = 0, 1, ...  With a flag array (second
+// pass after the tuned kernels, where almost no group is flagged) the CTA fetches the flags of its
+// next 256 groups with one batch of loads, keeps them as 8 ballot words in shared memory and visits
+// only the set bits: skipping costs one load latency per 256 groups instead of one per group, and
+// flagged groups stay spread over all CTAs.  next() must be called by all threads of the CTA; the
+// result is uniform.
+struct GroupIter {
+    const uint32_t* flags;
+    uint32_t n, t0, word, mask;   // t0 = first local index of the NEXT chunk
+    uint32_t* smask;              // kWarps words of shared memory
+    __device__ GroupIter(const uint32_t* f, uint32_t n_groups, uint32_t* sm)
+        : flags(f), n(n_groups), t0(0), word(kWarps), mask(0), smask(sm) {}
+    __device__ bool next(uint32_t& g) {
+        if (!flags) {
+            g = blockIdx.x + t0 * gridDim.x;
+            ++t0;
+            return g < n;
+        }
+        for (;;) {
+            if (mask) {
+                const uint32_t j = (uint32_t)__ffs((int)mask) - 1u;
+                mask &= mask - 1u;
+                g = blockIdx.x + (t0 - kThreads + (word - 1u) * 32u + j) * gridDim.x;
+                return true;
+            }
+            if (word == kWarps) {   // flags of the CTA's next kThreads groups
+                if ((uint64_t)blockIdx.x + (uint64_t)t0 * gridDim.x >= n) return false;
+                __syncthreads();    // everybody is done with the previous chunk's words
+                const uint64_t i = (uint64_t)blockIdx.x + (uint64_t)(t0 + threadIdx.x) * gridDim.x;
+                const unsigned b = __ballot_sync(0xffffffffu, i < n && flags[i] != 0u);
+                if ((threadIdx.x & 31) == 0) smask[threadIdx.x >> 5] = b;
+                __syncthreads();
+                t0 += kThreads;
+                word = 0;
+            }
+            mask = smask[word++];
+        }
+    }
+};
+
 // exclusive block scans; `wbuf` holds one int per warp.  Two __syncthreads each.
 __device__ __forceinline__ int block_excl_sum(int v, int& total, int* wbuf) {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -150,8 +190,9 @@ compress_rle_generic_kernel(const T* __restrict__ in, uint32_t G, uint32_t n_gro
     __shared__ uint32_t carry_sm[3];
     const int tid = threadIdx.x;
 
-    for (uint32_t g = blockIdx.x; g < n_groups; g += gridDim.x) {
-        if (only_flagged && !only_flagged[g]) continue;   // second pass after the tuned kernel
+    __shared__ uint32_t smask[kWarps];
+    GroupIter it(only_flagged, n_groups, smask);
+    for (uint32_t g; it.next(g);) {
         const T* gin = in + (size_t)g * G;
         uint8_t* gout = payload + (size_t)g * slot_bytes;
         const bool vec_ok = (reinterpret_cast<uintptr_t>(gin) & 15) == 0;
@@ -291,8 +332,9 @@ decompress_rle_generic_kernel(const uint8_t* __restrict__ payload, size_t slot_b
     __shared__ int wbuf[kWarps];
     const int tid = threadIdx.x;
 
-    for (uint32_t g = blockIdx.x; g < n_groups; g += gridDim.x) {
-        if (only_flagged && !only_flagged[g]) continue;   // second pass after the tuned kernel
+    __shared__ uint32_t smask[kWarps];
+    GroupIter it(only_flagged, n_groups, smask);
+    for (uint32_t g; it.next(g);) {
         const uint32_t gi = src_index ? src_index[g] : g; // which stored block this output group decodes
         const uint8_t* gp = payload + (slot_offsets ? (size_t)slot_offsets[gi] : (size_t)gi * slot_bytes);
         uint32_t npairs = comp_bytes[gi] >> 1;  // a trailing odd byte is ignored (:245-247)
