@@ -76,10 +76,15 @@ __constant__ uint32_t c_dup_sel[8][2] = {{0x2100, 0x6543}, {0x2110, 0x6543}, {0x
 // ---- PTX helpers ------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// mbarrier used by this CTA only (bulk-TMA completion): the async proxy must see the initialisation
 __device__ __forceinline__ void mbar_init(uint32_t a, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(a), "r"(count) : "memory");
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+// mbarrier that peer CTAs complete (st.async): the initialisation is released to the cluster
+__device__ __forceinline__ void mbar_init_cluster(uint32_t a, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(a), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
 __device__ __forceinline__ void mbar_expect_tx(uint32_t a, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(a), "r"(bytes) : "memory");
@@ -207,7 +212,7 @@ template <typename T> __device__ __forceinline__ uint16_t out_bits(float a) {
 // have landed.  One split cluster barrier at kernel start (arrive after the mbarriers are armed,
 // wait just before the first remote store) makes sure a peer's shared memory is only written once
 // that CTA runs and has armed its mbarriers; by then the peers have long arrived.  The arrive is
-// relaxed: fence.mbarrier_init.release.cluster (in mbar_init) is what publishes the mbarriers.
+// relaxed: fence.mbarrier_init.release.cluster (in mbar_init_cluster) is what publishes the mbarriers.
 __device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory"); }
 __device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
 
@@ -216,8 +221,8 @@ template <int R>
 __device__ __forceinline__ void exchange_init(FastSmem& sm, int words0, int words1) {
     if (R > kW) {
         if (threadIdx.x == 0) {
-            mbar_init(smem_u32(&sm.xmbar[0]), 1);
-            mbar_init(smem_u32(&sm.xmbar[1]), 1);
+            mbar_init_cluster(smem_u32(&sm.xmbar[0]), 1);
+            mbar_init_cluster(smem_u32(&sm.xmbar[1]), 1);
             mbar_expect_tx(smem_u32(&sm.xmbar[0]), (uint32_t)(R * 4 * words0));
             if (words1) mbar_expect_tx(smem_u32(&sm.xmbar[1]), (uint32_t)(R * 4 * words1));
         }
