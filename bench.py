@@ -467,7 +467,22 @@ def run_cfg4(args, local_rank):
     want = codec.decompress(codec.compress(x[:4096 * G], G))
     assert torch.equal(out[:4096].view(torch.int16), want.view(torch.int16))
     tier.close()
+    del out
+
+    # residency policy over the same pages: one decode step touches every page; then a prefetch-sized promotion
+    from cxl_speckv_b200.tier import TierPolicy
+    pol = TierPolicy(pages, l1_pages=pages // 16)
+    allp = np.arange(pages, dtype=np.uint64)
+    pol.place(allp[:pages // 16], 0); pol.place(allp[pages // 16:], 2)
+    perm = torch.randperm(pages, device=dev, generator=gen)
+    t_touch = timed(lambda: pol.touch(perm))
+    batch = allp[pages // 16:][:4096]
+    torch.cuda.synchronize(); t0 = time.perf_counter(); ok, ev = pol.promote(batch); t_prom = time.perf_counter() - t0
+    assert ok.all() and ev.size == 4096
+    pol.close()
     print(json.dumps({"report": "cfg4", "workload": f"Llama-3-8B 32K ctx paged KV, {layers} layers, {pages} pages of 4 KiB",
+                      "policy": {"touch_Gpages_per_s": pages / t_touch / 1e6, "touch_ms_all_pages": t_touch,
+                                 "promote_4096_with_eviction_ms": t_prom * 1e3},
                       "translate_Gaddr_per_s": pages / t_tr / 1e6, "translate_GB/s": pages * 16 / t_tr / 1e6,
                       "page_lookup_Gaddr_per_s": pages / t_lk / 1e6,
                       "offload": {"s": t_off, "stored_bytes": st_off["last_offload_stored_bytes"], "pcie_GB/s": st_off["last_offload_stored_bytes"] / t_off / 1e9,

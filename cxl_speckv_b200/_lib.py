@@ -33,6 +33,13 @@ class TierStats(C.Structure):
                [("last_offload_ms", C.c_double), ("last_restore_ms", C.c_double)]
 
 
+class PolicyStats(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in ("l1_hits", "l1_misses", "l2_hits", "l2_misses", "l3_accesses",
+                                          "migrations_l1_to_l3", "migrations_l3_to_l1")] + \
+               [("l1_hit_rate", C.c_double), ("l2_hit_rate", C.c_double)] + \
+               [(n, C.c_uint64) for n in ("l1_pages", "l2_pages", "l3_pages")]
+
+
 def lib_path() -> str:
     return os.environ.get("SPECKV_LIB", os.path.join(PKG, "libcxlspeckv.so"))
 
@@ -110,6 +117,17 @@ def lib() -> C.CDLL:
     L.speckv_ext_submit_dma_batch.argtypes = [vp, vp, C.c_uint32, vp]; L.speckv_ext_submit_dma_batch.restype = C.c_int
     L.speckv_ext_poll_complete.argtypes = []; L.speckv_ext_poll_complete.restype = C.c_uint32
     L.speckv_ext_set_param.argtypes = [C.c_uint32, C.c_uint32]; L.speckv_ext_set_param.restype = C.c_int
+    L.speckv_ext_policy_create.argtypes = [C.c_uint64] * 4 + [C.POINTER(vp)]; L.speckv_ext_policy_create.restype = C.c_int
+    L.speckv_ext_policy_destroy.argtypes = [vp]; L.speckv_ext_policy_destroy.restype = None
+    L.speckv_ext_policy_place.argtypes = [vp, vp, sz, C.c_int, vp]; L.speckv_ext_policy_place.restype = C.c_int
+    L.speckv_ext_policy_release.argtypes = [vp, vp, sz]; L.speckv_ext_policy_release.restype = C.c_int
+    L.speckv_ext_policy_touch.argtypes = [vp, vp, sz, C.c_int, vp]; L.speckv_ext_policy_touch.restype = C.c_int
+    L.speckv_ext_policy_is_hot.argtypes = [vp, vp, sz, vp, vp]; L.speckv_ext_policy_is_hot.restype = C.c_int
+    L.speckv_ext_policy_promote.argtypes = [vp, vp, sz, vp, vp, C.POINTER(sz)]; L.speckv_ext_policy_promote.restype = C.c_int
+    L.speckv_ext_policy_demote.argtypes = [vp, vp, sz, vp]; L.speckv_ext_policy_demote.restype = C.c_int
+    L.speckv_ext_policy_get_tiers.argtypes = [vp, vp, sz, vp]; L.speckv_ext_policy_get_tiers.restype = C.c_int
+    L.speckv_ext_policy_lru_order.argtypes = [vp, vp, sz, C.POINTER(sz)]; L.speckv_ext_policy_lru_order.restype = C.c_int
+    L.speckv_ext_policy_get_stats.argtypes = [vp, C.POINTER(PolicyStats)]; L.speckv_ext_policy_get_stats.restype = C.c_int
     L.speckv_ext_get_stats.argtypes = [C.POINTER(Stats)]; L.speckv_ext_get_stats.restype = None
     L.speckv_ext_reset_stats.argtypes = []; L.speckv_ext_reset_stats.restype = None
     _LIB = L

@@ -56,3 +56,100 @@ class HostTier:
         s = _lib.TierStats()
         lib().speckv_ext_tier_get_stats(self._h, C.byref(s))
         return {k: getattr(s, k) for k, _ in s._fields_}
+
+
+L1, L2, L3, UNALLOCATED = 0, 1, 2, 255
+
+
+class TierPolicy:
+    """Residency bookkeeping of the KV pages (speckv_ext_policy_*): the reference's
+    CXLMemoryManager policy (src/cxl_memory/cxl_memory_manager.cpp:28-324) with the per-page state
+    in device memory.  Page ids are dense indices; capacities count pages."""
+
+    def __init__(self, n_pages: int, l1_pages: int, l2_pages: int = 1 << 62, l3_pages: int = 1 << 62):
+        self._h = C.c_void_p()
+        self.n_pages = n_pages
+        check(lib().speckv_ext_policy_create(n_pages, l1_pages, l2_pages, l3_pages, C.byref(self._h)),
+              "speckv_ext_policy_create")
+
+    def close(self):
+        if self._h:
+            lib().speckv_ext_policy_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @staticmethod
+    def _ids(ids) -> np.ndarray:
+        return np.ascontiguousarray(ids, dtype=np.uint64).ravel()
+
+    def place(self, ids, tier: int) -> np.ndarray:
+        ids = self._ids(ids)
+        out = np.zeros(ids.size, dtype=np.uint8)
+        check(lib().speckv_ext_policy_place(self._h, ids.ctypes.data, ids.size, tier, out.ctypes.data),
+              "speckv_ext_policy_place")
+        return out
+
+    def release(self, ids) -> None:
+        ids = self._ids(ids)
+        check(lib().speckv_ext_policy_release(self._h, ids.ctypes.data, ids.size), "speckv_ext_policy_release")
+
+    def touch(self, ids) -> None:
+        """ids: a CUDA int64 tensor (stream-ordered, no synchronisation) or anything array-like on the host."""
+        if isinstance(ids, torch.Tensor) and ids.is_cuda:
+            ids = ids.contiguous()
+            assert ids.dtype in (torch.int64, torch.uint64)
+            with torch.cuda.device(ids.device):
+                check(lib().speckv_ext_policy_touch(self._h, ids.data_ptr(), ids.numel(), 1, _stream()),
+                      "speckv_ext_policy_touch")
+            return
+        ids = self._ids(ids)
+        check(lib().speckv_ext_policy_touch(self._h, ids.ctypes.data, ids.size, 0, None), "speckv_ext_policy_touch")
+
+    def is_hot(self, ids: torch.Tensor) -> torch.Tensor:
+        ids = ids.contiguous()
+        out = torch.empty(ids.numel(), dtype=torch.uint8, device=ids.device)
+        with torch.cuda.device(ids.device):
+            check(lib().speckv_ext_policy_is_hot(self._h, ids.data_ptr(), ids.numel(), out.data_ptr(), _stream()),
+                  "speckv_ext_policy_is_hot")
+        return out
+
+    def promote(self, ids):
+        """-> (ok[n] uint8, evicted page ids in order)"""
+        ids = self._ids(ids)
+        ok = np.zeros(ids.size, dtype=np.uint8)
+        ev = np.zeros(max(ids.size, 1), dtype=np.uint64)
+        n_ev = C.c_size_t()
+        check(lib().speckv_ext_policy_promote(self._h, ids.ctypes.data, ids.size, ok.ctypes.data, ev.ctypes.data,
+                                              C.byref(n_ev)), "speckv_ext_policy_promote")
+        return ok, ev[:n_ev.value].copy()
+
+    def demote(self, ids) -> np.ndarray:
+        ids = self._ids(ids)
+        ok = np.zeros(ids.size, dtype=np.uint8)
+        check(lib().speckv_ext_policy_demote(self._h, ids.ctypes.data, ids.size, ok.ctypes.data),
+              "speckv_ext_policy_demote")
+        return ok
+
+    def tiers(self, ids=None) -> np.ndarray:
+        ids = self._ids(np.arange(self.n_pages) if ids is None else ids)
+        out = np.zeros(ids.size, dtype=np.uint8)
+        check(lib().speckv_ext_policy_get_tiers(self._h, ids.ctypes.data, ids.size, out.ctypes.data),
+              "speckv_ext_policy_get_tiers")
+        return out
+
+    def lru_order(self) -> np.ndarray:
+        out = np.zeros(self.n_pages, dtype=np.uint64)
+        n = C.c_size_t()
+        check(lib().speckv_ext_policy_lru_order(self._h, out.ctypes.data, out.size, C.byref(n)),
+              "speckv_ext_policy_lru_order")
+        return out[:n.value].copy()
+
+    def stats(self) -> dict:
+        s = _lib.PolicyStats()
+        check(lib().speckv_ext_policy_get_stats(self._h, C.byref(s)), "speckv_ext_policy_get_stats")
+        return {k: getattr(s, k) for k, _ in s._fields_}

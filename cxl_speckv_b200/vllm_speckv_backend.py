@@ -85,10 +85,52 @@ class CxlSpeckvKVAllocator:
         if ret != 0:
             raise RuntimeError(f"speckv_ext_offload_pages failed: {ret}")
 
+    def fetch_pages(self, first_page: int, n_pages: int):
+        lib = self._speckv.lib
+        lib.speckv_ext_fetch_pages.argtypes = [ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_void_p]
+        lib.speckv_ext_fetch_pages.restype = ctypes.c_int
+        ret = lib.speckv_ext_fetch_pages(self._handle, first_page, n_pages, None)
+        if ret != 0:
+            raise RuntimeError(f"speckv_ext_fetch_pages failed: {ret}")
+
+    # ---- additive: residency policy driving the data path ----
+    def attach_policy(self, policy):
+        """`policy`: a cxl_speckv_b200.tier.TierPolicy over this region's pages (page i of the policy =
+        page i of the region).  residency_step() then keeps the pool in line with its decisions."""
+        self._policy = policy
+
+    def residency_step(self, touched=None, promote=None):
+        """One policy round: record the pages the step read (`touched`: CUDA tensor or array of page
+        indices), promote the pages in `promote` (e.g. the prefetcher's predictions) to L1, and move
+        data accordingly -- promoted pages are restored into the pool, the pages the policy evicted
+        to make room are compressed out to the host tier.  Returns (ok, evicted)."""
+        pol = self._policy
+        if touched is not None:
+            pol.touch(touched)
+        if promote is None or len(promote) == 0:
+            return [], []
+        ok, evicted = pol.promote(promote)
+        for a, b in _runs(sorted(int(p) for p in evicted)):
+            self.offload_pages(a, b - a)
+        for a, b in _runs(sorted({int(p) for p, o in zip(promote, ok) if o})):
+            self.fetch_pages(a, b - a)
+        return ok, evicted
+
     def _calc_offset(self, req_id: int, layer: int, head: int, pos: int, kind: int, entry_bytes: int) -> int:
         # [req][layer][kind][pos][head] * entry_bytes  (reference :95-100)
         return ((((req_id * self._num_layers + layer) * 2 + kind) * self._num_tokens + pos)
                 * self._num_heads + head) * entry_bytes
+
+
+def _runs(pages):
+    """[3, 4, 5, 9] -> [(3, 6), (9, 10)]: contiguous page ranges for the range-based offload / fetch calls."""
+    out = []
+    for p in pages:
+        if out and out[-1][1] == p:
+            out[-1][1] = p + 1
+        else:
+            out.append([p, p + 1])
+    return [(a, b) for a, b in out]
 
 
 def decode_step_example(model, kv_allocator: CxlSpeckvKVAllocator, state, depth_k: int = 4):

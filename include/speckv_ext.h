@@ -230,6 +230,62 @@ SPECKV_API speckv_status_t speckv_ext_offload_pages(speckv_handle_t handle, uint
 SPECKV_API speckv_status_t speckv_ext_fetch_pages(speckv_handle_t handle, uint64_t first_page, uint64_t n_pages,
                                                   void* cuda_stream);
 
+/* ---- tier residency policy -------------------------------- */
+/* CXLMemoryManager's residency bookkeeping (src/cxl_memory/cxl_memory_manager.cpp:28-324) over
+ * dense page indices 0..n_pages-1, with the per-page state (tier, access count, LRU stamp) in
+ * device memory so that a decode step can report millions of touched pages with one kernel:
+ *   place    = allocate() of single pages into a tier (an L1 preference falls back to L3 when L1
+ *              is full, :37-40)
+ *   touch    = update_access_tracking() for every id in order (:221-246): ++access_count,
+ *              l1_hits / l2_hits / l3_accesses by tier, page to the back of the LRU list
+ *   is_hot   = access_count > 10 (:248-258)
+ *   promote  = promote_to_l1() for every id in order (:130-162); when L1 is full the least
+ *              recently used L1 page is demoted to L3 first and reported in `evicted`
+ *   demote   = demote_to_l3() (:164-194)
+ * Tiers: 0 = L1 (HBM), 1 = L2 (prefetch buffer), 2 = L3 (pool), 255 = not allocated.
+ * The reference's own eviction (evict_l1_lru, :285-293) re-locks a mutex it already holds and
+ * never returns; the semantics here are that step repeated until a page is freed: entries are
+ * popped from the front of the LRU list (entries that are not L1-resident are dropped, as the
+ * reference's pop drops them) until an L1 page has been popped and demoted; if the list holds
+ * no L1 page nothing is evicted and the promotion proceeds, as in the reference.  Capacities
+ * count pages.  Pair promote/demote with
+ * speckv_ext_fetch_pages / speckv_ext_offload_pages to move the data. */
+typedef struct speckv_policy speckv_policy_t;
+typedef struct {
+    uint64_t l1_hits, l1_misses, l2_hits, l2_misses, l3_accesses;
+    uint64_t migrations_l1_to_l3, migrations_l3_to_l1;
+    double l1_hit_rate, l2_hit_rate;
+    uint64_t l1_pages, l2_pages, l3_pages;
+} speckv_policy_stats_t;
+SPECKV_API speckv_status_t speckv_ext_policy_create(uint64_t n_pages, uint64_t l1_capacity_pages,
+                                                    uint64_t l2_capacity_pages, uint64_t l3_capacity_pages,
+                                                    speckv_policy_t** out);
+SPECKV_API void speckv_ext_policy_destroy(speckv_policy_t* p);
+/* h_ids: host array.  out_tiers (optional, host): the tier each page went to, 255 if rejected
+ * (index out of range or already allocated). */
+SPECKV_API speckv_status_t speckv_ext_policy_place(speckv_policy_t* p, const uint64_t* h_ids, size_t n, int tier,
+                                                   uint8_t* out_tiers);
+SPECKV_API speckv_status_t speckv_ext_policy_release(speckv_policy_t* p, const uint64_t* h_ids, size_t n);
+/* ids on the device (ids_on_device != 0, stream-ordered, no host synchronisation) or on the host */
+SPECKV_API speckv_status_t speckv_ext_policy_touch(speckv_policy_t* p, const uint64_t* ids, size_t n,
+                                                   int ids_on_device, void* cuda_stream);
+/* d_ids / d_out on the device, stream-ordered */
+SPECKV_API speckv_status_t speckv_ext_policy_is_hot(speckv_policy_t* p, const uint64_t* d_ids, size_t n,
+                                                    uint8_t* d_out, void* cuda_stream);
+/* Host arrays.  out_ok[n] (optional): 1 where the reference's call returns true.  out_evicted
+ * (optional, capacity >= n): pages demoted to make room, in order; *out_n_evicted their count. */
+SPECKV_API speckv_status_t speckv_ext_policy_promote(speckv_policy_t* p, const uint64_t* h_ids, size_t n,
+                                                     uint8_t* out_ok, uint64_t* out_evicted, size_t* out_n_evicted);
+SPECKV_API speckv_status_t speckv_ext_policy_demote(speckv_policy_t* p, const uint64_t* h_ids, size_t n,
+                                                    uint8_t* out_ok);
+SPECKV_API speckv_status_t speckv_ext_policy_get_tiers(speckv_policy_t* p, const uint64_t* h_ids, size_t n,
+                                                       uint8_t* out_tiers);
+/* LRU list, least recently used first (every member, as the reference's l1_lru_list_ holds any
+ * touched page).  *out_n = list length; at most `capacity` ids are written. */
+SPECKV_API speckv_status_t speckv_ext_policy_lru_order(speckv_policy_t* p, uint64_t* out_ids, size_t capacity,
+                                                       size_t* out_n);
+SPECKV_API speckv_status_t speckv_ext_policy_get_stats(speckv_policy_t* p, speckv_policy_stats_t* out);
+
 /* ---- speculative prefetch scoring ---------------------------------------------------- */
 /* Installs the predictor's weights on the current device: embedding [vocab][emb_dim] and
  * output projection [vocab][hidden], fp32, row-major -- the two tables

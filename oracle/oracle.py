@@ -32,6 +32,7 @@ _i8p = C.POINTER(C.c_int8)
 _f32p = C.POINTER(C.c_float)
 _u32p = C.POINTER(C.c_uint32)
 _u64p = C.POINTER(C.c_uint64)
+_f64p = C.POINTER(C.c_double)
 
 
 def build(ref: bool = True) -> None:
@@ -106,6 +107,22 @@ class Port:
                                                    _f32p, C.c_size_t]
             L.oracle_fnv1a64.restype = C.c_uint64
             L.oracle_fnv1a64.argtypes = [C.c_void_p, C.c_size_t]
+            L.oracle_policy_new.restype = C.c_void_p
+            L.oracle_policy_new.argtypes = [C.c_uint64] * 4
+            L.oracle_policy_free.argtypes = [C.c_void_p]
+            for f in ("oracle_policy_touch", "oracle_policy_release"):
+                getattr(L, f).restype = None
+                getattr(L, f).argtypes = [C.c_void_p, C.c_uint64]
+            for f in ("oracle_policy_is_hot", "oracle_policy_demote", "oracle_policy_tier"):
+                getattr(L, f).restype = C.c_int
+                getattr(L, f).argtypes = [C.c_void_p, C.c_uint64]
+            L.oracle_policy_place.restype = C.c_int
+            L.oracle_policy_place.argtypes = [C.c_void_p, C.c_uint64, C.c_int]
+            L.oracle_policy_promote.restype = C.c_int
+            L.oracle_policy_promote.argtypes = [C.c_void_p, C.c_uint64, _u64p]
+            L.oracle_policy_lru.restype = C.c_size_t
+            L.oracle_policy_lru.argtypes = [C.c_void_p, _u64p, C.c_size_t]
+            L.oracle_policy_stats.argtypes = [C.c_void_p, C.c_void_p]
             cls._lib = L
         return cls._lib
 
@@ -288,6 +305,15 @@ class Ref:
             L.ref_mm_translate.argtypes = [C.c_void_p, C.c_uint64]
             L.ref_mm_is_in_cache.restype = C.c_int
             L.ref_mm_is_in_cache.argtypes = [C.c_void_p, C.c_uint64, C.c_int]
+            for f in ("ref_mm_touch", "ref_mm_release"):
+                getattr(L, f).restype = None
+                getattr(L, f).argtypes = [C.c_void_p, C.c_uint64]
+            for f in ("ref_mm_is_hot", "ref_mm_promote", "ref_mm_demote", "ref_mm_tier"):
+                getattr(L, f).restype = C.c_int
+                getattr(L, f).argtypes = [C.c_void_p, C.c_uint64]
+            L.ref_mm_lru.restype = C.c_size_t
+            L.ref_mm_lru.argtypes = [C.c_void_p, _u64p, C.c_size_t]
+            L.ref_mm_stats.argtypes = [C.c_void_p, _u64p, _f64p]
             cls._lib = L
             cls._engine = C.c_void_p(L.ref_engine_new())
         return cls._lib
@@ -360,6 +386,96 @@ class Ref:
                               _ptr(scales, _f32p), _ptr(comp, _u32p), out.ctypes.data, threads,
                               int(do_compress), int(do_decompress))
         return payload.reshape(n_groups, slot), scales, comp, out.reshape(n_groups, group_elems)
+
+
+class PolicyStats(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in ("l1_hits", "l1_misses", "l2_hits", "l2_misses", "l3_accesses",
+                                          "migrations_l1_to_l3", "migrations_l3_to_l1")] + \
+               [("l1_hit_rate", C.c_double), ("l2_hit_rate", C.c_double)] + \
+               [(n, C.c_uint64) for n in ("l1_pages", "l2_pages", "l3_pages")]
+
+
+def run_policy_trace(ops, n_pages: int, caps=(1 << 40, 1 << 40, 1 << 40), impl: str = "port"):
+    """Runs a residency-policy trace and returns what an observer can see.
+
+    ops: list of (op, page[, tier]) with op in place / touch / hot / promote / demote / release.
+    impl "port" = oracle/speckv_oracle.c; impl "ref" = the reference's CXLMemoryManager through
+    oracle/_ref (one page per allocation; its capacities are whole GiB, so `caps` is ignored and a
+    trace for it must never fill L1 -- the reference's eviction path deadlocks).
+    Returns {"results": [...], "tiers": [...], "lru": [...], "stats": {...}}."""
+    results = []
+    if impl == "port":
+        L = Port.lib()
+        h = C.c_void_p(L.oracle_policy_new(n_pages, *caps))
+        for op in ops:
+            name, page = op[0], op[1]
+            if name == "place":
+                results.append(L.oracle_policy_place(h, page, op[2]))
+            elif name == "touch":
+                L.oracle_policy_touch(h, page); results.append(0)
+            elif name == "hot":
+                results.append(L.oracle_policy_is_hot(h, page))
+            elif name == "promote":
+                ev = C.c_uint64()
+                ok = L.oracle_policy_promote(h, page, C.byref(ev))
+                results.append((ok, None if ev.value == 0xFFFFFFFFFFFFFFFF else ev.value))
+            elif name == "demote":
+                results.append(L.oracle_policy_demote(h, page))
+            elif name == "release":
+                L.oracle_policy_release(h, page); results.append(0)
+            else:
+                raise ValueError(name)
+        tiers = [L.oracle_policy_tier(h, g) for g in range(n_pages)]
+        buf = (C.c_uint64 * max(n_pages, 1))()
+        k = L.oracle_policy_lru(h, buf, n_pages)
+        lru = [int(buf[i]) for i in range(k)]
+        st = PolicyStats()
+        L.oracle_policy_stats(h, C.byref(st))
+        stats = {n: getattr(st, n) for n, _ in PolicyStats._fields_}
+        L.oracle_policy_free(h)
+    else:
+        L = Ref.lib()
+        m = C.c_void_p(L.ref_mm_new())
+        va_of, page_of = {}, {}
+        for op in ops:
+            name, page = op[0], op[1]
+            if name == "place":
+                if page in va_of:
+                    results.append(-1)
+                    continue
+                va = L.ref_mm_allocate(m, 4096, 0, op[2])
+                va_of[page] = va; page_of[va] = page
+                results.append(L.ref_mm_tier(m, va))
+                continue
+            va = va_of.get(page, 0x10)           # an address the manager has never seen
+            if name == "touch":
+                L.ref_mm_touch(m, va); results.append(0)
+            elif name == "hot":
+                results.append(L.ref_mm_is_hot(m, va))
+            elif name == "promote":
+                results.append((L.ref_mm_promote(m, va), None))
+            elif name == "demote":
+                results.append(L.ref_mm_demote(m, va))
+            elif name == "release":
+                L.ref_mm_release(m, va); va_of.pop(page, None); results.append(0)
+            else:
+                raise ValueError(name)
+        tiers = [L.ref_mm_tier(m, va_of[g]) if g in va_of else 255 for g in range(n_pages)]
+        k = L.ref_mm_lru(m, None, 0)
+        buf = (C.c_uint64 * max(k, 1))()
+        k = L.ref_mm_lru(m, buf, k)
+        # entries of released L2/L3 pages dangle in the reference's list (:89-100); their addresses are
+        # never handed out again, so only the entries of live pages are observable
+        lru = [page_of[int(buf[i])] for i in range(k) if va_of.get(page_of.get(int(buf[i]))) == int(buf[i])]
+        c7 = (C.c_uint64 * 7)(); r2 = (C.c_double * 2)()
+        L.ref_mm_stats(m, c7, r2)
+        names = ["l1_hits", "l1_misses", "l2_hits", "l2_misses", "l3_accesses", "migrations_l1_to_l3", "migrations_l3_to_l1"]
+        stats = {n: int(c7[i]) for i, n in enumerate(names)}
+        stats["l1_hit_rate"], stats["l2_hit_rate"] = r2[0], r2[1]
+        for t, n in enumerate(("l1_pages", "l2_pages", "l3_pages")):
+            stats[n] = sum(1 for x in tiers if x == t)
+        L.ref_mm_free(m)
+    return {"results": results, "tiers": tiers, "lru": lru, "stats": stats}
 
 
 def splitmix64_block(seed: int, n: int) -> np.ndarray:

@@ -234,5 +234,34 @@ uint64_t ref_mm_translate(void* m, uint64_t va) {
 int ref_mm_is_in_cache(void* m, uint64_t va, int tier) {
     return static_cast<cxlspeckv::CXLMemoryManager*>(m)->is_in_cache(va, static_cast<cxlspeckv::MemoryTier>(tier)) ? 1 : 0;
 }
+// residency policy entry points (:130-258).  promote_to_l1 is only safe to call while L1 has room:
+// its eviction path re-locks page_table_mutex_ (evict_l1_lru -> demote_to_l3) and never returns.
+void ref_mm_touch(void* m, uint64_t va) { static_cast<cxlspeckv::CXLMemoryManager*>(m)->update_access_tracking(va); }
+int ref_mm_is_hot(void* m, uint64_t va) { return static_cast<cxlspeckv::CXLMemoryManager*>(m)->is_hot_page(va) ? 1 : 0; }
+int ref_mm_promote(void* m, uint64_t va) { return static_cast<cxlspeckv::CXLMemoryManager*>(m)->promote_to_l1(va) ? 1 : 0; }
+int ref_mm_demote(void* m, uint64_t va) { return static_cast<cxlspeckv::CXLMemoryManager*>(m)->demote_to_l3(va) ? 1 : 0; }
+void ref_mm_release(void* m, uint64_t va) { static_cast<cxlspeckv::CXLMemoryManager*>(m)->deallocate(va); }
+int ref_mm_tier(void* m, uint64_t va) {
+    auto* mm = static_cast<cxlspeckv::CXLMemoryManager*>(m);
+    for (int t = 0; t < 3; ++t)
+        if (mm->is_in_cache(va, static_cast<cxlspeckv::MemoryTier>(t))) return t;
+    return 255;
+}
+size_t ref_mm_lru(void* m, uint64_t* out, size_t cap) {   // l1_lru_list_, least recently used first
+    auto* mm = static_cast<cxlspeckv::CXLMemoryManager*>(m);
+    size_t k = 0;
+    for (uint64_t va : mm->l1_lru_list_) {
+        if (k < cap) out[k] = va;
+        ++k;
+    }
+    return k;
+}
+// {l1_hits, l1_misses, l2_hits, l2_misses, l3_accesses, migrations_l1_to_l3, migrations_l3_to_l1}, rates
+void ref_mm_stats(void* m, uint64_t* counters7, double* rates2) {
+    auto st = static_cast<cxlspeckv::CXLMemoryManager*>(m)->get_statistics();
+    counters7[0] = st.l1_hits; counters7[1] = st.l1_misses; counters7[2] = st.l2_hits; counters7[3] = st.l2_misses;
+    counters7[4] = st.l3_accesses; counters7[5] = st.migrations_l1_to_l3; counters7[6] = st.migrations_l3_to_l1;
+    rates2[0] = st.l1_hit_rate; rates2[1] = st.l2_hit_rate;
+}
 
 }  // extern "C"

@@ -470,6 +470,142 @@ unsigned oracle_depth_feedback(oracle_depth_t* d, int was_correct) {
     return d->depth;
 }
 
+/* ---- tier residency policy (cxl_memory_manager.cpp:28-324) ------------------------------------ */
+#define POL_NONE 0xffffffffffffffffull
+struct oracle_policy {
+    uint64_t n, cap[3], used[3];
+    uint8_t* tier;            /* 0,1,2 or 255 */
+    uint32_t* count;
+    uint64_t *prev, *next;    /* LRU list links; POL_NONE = end */
+    uint8_t* in_lru;
+    uint64_t head, tail;      /* head = least recently used */
+    oracle_policy_stats_t st;
+};
+
+oracle_policy_t* oracle_policy_new(uint64_t n_pages, uint64_t l1_cap, uint64_t l2_cap, uint64_t l3_cap) {
+    oracle_policy_t* p = (oracle_policy_t*)calloc(1, sizeof(*p));
+    if (!p) return NULL;
+    p->n = n_pages;
+    p->cap[0] = l1_cap; p->cap[1] = l2_cap; p->cap[2] = l3_cap;
+    p->tier = (uint8_t*)malloc(n_pages ? n_pages : 1);
+    p->count = (uint32_t*)calloc(n_pages ? n_pages : 1, sizeof(uint32_t));
+    p->prev = (uint64_t*)malloc((n_pages ? n_pages : 1) * sizeof(uint64_t));
+    p->next = (uint64_t*)malloc((n_pages ? n_pages : 1) * sizeof(uint64_t));
+    p->in_lru = (uint8_t*)calloc(n_pages ? n_pages : 1, 1);
+    memset(p->tier, 255, n_pages ? n_pages : 1);
+    p->head = p->tail = POL_NONE;
+    return p;
+}
+
+void oracle_policy_free(oracle_policy_t* p) {
+    if (!p) return;
+    free(p->tier); free(p->count); free(p->prev); free(p->next); free(p->in_lru); free(p);
+}
+
+static void pol_unlink(oracle_policy_t* p, uint64_t g) {
+    if (!p->in_lru[g]) return;
+    if (p->prev[g] != POL_NONE) p->next[p->prev[g]] = p->next[g]; else p->head = p->next[g];
+    if (p->next[g] != POL_NONE) p->prev[p->next[g]] = p->prev[g]; else p->tail = p->prev[g];
+    p->in_lru[g] = 0;
+}
+
+/* update_lru(): remove if present, append as most recently used  (:319-324) */
+static void pol_to_back(oracle_policy_t* p, uint64_t g) {
+    pol_unlink(p, g);
+    p->prev[g] = p->tail; p->next[g] = POL_NONE;
+    if (p->tail != POL_NONE) p->next[p->tail] = g; else p->head = g;
+    p->tail = g;
+    p->in_lru[g] = 1;
+}
+
+int oracle_policy_place(oracle_policy_t* p, uint64_t g, int tier) {
+    if (g >= p->n || tier < 0 || tier > 2 || p->tier[g] != 255) return -1;
+    /* only an L1 preference falls back, to L3  (:37-40) */
+    if (tier == 0 && p->used[0] + 1 > p->cap[0]) tier = 2;
+    p->tier[g] = (uint8_t)tier;
+    p->used[tier]++;
+    p->count[g] = 0;
+    return tier;
+}
+
+void oracle_policy_release(oracle_policy_t* p, uint64_t g) {
+    if (g >= p->n || p->tier[g] == 255) return;
+    /* the reference drops the LRU entry only for an L1 page (:89-92); an L2/L3 page that was
+     * touched keeps a dangling entry there.  Pages are indices here, so the entry is always dropped. */
+    pol_unlink(p, g);
+    p->used[p->tier[g]]--;
+    p->tier[g] = 255;
+    p->count[g] = 0;
+}
+
+void oracle_policy_touch(oracle_policy_t* p, uint64_t g) {
+    if (g >= p->n || p->tier[g] == 255) return;
+    p->count[g]++;
+    if (p->tier[g] == 0) p->st.l1_hits++;
+    else if (p->tier[g] == 1) p->st.l2_hits++;
+    else p->st.l3_accesses++;
+    pol_to_back(p, g);
+}
+
+int oracle_policy_is_hot(oracle_policy_t* p, uint64_t g) {
+    if (g >= p->n || p->tier[g] == 255) return 0;
+    return p->count[g] > 10;
+}
+
+int oracle_policy_demote(oracle_policy_t* p, uint64_t g) {
+    if (g >= p->n || p->tier[g] == 255 || p->tier[g] == 2) return 0;
+    if (p->tier[g] == 0) {
+        pol_unlink(p, g);
+        p->st.migrations_l1_to_l3++;
+    }
+    p->used[p->tier[g]]--;
+    p->tier[g] = 2;
+    p->used[2]++;
+    return 1;
+}
+
+int oracle_policy_promote(oracle_policy_t* p, uint64_t g, uint64_t* evicted) {
+    if (evicted) *evicted = POL_NONE;
+    if (g >= p->n || p->tier[g] == 255 || p->tier[g] == 0) return 0;
+    if (p->used[0] + 1 > p->cap[0]) {
+        /* evict_l1_lru (:285-293), repeated until an L1 page has been demoted */
+        while (p->head != POL_NONE) {
+            const uint64_t v = p->head;
+            pol_unlink(p, v);
+            if (p->tier[v] == 0) {
+                oracle_policy_demote(p, v);
+                if (evicted) *evicted = v;
+                break;
+            }
+        }
+    }
+    if (p->tier[g] == 2) p->st.migrations_l3_to_l1++;
+    p->used[p->tier[g]]--;
+    p->tier[g] = 0;
+    p->used[0]++;
+    pol_to_back(p, g);
+    return 1;
+}
+
+int oracle_policy_tier(const oracle_policy_t* p, uint64_t g) { return g < p->n ? p->tier[g] : 255; }
+
+size_t oracle_policy_lru(const oracle_policy_t* p, uint64_t* out, size_t cap) {
+    size_t k = 0;
+    for (uint64_t g = p->head; g != POL_NONE; g = p->next[g]) {
+        if (k < cap) out[k] = g;
+        ++k;
+    }
+    return k;
+}
+
+void oracle_policy_stats(const oracle_policy_t* p, oracle_policy_stats_t* out) {
+    *out = p->st;
+    const uint64_t t1 = out->l1_hits + out->l1_misses, t2 = out->l2_hits + out->l2_misses;
+    out->l1_hit_rate = t1 ? (double)out->l1_hits / (double)t1 : 0.0;
+    out->l2_hit_rate = t2 ? (double)out->l2_hits / (double)t2 : 0.0;
+    out->l1_pages = p->used[0]; out->l2_pages = p->used[1]; out->l3_pages = p->used[2];
+}
+
 uint64_t oracle_fnv1a64(const void* p, size_t n) {
     const uint8_t* b = (const uint8_t*)p;
     uint64_t h = 0xcbf29ce484222325ULL;

@@ -175,3 +175,49 @@ def test_division_identities_quick():
     subprocess.check_call(["make", "-s", "-C", here, "verify"])
     out = subprocess.run([os.path.join(here, "verify_fastdiv"), "quick"], capture_output=True, text=True, timeout=600)
     assert out.returncode == 0 and out.stdout.strip().endswith("OK"), out.stdout
+
+
+def test_policy_port_matches_reference_manager():
+    """oracle_policy_* against the reference's CXLMemoryManager (oracle/_ref) on random traces that
+    never fill L1 (its eviction path deadlocks): per-call results, final tiers, LRU order, stats."""
+    import random
+    from oracle.oracle import run_policy_trace
+    for seed in range(4):
+        rng = random.Random(seed)
+        n = rng.choice([8, 64, 300])
+        ops = [("place", g, rng.choice([0, 1, 2, 2])) for g in range(n) if rng.random() < 0.9]
+        for _ in range(3000):
+            r, g = rng.random(), rng.randrange(n)
+            if r < 0.6:
+                ops.append(("touch", g))
+            elif r < 0.7:
+                ops.append(("hot", g))
+            elif r < 0.8:
+                ops.append(("promote", g))
+            elif r < 0.9:
+                ops.append(("demote", g))
+            elif r < 0.93:
+                ops.append(("release", g))
+            else:
+                ops.append(("place", g, rng.choice([0, 1, 2])))
+        a = run_policy_trace(ops, n, impl="port")
+        b = run_policy_trace(ops, n, impl="ref")
+        assert a["results"] == b["results"]
+        assert a["tiers"] == b["tiers"]
+        assert a["lru"] == b["lru"]
+        assert a["stats"] == b["stats"]
+
+
+def test_policy_port_eviction_semantics():
+    """The defined eviction (the reference's evict_l1_lru step repeated until it frees a page)."""
+    from oracle.oracle import run_policy_trace
+    ops = [("place", g, 2) for g in range(6)] + [("place", 6, 1)]
+    ops += [("touch", 5), ("touch", 6)]                    # non-L1 entries at the front of the LRU list
+    ops += [("promote", 0), ("promote", 1)]                # L1 (capacity 2) now holds 0, 1; LRU: 5 6 0 1
+    ops += [("promote", 2)]                                # full: pops 5, 6 (dropped), then evicts 0
+    ops += [("touch", 1), ("promote", 3)]                  # LRU: 2 1 -> evicts 2
+    r = run_policy_trace(ops, 7, caps=(2, 1 << 40, 1 << 40), impl="port")
+    assert r["results"][-3:] == [(1, 0), 0, (1, 2)]
+    assert r["tiers"] == [2, 0, 2, 0, 2, 2, 1]
+    assert r["lru"] == [1, 3]
+    assert r["stats"]["migrations_l1_to_l3"] == 2 and r["stats"]["migrations_l3_to_l1"] == 4
