@@ -78,6 +78,10 @@ def lib() -> C.CDLL:
     L.speckv_ext_decompress.restype = C.c_int
     L.speckv_ext_decompress_indexed.argtypes = [vp, sz, vp, vp, vp, sz, sz, C.c_int, vp, vp, C.c_int, vp]
     L.speckv_ext_decompress_indexed.restype = C.c_int
+    L.speckv_ext_compress_gather.argtypes = [vp, vp, C.c_int, sz, sz, vp, sz, vp, vp, C.c_int, vp]
+    L.speckv_ext_compress_gather.restype = C.c_int
+    L.speckv_ext_decompress_scatter.argtypes = [vp, sz, vp, vp, vp, vp, sz, sz, C.c_int, vp, vp, C.c_int, vp]
+    L.speckv_ext_decompress_scatter.restype = C.c_int
     L.speckv_ext_compress_host.argtypes = [vp, C.c_int, sz, sz, vp, sz, vp, vp, C.c_int]
     L.speckv_ext_compress_host.restype = C.c_int
     L.speckv_ext_decompress_host.argtypes = [vp, sz, vp, vp, sz, sz, C.c_int, vp, vp, C.c_int]

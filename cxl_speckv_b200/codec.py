@@ -94,6 +94,61 @@ def decompress_indexed(c: CompressedKV, block_index: torch.Tensor, out: Optional
     return out
 
 
+def compress_gather(cache: torch.Tensor, block_table: torch.Tensor, scheme: int = COMP_INT8_DELTA_RLE,
+                    out: Optional[CompressedKV] = None) -> CompressedKV:
+    """Compress the blocks of a paged KV cache named by block_table, reading them where they lie.
+
+    cache: [num_blocks, ...] contiguous CUDA tensor (one block = one codec group, e.g. vLLM's
+    [num_blocks, block_size, kv_heads, head_dim]); block_table: int32 CUDA tensor of block ids.
+    Stored group i encodes cache block block_table[i]."""
+    if not cache.is_cuda or cache.dtype not in _DTYPES or not cache.is_contiguous():
+        raise ValueError("compress_gather() takes a contiguous CUDA fp16/bf16/fp32 cache tensor")
+    group_elems = cache[0].numel()
+    block_table = block_table.to(device=cache.device, dtype=torch.int32).contiguous()
+    n_groups = block_table.numel()
+    sb = slot_bytes(group_elems, scheme)
+    if out is None:
+        out = CompressedKV(torch.empty((n_groups, sb), dtype=torch.uint8, device=cache.device),
+                           torch.empty(n_groups, dtype=torch.float32, device=cache.device),
+                           torch.empty(n_groups, dtype=torch.int32, device=cache.device),
+                           group_elems, cache.dtype, scheme)
+    with torch.cuda.device(cache.device):
+        st = lib().speckv_ext_compress_gather(cache.data_ptr(), block_table.data_ptr(), _DTYPES[cache.dtype],
+                                              group_elems, n_groups, out.payload.data_ptr(), out.payload.shape[1],
+                                              out.scales.data_ptr(), out.comp_bytes.data_ptr(), scheme, _stream())
+    check(st, "speckv_ext_compress_gather")
+    return out
+
+
+def decompress_scatter(c: CompressedKV, cache: torch.Tensor, block_table: torch.Tensor,
+                       src_index: Optional[torch.Tensor] = None,
+                       out_elems: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Decode stored blocks straight into the paged KV cache: request i decodes stored block
+    src_index[i] (block i when src_index is None) into cache block block_table[i]."""
+    if not cache.is_cuda or cache.dtype not in _DTYPES or not cache.is_contiguous():
+        raise ValueError("decompress_scatter() takes a contiguous CUDA fp16/bf16/fp32 cache tensor")
+    if cache[0].numel() != c.group_elems:
+        raise ValueError("cache block size differs from the stored group size")
+    block_table = block_table.to(device=cache.device, dtype=torch.int32).contiguous()
+    n = block_table.numel()
+    if src_index is not None:
+        src_index = src_index.to(device=cache.device, dtype=torch.int32).contiguous()
+        if src_index.numel() != n:
+            raise ValueError("src_index and block_table differ in length")
+    elif n != c.n_groups:
+        raise ValueError("block_table must name one cache block per stored block")
+    with torch.cuda.device(cache.device):
+        st = lib().speckv_ext_decompress_scatter(c.payload.data_ptr(), c.payload.shape[1], c.scales.data_ptr(),
+                                                 c.comp_bytes.data_ptr(),
+                                                 src_index.data_ptr() if src_index is not None else None,
+                                                 block_table.data_ptr(), n, c.group_elems, _DTYPES[cache.dtype],
+                                                 cache.data_ptr(),
+                                                 out_elems.data_ptr() if out_elems is not None else None,
+                                                 c.scheme, _stream())
+    check(st, "speckv_ext_decompress_scatter")
+    return cache
+
+
 def translate(va: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Batched FPGACacheEngine::translate_address over an int64 tensor of (uint64) addresses."""
     if va.dtype != torch.int64 or not va.is_cuda:

@@ -331,6 +331,67 @@ speckv_status_t speckv_ext_decompress_indexed(const void* d_payload, size_t slot
     return status_of(e);
 }
 
+speckv_status_t speckv_ext_compress_gather(const void* d_cache, const uint32_t* d_block_table, speckv_dtype_t dtype,
+                                           size_t group_elems, size_t n_groups, void* d_payload, size_t slot_bytes,
+                                           float* d_scales, uint32_t* d_comp_bytes, speckv_comp_scheme_t scheme,
+                                           void* cuda_stream) {
+    if (device_count() <= 0) return SPECKV_ERR_DRIVER;
+    if (!valid_common(dtype, group_elems, n_groups, slot_bytes, scheme) || scheme == SPECKV_COMP_FP16) return SPECKV_ERR_INVAL;
+    if (n_groups == 0) return SPECKV_OK;
+    if (!d_payload || !d_scales || !d_comp_bytes || !d_block_table || (!d_cache && group_elems)) return SPECKV_ERR_INVAL;
+    if (reinterpret_cast<uintptr_t>(d_payload) & 15) return SPECKV_ERR_INVAL;
+    CodecArgs a;
+    a.in = d_cache;
+    a.elem_index = d_block_table;
+    a.payload = d_payload;
+    a.scales = d_scales;
+    a.comp_bytes = d_comp_bytes;
+    a.slot_bytes = slot_bytes;
+    a.group_elems = (uint32_t)group_elems;
+    a.n_groups = (uint32_t)n_groups;
+    a.dtype = dtype;
+    a.scheme = scheme;
+    a.sm_count = current_sm_count();
+    cudaError_t e = launch_compress(a, static_cast<cudaStream_t>(cuda_stream));
+    if (e == cudaSuccess) {
+        g_n_comp += n_groups;
+        g_b_comp += (uint64_t)n_groups * group_elems * elem_bytes(dtype);
+    }
+    return status_of(e);
+}
+
+speckv_status_t speckv_ext_decompress_scatter(const void* d_payload, size_t slot_bytes, const float* d_scales,
+                                              const uint32_t* d_comp_bytes, const uint32_t* d_src_index,
+                                              const uint32_t* d_block_table, size_t n_requests, size_t group_elems,
+                                              speckv_dtype_t dtype, void* d_cache, uint32_t* d_out_elems,
+                                              speckv_comp_scheme_t scheme, void* cuda_stream) {
+    if (device_count() <= 0) return SPECKV_ERR_DRIVER;
+    if (!valid_common(dtype, group_elems, n_requests, slot_bytes, scheme) || scheme == SPECKV_COMP_FP16) return SPECKV_ERR_INVAL;
+    if (n_requests == 0) return SPECKV_OK;
+    if (!d_payload || !d_scales || !d_comp_bytes || !d_block_table || (!d_cache && group_elems)) return SPECKV_ERR_INVAL;
+    if (reinterpret_cast<uintptr_t>(d_payload) & 15) return SPECKV_ERR_INVAL;
+    CodecArgs a;
+    a.out = d_cache;
+    a.elem_index = d_block_table;
+    a.payload = const_cast<void*>(d_payload);
+    a.scales = const_cast<float*>(d_scales);
+    a.comp_bytes = const_cast<uint32_t*>(d_comp_bytes);
+    a.out_elems = d_out_elems;
+    a.src_index = d_src_index;
+    a.slot_bytes = slot_bytes;
+    a.group_elems = (uint32_t)group_elems;
+    a.n_groups = (uint32_t)n_requests;
+    a.dtype = dtype;
+    a.scheme = scheme;
+    a.sm_count = current_sm_count();
+    cudaError_t e = launch_decompress(a, static_cast<cudaStream_t>(cuda_stream));
+    if (e == cudaSuccess) {
+        g_n_decomp += n_requests;
+        g_b_decomp += (uint64_t)n_requests * group_elems * elem_bytes(dtype);
+    }
+    return status_of(e);
+}
+
 speckv_status_t speckv_ext_compress_host(const void* h_in, speckv_dtype_t dtype, size_t group_elems, size_t n_groups,
                                          void* h_payload, size_t slot_bytes, float* h_scales, uint32_t* h_comp_bytes,
                                          speckv_comp_scheme_t scheme) {

@@ -17,6 +17,9 @@ struct CodecArgs {
     const uint32_t* src_index = nullptr;  // decompress, optional: output group i decodes payload group src_index[i]
     const uint64_t* slot_offsets = nullptr;  // decompress, optional: block b starts at payload + slot_offsets[b]
                                              // (16 B aligned, packed container) instead of b * slot_bytes
+    const uint32_t* elem_index = nullptr;    // optional paged gather / scatter: group i's elements are block
+                                             // elem_index[i] of the element buffer (compress reads `in` there,
+                                             // decompress writes `out` there) instead of block i
     size_t slot_bytes = 0;
     uint32_t group_elems = 0;
     uint32_t n_groups = 0;

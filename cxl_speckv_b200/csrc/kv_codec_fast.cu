@@ -345,7 +345,7 @@ template <typename T, int R>
 __global__ void __launch_bounds__(kThreadsF, kCtasPerSm)
 compress_fast_kernel(const T* __restrict__ in, uint32_t n_groups, uint8_t* __restrict__ payload, size_t slot_bytes,
                      float* __restrict__ scales, uint32_t* __restrict__ comp_bytes,
-                     uint32_t* __restrict__ needs_generic) {
+                     uint32_t* __restrict__ needs_generic, const uint32_t* __restrict__ elem_index) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     FastSmem& sm = *reinterpret_cast<FastSmem*>(smem_raw);
     constexpr int C = R > kW ? R / kW : 1;        // CTAs per group (cluster size)
@@ -365,7 +365,8 @@ compress_fast_kernel(const T* __restrict__ in, uint32_t n_groups, uint8_t* __res
         ridx = warp % R;
     }
     const bool active = g < n_groups;
-    const T* rin = in + (size_t)g * G + (size_t)ridx * kRegion;
+    // paged gather: the group's elements are block elem_index[g] of the element buffer
+    const T* rin = in + (size_t)((elem_index && active) ? elem_index[g] : g) * G + (size_t)ridx * kRegion;
     uint8_t* reg = sm.tile[warp] + kPadBytes;
     const uint32_t reg_s = smem_u32(reg);
     const uint32_t mb = smem_u32(&sm.mbar[warp]);
@@ -567,7 +568,8 @@ __global__ void __launch_bounds__(kThreadsF, kCtasPerSm)
 decompress_fast_kernel(const uint8_t* __restrict__ payload, size_t slot_bytes, const float* __restrict__ scales,
                        const uint32_t* __restrict__ comp_bytes, uint32_t n_groups, T* __restrict__ out,
                        uint32_t* __restrict__ out_elems, uint32_t* __restrict__ needs_generic,
-                       const uint32_t* __restrict__ src_index, const uint64_t* __restrict__ slot_offsets) {
+                       const uint32_t* __restrict__ src_index, const uint64_t* __restrict__ slot_offsets,
+                       const uint32_t* __restrict__ elem_index) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     FastSmem& sm = *reinterpret_cast<FastSmem*>(smem_raw);
     constexpr int C = R > kW ? R / kW : 1;
@@ -676,7 +678,7 @@ decompress_fast_kernel(const uint8_t* __restrict__ payload, size_t slot_bytes, c
     if (any_cplx || np == 0) return;
 
     // ---- C. expand in place: element e of run j carries code q_before + ... + v_j * (e - start_j + 1) ----
-    uint8_t* gout = reinterpret_cast<uint8_t*>(out + (size_t)g * G);
+    uint8_t* gout = reinterpret_cast<uint8_t*>(out + (size_t)(elem_index ? elem_index[g] : g) * G);   // paged scatter
     const uint32_t e0 = e_before;
     uint32_t ecur = e0;                       // next element index to produce
     uint32_t qcur = q_before & 0xffu;         // code of element ecur - 1
@@ -786,7 +788,8 @@ cudaError_t compress_fast_t(int R, const CodecArgs& a, uint32_t* flags, cudaStre
     size_t sb = a.slot_bytes;
     float* sc = a.scales;
     uint32_t* cb = a.comp_bytes;
-    void* args[] = {&in, &n, &pay, &sb, &sc, &cb, &flags};
+    const uint32_t* ei = a.elem_index;
+    void* args[] = {&in, &n, &pay, &sb, &sc, &cb, &flags, &ei};
     switch (R) {
 #define SPECKV_CASE(RR) case RR: return launch_clustered(compress_fast_kernel<T, RR>, RR, n, st, args);
         SPECKV_CASE(1) SPECKV_CASE(2) SPECKV_CASE(4) SPECKV_CASE(8) SPECKV_CASE(16) SPECKV_CASE(32) SPECKV_CASE(64) SPECKV_CASE(128)
@@ -806,7 +809,8 @@ cudaError_t decompress_fast_t(int R, const CodecArgs& a, uint32_t* flags, cudaSt
     uint32_t* oe = a.out_elems;
     const uint32_t* si = a.src_index;
     const uint64_t* so = a.slot_offsets;
-    void* args[] = {&pay, &sb, &sc, &cb, &n, &out, &oe, &flags, &si, &so};
+    const uint32_t* ei = a.elem_index;
+    void* args[] = {&pay, &sb, &sc, &cb, &n, &out, &oe, &flags, &si, &so, &ei};
     switch (R) {
 #define SPECKV_CASE(RR) case RR: return launch_clustered(decompress_fast_kernel<T, RR>, RR, n, st, args);
         SPECKV_CASE(1) SPECKV_CASE(2) SPECKV_CASE(4) SPECKV_CASE(8) SPECKV_CASE(16) SPECKV_CASE(32) SPECKV_CASE(64) SPECKV_CASE(128)

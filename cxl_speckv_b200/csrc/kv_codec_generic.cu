@@ -182,7 +182,7 @@ __global__ void __launch_bounds__(kThreads)
 compress_rle_generic_kernel(const T* __restrict__ in, uint32_t G, uint32_t n_groups,
                             uint8_t* __restrict__ payload, size_t slot_bytes,
                             float* __restrict__ scales, uint32_t* __restrict__ comp_bytes,
-                            const uint32_t* __restrict__ only_flagged) {
+                            const uint32_t* __restrict__ only_flagged, const uint32_t* __restrict__ elem_index) {
     __shared__ __align__(16) uint16_t stage[kTile + 16];
     __shared__ int wbuf[kWarps];
     __shared__ float fbuf[kWarps];
@@ -193,7 +193,7 @@ compress_rle_generic_kernel(const T* __restrict__ in, uint32_t G, uint32_t n_gro
     __shared__ uint32_t smask[kWarps];
     GroupIter it(only_flagged, n_groups, smask);
     for (uint32_t g; it.next(g);) {
-        const T* gin = in + (size_t)g * G;
+        const T* gin = in + (size_t)(elem_index ? elem_index[g] : g) * G;
         uint8_t* gout = payload + (size_t)g * slot_bytes;
         const bool vec_ok = (reinterpret_cast<uintptr_t>(gin) & 15) == 0;
 
@@ -319,7 +319,8 @@ decompress_rle_generic_kernel(const uint8_t* __restrict__ payload, size_t slot_b
                               const float* __restrict__ scales, const uint32_t* __restrict__ comp_bytes,
                               uint32_t G, uint32_t n_groups, T* __restrict__ out,
                               uint32_t* __restrict__ out_elems, const uint32_t* __restrict__ only_flagged,
-                              const uint32_t* __restrict__ src_index, const uint64_t* __restrict__ slot_offsets) {
+                              const uint32_t* __restrict__ src_index, const uint64_t* __restrict__ slot_offsets,
+                              const uint32_t* __restrict__ elem_index) {
     // Output-stationary expansion: a chunk of 2048 pairs is scanned once (start position and
     // starting code of every pair go to shared memory); then every thread produces 16 consecutive
     // output elements at a time -- binary search for the pair covering its first element, then a
@@ -341,7 +342,7 @@ decompress_rle_generic_kernel(const uint8_t* __restrict__ payload, size_t slot_b
         npairs = min(npairs, (uint32_t)(slot_bytes >> 1));
         const float s = scales[gi];
         const bool special = scale_is_special(s);
-        T* gout = out + (size_t)g * G;
+        T* gout = out + (size_t)(elem_index ? elem_index[g] : g) * G;
         const bool vec_ok = (reinterpret_cast<uintptr_t>(gout) & 15) == 0;
         const bool in_vec_ok = (reinterpret_cast<uintptr_t>(gp) & 15) == 0;
 
@@ -428,11 +429,12 @@ template <typename T>
 __global__ void __launch_bounds__(kThreads)
 compress_int8_generic_kernel(const T* __restrict__ in, uint32_t G, uint32_t n_groups,
                              uint8_t* __restrict__ payload, size_t slot_bytes,
-                             float* __restrict__ scales, uint32_t* __restrict__ comp_bytes) {
+                             float* __restrict__ scales, uint32_t* __restrict__ comp_bytes,
+                             const uint32_t* __restrict__ elem_index) {
     __shared__ float fbuf[kWarps];
     const int tid = threadIdx.x;
     for (uint32_t g = blockIdx.x; g < n_groups; g += gridDim.x) {
-        const T* gin = in + (size_t)g * G;
+        const T* gin = in + (size_t)(elem_index ? elem_index[g] : g) * G;
         uint8_t* gout = payload + (size_t)g * slot_bytes;
         const bool vec_ok = (reinterpret_cast<uintptr_t>(gin) & 15) == 0;
         const float m = group_absmax<T>(gin, G, vec_ok, fbuf);
@@ -467,14 +469,15 @@ __global__ void __launch_bounds__(kThreads)
 decompress_int8_generic_kernel(const uint8_t* __restrict__ payload, size_t slot_bytes,
                                const float* __restrict__ scales, const uint32_t* __restrict__ comp_bytes,
                                uint32_t G, uint32_t n_groups, T* __restrict__ out,
-                               uint32_t* __restrict__ out_elems, const uint32_t* __restrict__ src_index) {
+                               uint32_t* __restrict__ out_elems, const uint32_t* __restrict__ src_index,
+                               const uint32_t* __restrict__ elem_index) {
     const int tid = threadIdx.x;
     for (uint32_t g = blockIdx.x; g < n_groups; g += gridDim.x) {
         const uint32_t gi = src_index ? src_index[g] : g;
         const uint8_t* gp = payload + (size_t)gi * slot_bytes;
         const uint32_t n = min(min(comp_bytes[gi], G), (uint32_t)slot_bytes);
         const float s = scales[gi];
-        T* gout = out + (size_t)g * G;
+        T* gout = out + (size_t)(elem_index ? elem_index[g] : g) * G;
         const bool special = scale_is_special(s);
         for (uint32_t i = tid; i < n; i += kThreads)
             gout[i] = narrow<T>(special ? dequantize_special(gp[i], s) : dequantize(gp[i], s));
@@ -521,10 +524,10 @@ static cudaError_t launch_compress_t(const CodecArgs& a, cudaStream_t st, const 
     const int grid = grid_for(a.n_groups, a.sm_count, 8);
     if (a.scheme == 2) {
         compress_rle_generic_kernel<T><<<grid, kThreads, 0, st>>>(in, a.group_elems, a.n_groups, pay, a.slot_bytes,
-                                                                  a.scales, a.comp_bytes, only_flagged);
+                                                                  a.scales, a.comp_bytes, only_flagged, a.elem_index);
     } else {
         compress_int8_generic_kernel<T><<<grid, kThreads, 0, st>>>(in, a.group_elems, a.n_groups, pay, a.slot_bytes,
-                                                                   a.scales, a.comp_bytes);
+                                                                   a.scales, a.comp_bytes, a.elem_index);
     }
     count_launch();
     return cudaGetLastError();
@@ -538,11 +541,11 @@ static cudaError_t launch_decompress_t(const CodecArgs& a, cudaStream_t st, cons
     if (a.scheme == 2) {
         decompress_rle_generic_kernel<T><<<grid, kThreads, 0, st>>>(pay, a.slot_bytes, a.scales, a.comp_bytes,
                                                                     a.group_elems, a.n_groups, out, a.out_elems, only_flagged, a.src_index,
-                                                                    a.slot_offsets);
+                                                                    a.slot_offsets, a.elem_index);
     } else {
         decompress_int8_generic_kernel<T><<<grid, kThreads, 0, st>>>(pay, a.slot_bytes, a.scales, a.comp_bytes,
                                                                      a.group_elems, a.n_groups, out, a.out_elems,
-                                                                     a.src_index);
+                                                                     a.src_index, a.elem_index);
     }
     count_launch();
     return cudaGetLastError();
@@ -551,6 +554,7 @@ static cudaError_t launch_decompress_t(const CodecArgs& a, cudaStream_t st, cons
 cudaError_t launch_compress_generic(const CodecArgs& a, cudaStream_t st, const uint32_t* only_flagged) {
     if (a.n_groups == 0) return cudaSuccess;
     if (a.scheme == 0) {
+        if (a.elem_index) return cudaErrorInvalidValue;   // the raw passthrough has no gather form
         const uint32_t bytes = a.group_elems * 2u;
         cudaError_t e = cudaMemcpy2DAsync(a.payload, a.slot_bytes, a.in, bytes, bytes, a.n_groups,
                                           cudaMemcpyDeviceToDevice, st);
@@ -570,6 +574,7 @@ cudaError_t launch_compress_generic(const CodecArgs& a, cudaStream_t st, const u
 cudaError_t launch_decompress_generic(const CodecArgs& a, cudaStream_t st, const uint32_t* only_flagged) {
     if (a.n_groups == 0) return cudaSuccess;
     if (a.scheme == 0) {
+        if (a.elem_index) return cudaErrorInvalidValue;
         passthrough_out_kernel<<<grid_for(a.n_groups, a.sm_count, 8), kThreads, 0, st>>>(
             static_cast<const uint8_t*>(a.payload), a.slot_bytes, a.comp_bytes, a.group_elems, a.n_groups,
             static_cast<uint16_t*>(a.out), a.out_elems, a.src_index);

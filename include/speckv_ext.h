@@ -86,6 +86,26 @@ SPECKV_API speckv_status_t speckv_ext_decompress_indexed(const void* d_payload, 
                                               uint32_t* d_out_elems, speckv_comp_scheme_t scheme,
                                               void* cuda_stream);
 
+/* Paged gather / scatter fused with the codec: the element buffer is a paged KV cache made of
+ * blocks of group_elems elements (vLLM layout: one block = block_size tokens x kv_heads x
+ * head_dim, contiguous), and a block table says which blocks take part.
+ *   compress_gather: stored group i (slot i, scales[i], comp_bytes[i]) encodes cache block
+ *     d_block_table[i] read at d_cache + d_block_table[i] * group_elems -- no staging copy.
+ *   decompress_scatter: request i decodes stored block d_src_index[i] (or block i when
+ *     d_src_index is NULL) into cache block d_block_table[i]; d_out_elems[i] is per request.
+ * Block ids must be distinct within a scatter call.  Schemes INT8_DELTA_RLE and INT8. */
+SPECKV_API speckv_status_t speckv_ext_compress_gather(const void* d_cache, const uint32_t* d_block_table,
+                                                      speckv_dtype_t dtype, size_t group_elems, size_t n_groups,
+                                                      void* d_payload, size_t slot_bytes, float* d_scales,
+                                                      uint32_t* d_comp_bytes, speckv_comp_scheme_t scheme,
+                                                      void* cuda_stream);
+SPECKV_API speckv_status_t speckv_ext_decompress_scatter(const void* d_payload, size_t slot_bytes, const float* d_scales,
+                                                         const uint32_t* d_comp_bytes, const uint32_t* d_src_index,
+                                                         const uint32_t* d_block_table, size_t n_requests,
+                                                         size_t group_elems, speckv_dtype_t dtype, void* d_cache,
+                                                         uint32_t* d_out_elems, speckv_comp_scheme_t scheme,
+                                                         void* cuda_stream);
+
 /* Same two operations on HOST buffers: chunks are staged through device
  * buffers on internal streams (H2D, kernel, D2H overlapped) and the call
  * returns when the results are in host memory.  Pinned host memory

@@ -441,3 +441,61 @@ def test_ratio_stats_match_reference_accounting():
     assert abs(mean.value - (G * 4.0 / comp).mean()) < 1e-9 * mean.value
     # zeros: 2048 elements -> 9 pairs (255 cap) -> ratio 8192 / 18; N(0,1): ~2.0
     assert comp[0] == 18 and 1.99 < (G * 4.0 / comp[200:]).mean() < 2.03
+
+
+@pytest.mark.parametrize("G,num_blocks,n_sel", [(2048, 600, 257), (131072, 9, 5), (16384, 40, 40), (1000, 50, 21)])
+@pytest.mark.parametrize("tdt", [F16, BF16])
+def test_paged_gather_scatter_matches_staged_path(G, num_blocks, n_sel, tdt):
+    """speckv_ext_compress_gather / _decompress_scatter (paged KV cache + block table) give
+    the oracle's bytes for the listed blocks, and scatter writes only the blocks named."""
+    rng = np.random.default_rng(G + num_blocks)
+    x = make_inputs(rng, num_blocks, G, "mixed")
+    if tdt == BF16:
+        raw = bf16_from_f32(x.astype(np.float32))
+        xf = bf16_to_f32(raw)
+    else:
+        raw, xf = x, x.astype(np.float32)
+    cache = to_dev(raw, tdt).view(num_blocks, G)
+    table = rng.permutation(num_blocks)[:n_sel].astype(np.int32)
+    td = torch.from_numpy(table).to(DEV)
+    c = codec.compress_gather(cache, td)
+    torch.cuda.synchronize()
+    sel = np.ascontiguousarray(xf.reshape(num_blocks, G)[table]).reshape(-1)
+    payload, scales, comp = Port.compress_batch(sel, G, threads=8)
+    assert np.array_equal(f32_bits(c.scales.cpu().numpy()), f32_bits(scales))
+    assert np.array_equal(c.comp_bytes.cpu().numpy().view(np.uint32), comp)
+    gp = c.payload.cpu().numpy()
+    for g in range(n_sel):
+        assert np.array_equal(gp[g, :comp[g]], payload[g, :comp[g]]), g
+    # scatter into a fresh cache through a different table, picking stored blocks in reverse
+    sentinel = 0x1234
+    dst = torch.full((num_blocks, G), sentinel, dtype=torch.int16, device=DEV).view(TORCH_DT[tdt])
+    dst_table = rng.permutation(num_blocks)[:n_sel].astype(np.int32)
+    src_index = np.arange(n_sel - 1, -1, -1).astype(np.int32)
+    oel = torch.zeros(n_sel, dtype=torch.int32, device=DEV)
+    codec.decompress_scatter(c, dst, torch.from_numpy(dst_table).to(DEV), torch.from_numpy(src_index).to(DEV), oel)
+    torch.cuda.synchronize()
+    want, want_n = Port.decompress_batch(payload, scales, comp, G, tdt, threads=8)
+    got = out_bits(dst)
+    want = want.view(np.uint16).reshape(n_sel, G)
+    assert np.array_equal(oel.cpu().numpy().view(np.uint32), want_n[src_index])
+    for i in range(n_sel):
+        assert np.array_equal(got[dst_table[i]], want[src_index[i]]), i
+    untouched = np.setdiff1d(np.arange(num_blocks), dst_table)
+    assert (got[untouched] == sentinel).all()
+    # INT8 scheme through the same tables
+    c8 = codec.compress_gather(cache, td, scheme=COMP_INT8)
+    q = Port.quantize(sel[:G], scales[0])
+    assert np.array_equal(c8.payload[0, :G].cpu().numpy().view(np.int8), q)
+
+
+def test_paged_gather_scatter_rejects_bad_arguments():
+    cache = torch.zeros((4, 2048), dtype=torch.float16, device=DEV)
+    table = torch.arange(4, dtype=torch.int32, device=DEV)
+    with pytest.raises(Exception):
+        codec.compress_gather(cache, table, scheme=COMP_FP16)      # raw passthrough has no gather form
+    c = codec.compress_gather(cache, table)
+    with pytest.raises(ValueError):
+        codec.decompress_scatter(c, torch.zeros((4, 4096), dtype=torch.float16, device=DEV), table)
+    with pytest.raises(ValueError):
+        codec.decompress_scatter(c, cache, table[:2])
