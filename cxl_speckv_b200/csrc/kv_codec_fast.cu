@@ -527,7 +527,11 @@ compress_fast_kernel(const T* __restrict__ in, uint32_t n_groups, uint8_t* __res
     // pair closes a run of that length (+ its own offset)
     uint32_t carry_tail = halo_nz1 ? ((uint32_t)__clz((int)halo_nz1) >> 3) + 1u : ((uint32_t)__clz((int)halo_nz0) >> 3) + 5u;
     const int src_lane = (lane + 31) & 31;
-#pragma unroll 2
+#ifndef SPECKV_UNROLL_2B
+#define SPECKV_UNROLL_2B 8
+#endif
+    constexpr int kUnroll2b = SPECKV_UNROLL_2B;   // full unrolling measured 2.4 % faster than 2; fetching slot k + 1 early: slower
+#pragma unroll kUnroll2b
     for (int k = 0; k < kIters; ++k) {
         const uint4 st = lds128(reg + k * 512 + lane * 16);
         __syncwarp();   // every lane has read its slot before any pair of this iteration lands on it
@@ -720,7 +724,11 @@ decompress_fast_kernel(const uint8_t* __restrict__ payload, size_t slot_bytes, c
     uint32_t qcur = q_before & 0xffu;         // code of element ecur - 1
     const uint32_t sbase = reg_s - (uint32_t)kPadBytes - 2u * (e0 & ~7u);   // element i is staged at sbase + 2*i
     uint32_t rd_s = reg_s + 16u * (uint32_t)lane;   // this lane's slot of the current iteration
-#pragma unroll 1
+#ifndef SPECKV_UNROLL_C
+#define SPECKV_UNROLL_C 1
+#endif
+    constexpr int kUnrollC = SPECKV_UNROLL_C;
+#pragma unroll kUnrollC
     for (uint32_t pk = 0; pk < np; pk += 256u, rd_s += 512u) {
         const uint4 w = lds128s(rd_s);
         __syncwarp();
