@@ -61,26 +61,28 @@ __device__ __forceinline__ uint32_t quantize_exact(float x, float s) {
     return round_wrap_u8<true>(__fmul_rn(y, 127.0f));
 }
 
-// Fast form: with r = RN(1/s) (computed once per group with __frcp_rn) one
-// residual correction reproduces RN(x/s):
-//     y0 = RN(x*r);  e = RN(x - y0*s) (exact, FMA);  y = RN(y0 + e*r)
-// oracle/verify_fastdiv.c proves by exhaustion that the resulting CODE equals
-// the reference's for every (x, max) pair of fp16 values, and for every pair of
-// bf16 values with max >= 2^-60; groups outside that domain (and fp32 input)
-// take quantize_exact.  |t| <= 16130 here, so no range check is needed.
-__device__ __forceinline__ uint32_t quantize_fast(float x, float s, float r) {
-    float y0 = __fmul_rn(x, r);
-    float e = __fmaf_rn(-y0, s, x);
-    float y = __fmaf_rn(e, r, y0);
+// Fast form: the reciprocal of the scale is computed once per group as an unevaluated sum
+//     rh = RN(1/s),  rl = RN(RN(1 - s*rh) * rh)          (recip_hi_lo: one Newton residual)
+// and each element takes two operations:
+//     y = RN(x*rh + RN(x*rl))
+// which carries ~47 bits of x/s into the single final rounding.  oracle/verify_fastdiv.c proves by
+// exhaustion that the resulting CODE equals the reference's for every (x, max) pair of fp16 values,
+// and for every pair of bf16 values with 2^-60 <= max < 2^120; groups outside that domain (and fp32
+// input) take quantize_exact.  |t| <= 16130 here, so no range check is needed.
+// (The previous form, y0 = RN(x*rh); y = RN(y0 + RN(x - y0*s)*rh), is also exact but costs three.)
+__device__ __forceinline__ void recip_hi_lo(float s, float& rh, float& rl) {
+    rh = __frcp_rn(s);
+    rl = __fmul_rn(__fmaf_rn(-s, rh, 1.0f), rh);
+}
+__device__ __forceinline__ uint32_t quantize_fast(float x, float rh, float rl) {
+    const float y = __fmaf_rn(x, rh, __fmul_rn(x, rl));
     return round_wrap_u8<false>(__fmul_rn(y, 127.0f));
 }
 
 // Same value as an int (only its low byte is meaningful): t + copysign(0.5, t) added
 // round-toward-zero, then truncated.  Used where the byte mask is applied later (packing).
-__device__ __forceinline__ uint32_t quantize_fast_i(float x, float s, float r) {
-    const float y0 = __fmul_rn(x, r);
-    const float e = __fmaf_rn(-y0, s, x);
-    const float y = __fmaf_rn(e, r, y0);
+__device__ __forceinline__ uint32_t quantize_fast_i(float x, float rh, float rl) {
+    const float y = __fmaf_rn(x, rh, __fmul_rn(x, rl));
     const float t = __fmul_rn(y, 127.0f);
     const float half = __uint_as_float((__float_as_uint(t) & 0x80000000u) | 0x3f000000u);
     return (uint32_t)__float2int_rz(__fadd_rz(t, half));
@@ -90,7 +92,7 @@ __device__ __forceinline__ uint32_t quantize_fast_i(float x, float s, float r) {
 template <typename T> __device__ __forceinline__ bool fast_quant_ok(float m);
 template <> __device__ __forceinline__ bool fast_quant_ok<__half>(float m) { return m > 0.0f && m < __int_as_float(0x7f800000); }
 template <> __device__ __forceinline__ bool fast_quant_ok<__nv_bfloat16>(float m) {
-    return m >= 8.673617379884035e-19f /* 2^-60 */ && m < __int_as_float(0x7f800000);
+    return m >= 8.673617379884035e-19f /* 2^-60 */ && m < 1.329227995784916e36f /* 2^120: above, rl loses bits */;
 }
 template <> __device__ __forceinline__ bool fast_quant_ok<float>(float) { return false; }
 

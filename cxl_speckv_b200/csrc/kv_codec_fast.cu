@@ -133,10 +133,6 @@ __device__ __forceinline__ void st_async_u32(uint32_t dst, uint32_t v, uint32_t 
                  : "memory");
 }
 __device__ __forceinline__ uint4 lds128(const void* p) { return *reinterpret_cast<const uint4*>(p); }
-__device__ __forceinline__ void stg128(void* p, uint4 v) {
-    asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
-                 : "memory");
-}
 
 template <typename T> __device__ __forceinline__ void unpack8(const uint4& raw, float (&x)[8]);
 template <> __device__ __forceinline__ void unpack8<__half>(const uint4& raw, float (&x)[8]) {
@@ -278,18 +274,6 @@ __device__ __forceinline__ uint32_t lds16s(uint32_t a) {
 // Store n (<= 8, or <= 9 with w4) consecutive 16-bit units held in w0..w3 (w4) at a 2-byte aligned
 // shared address.  `n_full` is the register capacity (8 or 9 units); n is n_full or n_full - 1.
 __device__ __forceinline__ void store_units8(uint32_t a, uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3, int n) {
-#ifdef SPECKV_EXP_NOCONFLICT   // timing experiment only (wrong output): same stores, bank-conflict-free addresses
-    {
-        const uint32_t lg = (threadIdx.x >> 3) & 3u;
-        const uint32_t b = a & ~3u;
-        sts32(b + 4u * ((0u + lg) & 3u), w0);
-        sts32(b + 4u * ((1u + lg) & 3u), w1);
-        sts32(b + 4u * ((2u + lg) & 3u), w2);
-        if (n == 8) sts32(b + 4u * ((3u + lg) & 3u), w3);
-        else sts16(b + 4u * ((3u + lg) & 3u), w3);
-        return;
-    }
-#endif
     if ((a & 2u) == 0) {
         sts32(a, w0);
         sts32(a + 4, w1);
@@ -327,14 +311,10 @@ __device__ __forceinline__ void store_units9(uint32_t a, uint32_t w0, uint32_t w
 // mod 16, so the whole vectors in between move with one bulk-TMA store (cp.async.bulk.global.shared::cta;
 // measured +7 % compress / +12 % decompress over per-lane 128-bit LDS + STG); the ragged first/last
 // vectors (shared with the neighbouring regions' streams) are written in 2-byte pieces, one per lane.
-#ifndef SPECKV_TMA_FLUSH
-#define SPECKV_TMA_FLUSH 1
-#endif
 __device__ __forceinline__ void flush_region(uint32_t sbase, uint8_t* gout, int lo, int hi, int lane) {
     if (hi <= lo) return;
     const int lo_al = min((lo + 7) & ~7, hi);
     const int hi_al = max(hi & ~7, lo_al);
-#if SPECKV_TMA_FLUSH
     // the aligned middle leaves with ONE bulk-TMA store issued by lane 0 (no per-vector LDS + STG); the
     // staged pairs were written through the generic proxy, so every lane fences them to the async proxy first
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -346,32 +326,12 @@ __device__ __forceinline__ void flush_region(uint32_t sbase, uint8_t* gout, int 
                      : "memory");
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
     }
-#endif
     int i = lo + lane;
     if (i < lo_al) *reinterpret_cast<uint16_t*>(gout + ((size_t)i << 1)) = (uint16_t)lds16s(sbase + ((uint32_t)i << 1));
     i = hi_al + lane;
     if (i < hi) *reinterpret_cast<uint16_t*>(gout + ((size_t)i << 1)) = (uint16_t)lds16s(sbase + ((uint32_t)i << 1));
-#if SPECKV_TMA_FLUSH
     // the tile must stay allocated until the copy engine has read it: lane 0 keeps the CTA alive
     if (lane == 0 && bytes) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-#else
-    const int nv = (hi_al - lo_al) >> 3;
-    const uint32_t sa = sbase + 2u * (uint32_t)lo_al + 16u * (uint32_t)lane;
-    uint8_t* ga = gout + 2 * (size_t)lo_al + 16 * (size_t)lane;
-    // a region is 256 vectors (+- the ragged ends): two rounds of four guarded copies per lane, no loop
-    const int left = nv - lane;   // vectors lane, lane + 32, ... while < nv
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-        uint4 a[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-            if (left > 32 * (4 * h + j)) a[j] = lds128s(sa + 512u * (uint32_t)(4 * h + j));
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-            if (left > 32 * (4 * h + j)) stg128(ga + 512 * (4 * h + j), a[j]);
-    }
-    for (int v = 256; v < left; v += 32) stg128(ga + 16 * (size_t)v, lds128s(sa + 16u * (uint32_t)v));   // decode expansions
-#endif
 }
 
 // ===================================================================================
@@ -440,7 +400,8 @@ compress_fast_kernel(const T* __restrict__ in, uint32_t n_groups, uint8_t* __res
     const float gmax = __uint_as_float(gmax_bits);
     const float s = scale_from_max(gmax);
     const bool fast = fast_quant_ok<T>(gmax);
-    const float r = __frcp_rn(s);
+    float r, rl;
+    recip_hi_lo(s, r, rl);
 
     // ---- 2a. quantise, delta, run-boundary flags; results parked in the lane's own 16-byte slot ----
     // slot = { dsh0, dsh1 : deltas shifted by one element (byte j = delta[pos_j - 1]),
@@ -453,7 +414,7 @@ compress_fast_kernel(const T* __restrict__ in, uint32_t n_groups, uint8_t* __res
             // halo: the 16 elements before the region give the last code, the last delta and the
             // run boundaries among the last 4 positions before the region (all local, no neighbour needed)
             uint32_t qh = 0;
-            if (lane < 16) qh = quantize_fast(widen<T>(halo_x), s, r);
+            if (lane < 16) qh = quantize_fast(widen<T>(halo_x), r, rl);
             const uint32_t qp = __shfl_up_sync(kFull, qh, 1);
             const uint32_t dh = (qh - qp) & 0xffu;
             const uint32_t dp = __shfl_up_sync(kFull, dh, 1);
@@ -473,7 +434,7 @@ compress_fast_kernel(const T* __restrict__ in, uint32_t n_groups, uint8_t* __res
             unpack8<T>(raw, x);
             uint32_t q[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) q[j] = quantize_fast_i(x[j], s, r);
+            for (int j = 0; j < 8; ++j) q[j] = quantize_fast_i(x[j], r, rl);
             // previous element's code: lane - 1, or (lane 0) lane 31 of the previous iteration
             const uint32_t rq = __shfl_sync(kFull, q[7], src_lane);
             const uint32_t pq = lane == 0 ? carry_q : rq;

@@ -200,7 +200,8 @@ compress_rle_generic_kernel(const T* __restrict__ in, uint32_t G, uint32_t n_gro
         const float m = group_absmax<T>(gin, G, vec_ok, fbuf);
         const float s = scale_from_max(m);
         const bool fast = fast_quant_ok<T>(m);
-        const float r = fast ? __frcp_rn(s) : 0.0f;
+        float r = 0.0f, rl = 0.0f;
+        if (fast) recip_hi_lo(s, r, rl);
 
         uint32_t carry_q = 0, carry_d = 0;
         int carry_p0 = 0, carry_lh = 0, carry_nh = 0, stage_base = 0;
@@ -213,7 +214,7 @@ compress_rle_generic_kernel(const T* __restrict__ in, uint32_t G, uint32_t n_gro
             uint32_t q[kEPT];
             if (fast) {
 #pragma unroll
-                for (int j = 0; j < kEPT; ++j) q[j] = quantize_fast(x[j], s, r);
+                for (int j = 0; j < kEPT; ++j) q[j] = quantize_fast(x[j], r, rl);
             } else {
 #pragma unroll
                 for (int j = 0; j < kEPT; ++j) q[j] = quantize_exact(x[j], s);
@@ -440,7 +441,8 @@ compress_int8_generic_kernel(const T* __restrict__ in, uint32_t G, uint32_t n_gr
         const float m = group_absmax<T>(gin, G, vec_ok, fbuf);
         const float s = scale_from_max(m);
         const bool fast = fast_quant_ok<T>(m);
-        const float r = fast ? __frcp_rn(s) : 0.0f;
+        float r = 0.0f, rl = 0.0f;
+        if (fast) recip_hi_lo(s, r, rl);
         for (uint32_t tile = 0; tile < G; tile += kTile) {
             const uint32_t start = tile + tid * kEPT;
             float x[kEPT];
@@ -448,7 +450,7 @@ compress_int8_generic_kernel(const T* __restrict__ in, uint32_t G, uint32_t n_gr
             uint32_t w[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
             for (int j = 0; j < kEPT; ++j) {
-                const uint32_t q = fast ? quantize_fast(x[j], s, r) : quantize_exact(x[j], s);
+                const uint32_t q = fast ? quantize_fast(x[j], r, rl) : quantize_exact(x[j], s);
                 w[j >> 2] |= q << (8 * (j & 3));
             }
             if (start + kEPT <= G) {

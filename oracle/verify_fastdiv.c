@@ -4,13 +4,14 @@
  * TEST INFRASTRUCTURE ONLY.  The kernels (cxl_speckv_b200/csrc/codec_math.cuh)
  * replace the reference's per-element IEEE division
  *     q = int8(round((x / s) * 127.0f)),  s = max|x| / 127.0f     cache_engine.cpp:183,190-191
- * with  r = RN(1/s);  y0 = RN(x*r);  y = RN(y0 + RN(x - y0*s)*r)   (one FMA residual step)
+ * with  rh = RN(1/s);  rl = RN(RN(1 - s*rh)*rh)  (once per group);  y = RN(x*rh + RN(x*rl))
  * and   (float)q / 127.0f                                           cache_engine.cpp:280
  * with  y0 = RN(q*r127);  y = RN(y0 + RN(q - y0*127)*r127).
  * fp16/bf16 inputs make the domain finite: max is one of < 2^15 values and x one
  * of <= max, so the identity of the resulting CODE is checked for every pair
- * (5.0e8 pairs per type).  bf16 groups with max < 2^-60 are reported separately:
- * the kernel sends those to the exact division path.
+ * (1.0e9 signed pairs per type).  bf16 groups with max < 2^-60 or max >= 2^120 are
+ * reported separately: the kernel sends those to the exact division path.  The older
+ * three-operation form y0 = RN(x*rh); y = RN(y0 + RN(x - y0*s)*rh) is checked too.
  *
  *   gcc -O2 -fopenmp -ffp-contract=off -o verify_fastdiv verify_fastdiv.c -lm
  *   ./verify_fastdiv            # exit status 0 == all identities hold
@@ -44,18 +45,21 @@ static long check_type(int bf, int step, long* total, long* lowdomain_bad) {
         float m = bf ? b2f(mh) : h2f(mh);
         float sc = m / 127.0f;
         float r = 1.0f / sc;
-        int fastok = bf ? (m >= 0x1p-60f) : 1;
+        float rl = fmaf(-sc, r, 1.0f) * r;
+        int fastok = bf ? (m >= 0x1p-60f && m < 0x1p120f) : 1;
         for (uint32_t xh = 0; xh <= mh; xh++) {
             float x = bf ? b2f(xh) : h2f(xh);
             for (int sgn = 0; sgn < 2; ++sgn) {
                 float xs = sgn ? -x : x;
                 int qt = cvt(roundf((xs / sc) * 127.0f)) & 0xff;
-                float y0 = xs * r;
-                float e = fmaf(-y0, sc, xs);
-                float y = fmaf(e, r, y0);
+                float y = fmaf(xs, r, xs * rl);                 /* the kernels' form */
                 int qk = round_kernel(y * 127.0f) & 0xff;
+                float y0 = xs * r;                               /* the older three-operation form */
+                float y3 = fmaf(fmaf(-y0, sc, xs), r, y0);
+                int qk3 = round_kernel(y3 * 127.0f) & 0xff;
                 tot++;
                 if (qk != qt) { if (fastok) bad++; else low++; }
+                if (qk3 != qt && fastok) bad++;
             }
         }
     }
@@ -71,7 +75,7 @@ int main(int argc, char** argv) {
     printf("fp16: pairs=%ld mismatches=%ld\n", tot, bad);
     fail += bad;
     bad = check_type(1, step, &tot, &low);
-    printf("bf16: pairs=%ld mismatches(max>=2^-60)=%ld  [max<2^-60 -> exact path; fast form would miss %ld]\n", tot, bad, low);
+    printf("bf16: pairs=%ld mismatches(2^-60<=max<2^120)=%ld  [other max -> exact path; fast form would miss %ld]\n", tot, bad, low);
     fail += bad;
     /* dequantiser identity over all 256 codes */
     float r127 = 1.0f / 127.0f;
