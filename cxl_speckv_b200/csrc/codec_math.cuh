@@ -88,6 +88,36 @@ __device__ __forceinline__ uint32_t quantize_fast_i(float x, float rh, float rl)
     return (uint32_t)__float2int_rz(__fadd_rz(t, half));
 }
 
+// Two packed elements at once (the tuned kernels): the +-0.5 of the rounding step takes its sign from
+// the INPUT (t has the sign of x whenever it is not zero, and +-0.5 both truncate to 0 when it is), so
+// one LOP3 builds both halves as a packed fp16/bf16 pair and the mixed-precision add of sm_100
+// (add.rz.f32.f16 / .bf16, SASS FHADD.RZ) consumes a half of it directly: 6.5 operations per element.
+template <typename T> struct HalfConst;
+template <> struct HalfConst<__half> { static constexpr uint32_t k = 0x38003800u; };          // (0.5h, 0.5h)
+template <> struct HalfConst<__nv_bfloat16> { static constexpr uint32_t k = 0x3f003f00u; };   // (0.5bf, 0.5bf)
+template <typename T> __device__ __forceinline__ float add_rz_mixed(uint16_t h, float t);
+template <> __device__ __forceinline__ float add_rz_mixed<__half>(uint16_t h, float t) {
+    float a;
+    asm("add.rz.f32.f16 %0, %1, %2;" : "=f"(a) : "h"(h), "f"(t));
+    return a;
+}
+template <> __device__ __forceinline__ float add_rz_mixed<__nv_bfloat16>(uint16_t h, float t) {
+    float a;
+    asm("add.rz.f32.bf16 %0, %1, %2;" : "=f"(a) : "h"(h), "f"(t));
+    return a;
+}
+// w = two packed elements, x0 / x1 = the same elements widened; half_k = HalfConst<T>::k held in a register
+template <typename T>
+__device__ __forceinline__ void quantize_fast_pair_i(uint32_t w, float x0, float x1, float rh, float rl, uint32_t half_k,
+                                                     uint32_t& q0, uint32_t& q1) {
+    uint32_t hs;
+    asm("lop3.b32 %0, %1, 0x80008000, %2, 0xEA;" : "=r"(hs) : "r"(w), "r"(half_k));   // (w & signs) | halves
+    const float t0 = __fmul_rn(__fmaf_rn(x0, rh, __fmul_rn(x0, rl)), 127.0f);
+    const float t1 = __fmul_rn(__fmaf_rn(x1, rh, __fmul_rn(x1, rl)), 127.0f);
+    q0 = (uint32_t)__float2int_rz(add_rz_mixed<T>((uint16_t)(hs & 0xffffu), t0));
+    q1 = (uint32_t)__float2int_rz(add_rz_mixed<T>((uint16_t)(hs >> 16), t1));
+}
+
 // Is the fast form valid for a group whose max-abs is m (element type T)?
 template <typename T> __device__ __forceinline__ bool fast_quant_ok(float m);
 template <> __device__ __forceinline__ bool fast_quant_ok<__half>(float m) { return m > 0.0f && m < __int_as_float(0x7f800000); }

@@ -426,6 +426,8 @@ compress_fast_kernel(const T* __restrict__ in, uint32_t n_groups, uint8_t* __res
             if (chg == 0) cplx = true;   // a run of 9+ equal deltas reaches the region edge
         }
         const int src_lane = (lane + 31) & 31;
+        uint32_t half_k = HalfConst<T>::k;
+        asm volatile("" : "+r"(half_k));   // keep it in a register: LOP3 takes only one immediate
 #pragma unroll
         for (int k = 0; k < kIters; ++k) {
             uint8_t* slot = reg + k * 512 + lane * 16;
@@ -433,8 +435,10 @@ compress_fast_kernel(const T* __restrict__ in, uint32_t n_groups, uint8_t* __res
             float x[8];
             unpack8<T>(raw, x);
             uint32_t q[8];
+            const uint32_t rw[4] = {raw.x, raw.y, raw.z, raw.w};
 #pragma unroll
-            for (int j = 0; j < 8; ++j) q[j] = quantize_fast_i(x[j], r, rl);
+            for (int j = 0; j < 4; ++j)
+                quantize_fast_pair_i<T>(rw[j], x[2 * j], x[2 * j + 1], r, rl, half_k, q[2 * j], q[2 * j + 1]);
             // previous element's code: lane - 1, or (lane 0) lane 31 of the previous iteration
             const uint32_t rq = __shfl_sync(kFull, q[7], src_lane);
             const uint32_t pq = lane == 0 ? carry_q : rq;

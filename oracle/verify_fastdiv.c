@@ -27,6 +27,13 @@ static float h2f(uint16_t h) { _Float16 x; memcpy(&x, &h, 2); return (float)x; }
 static float b2f(uint16_t h) { uint32_t u = (uint32_t)h << 16; float f; memcpy(&f, &u, 4); return f; }
 static inline int32_t cvt(float r) { if (!(fabsf(r) < 2147483648.0f)) return INT32_MIN; return (int32_t)r; }
 
+/* the tuned kernels' rounding takes the sign of the +-0.5 from the input x (packed sign trick):
+ * trunc(RZ(t + copysign(0.5, x))) -- t + 0.5 is exact in double, so RZ-to-float then trunc == trunc */
+static inline int round_kernel_sx(float t, float x) {
+    if (t != t) return 0;
+    double a = (double)t + copysign(0.5, (double)x);
+    return (int)a;                                  /* |a| < 2^31 in the fast domain */
+}
 /* the kernel's rounding: sign(t) * trunc(RZ(|t| + 0.5)) -- emulate RZ add in double (exact) */
 static inline int round_kernel(float t) {
     if (t != t) return 0;
@@ -54,6 +61,7 @@ static long check_type(int bf, int step, long* total, long* lowdomain_bad) {
                 int qt = cvt(roundf((xs / sc) * 127.0f)) & 0xff;
                 float y = fmaf(xs, r, xs * rl);                 /* the kernels' form */
                 int qk = round_kernel(y * 127.0f) & 0xff;
+                if ((round_kernel_sx(y * 127.0f, xs) & 0xff) != qk && fastok) bad++;   /* packed-sign variant */
                 float y0 = xs * r;                               /* the older three-operation form */
                 float y3 = fmaf(fmaf(-y0, sc, xs), r, y0);
                 int qk3 = round_kernel(y3 * 127.0f) & 0xff;
