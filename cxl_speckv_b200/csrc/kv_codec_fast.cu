@@ -414,6 +414,9 @@ compress_fast_kernel(const T* __restrict__ in, uint32_t n_groups, uint8_t* __res
     const float gmax = __uint_as_float(gmax_bits);
     const float s = scale_from_max(gmax);
     const bool fast = fast_quant_ok<T>(gmax);
+    // a group whose max-abs is 0 (zeros, possibly NaNs: cache_engine.cpp:176-179 skips them and the cast maps
+    // them to code 0) has the closed-form payload [0][255] x floor(G/255) + [0][G%255]: no second read
+    const bool zero_group = active && gmax_bits == 0u;
     float r, rl;
     recip_hi_lo(s, r, rl);
 
@@ -421,7 +424,7 @@ compress_fast_kernel(const T* __restrict__ in, uint32_t n_groups, uint8_t* __res
     // slot = { dsh0, dsh1 : deltas shifted by one element (byte j = delta[pos_j - 1]),
     //          nz0,  nz1  : bit 7 of byte j set iff position j starts a run (delta[j] != delta[j-1]) }
     uint32_t heads = 0;
-    bool cplx = !fast;
+    bool cplx = !fast && !zero_group;
     uint32_t carry_q = 0, carry_d1 = 0, halo_nz0 = 0u, halo_nz1 = 0x80000000u;
     if (active && fast) {
         if (ridx > 0) {
@@ -492,6 +495,18 @@ compress_fast_kernel(const T* __restrict__ in, uint32_t n_groups, uint8_t* __res
     if (!active) return;
     if (ridx == 0 && lane == 0) needs_generic[g] = any_cplx ? 1u : 0u;
     if (any_cplx) return;
+    if (zero_group) {
+        if (ridx == 0) {
+            constexpr uint32_t full = G / 255u, rem = G % 255u, npairs = full + (rem ? 1u : 0u);
+            uint16_t* go = reinterpret_cast<uint16_t*>(payload + (size_t)g * slot_bytes);
+            for (uint32_t i = lane; i < npairs; i += 32u) go[i] = i < full ? (uint16_t)0xff00u : (uint16_t)(rem << 8);
+            if (lane == 0) {
+                scales[g] = s;   // 1.0f
+                comp_bytes[g] = 2u * npairs;
+            }
+        }
+        return;
+    }
 
     // ---- 2b. emit: a head at position p closes the previous run -> pair (delta[p-1], p - previous head).
     //          Pairs are staged IN PLACE (behind the slots still to be read) at the alignment they
@@ -650,6 +665,7 @@ decompress_fast_kernel(const uint8_t* __restrict__ payload, size_t slot_bytes, c
 
     // ---- A. region totals: elements produced (sum of counts) and code advance (sum of value*count) ----
     uint32_t csum = 0, ssum = 0, nnz = 0;
+    bool fill = false;   // region decoded as a constant fill (all pair values zero) instead of through the staging area
     if (np > 0) {
         mbar_wait(mb, 0);
 #pragma unroll
@@ -684,8 +700,19 @@ decompress_fast_kernel(const uint8_t* __restrict__ payload, size_t slot_bytes, c
         csum = __reduce_add_sync(kFull, csum);
         ssum = __reduce_add_sync(kFull, ssum) & 0xffu;
         nnz = __reduce_add_sync(kFull, nnz);
-        // in-place staging needs the output stream to stay within kPadBytes of the read position
-        if (csum - nnz > (uint32_t)(kPadBytes / 2 - 8)) cplx = true;
+        // in-place staging needs the output stream to stay within kPadBytes of the read position.  A region that
+        // expands further is still decoded here when all its pair values are zero (zero blocks, long constant
+        // stretches): every element then repeats the code the region starts with, and nothing is staged.
+        if (csum - nnz > (uint32_t)(kPadBytes / 2 - 8)) {
+            uint32_t vor = 0;
+#pragma unroll
+            for (int k = 0; k < kIters; ++k) {
+                const uint4 w = lds128(reg + k * 512 + lane * 16);
+                vor |= (w.x | w.y | w.z | w.w) & 0x00ff00ffu;
+            }
+            fill = __reduce_or_sync(kFull, vor) == 0u;
+            if (!fill) cplx = true;
+        }
     }
     if (C > 1) cluster_wait();   // all CTAs of the cluster are running: their shared memory may be written
     group_publish<R>(sm, sm.xa, 0, warp, lane, ridx, min(csum, G + 1u));   // saturated: sums stay < 2^32, "> G" still shows
@@ -705,6 +732,19 @@ decompress_fast_kernel(const uint8_t* __restrict__ payload, size_t slot_bytes, c
     // ---- C. expand in place: element e of run j carries code q_before + ... + v_j * (e - start_j + 1) ----
     uint8_t* gout = reinterpret_cast<uint8_t*>(out + (size_t)(elem_index ? elem_index[g] : g) * G);   // paged scatter
     const uint32_t e0 = e_before;
+    if (fill) {
+        // constant fill: elements [e0, e0 + csum) all carry code q_before (zero blocks, long runs of one value)
+        const uint32_t e1 = e0 + csum;
+        const uint32_t hb = out_bits<T>(dequantize(q_before & 0xffu, s));
+        const uint32_t w2 = hb | (hb << 16);
+        const uint32_t a0 = min((e0 + 7u) & ~7u, e1), a1 = max(e1 & ~7u, a0);
+        uint16_t* go16 = reinterpret_cast<uint16_t*>(gout);
+        if (e0 + lane < a0) go16[e0 + lane] = (uint16_t)hb;
+        if (a1 + lane < e1) go16[a1 + lane] = (uint16_t)hb;
+        const uint4 v4 = make_uint4(w2, w2, w2, w2);
+        for (uint32_t e = a0 + 8u * lane; e < a1; e += 256u) *reinterpret_cast<uint4*>(go16 + e) = v4;
+        return;
+    }
     uint32_t ecur = e0;                       // next element index to produce
     uint32_t qcur = q_before & 0xffu;         // code of element ecur - 1
     const uint32_t sbase = reg_s - (uint32_t)kPadBytes - 2u * (e0 & ~7u);   // element i is staged at sbase + 2*i

@@ -499,3 +499,76 @@ def test_paged_gather_scatter_rejects_bad_arguments():
         codec.decompress_scatter(c, torch.zeros((4, 4096), dtype=torch.float16, device=DEV), table)
     with pytest.raises(ValueError):
         codec.decompress_scatter(c, cache, table[:2])
+
+
+@pytest.mark.parametrize("G", [2048, 8192, 32768, 131072])
+def test_zero_groups_closed_form(G):
+    """max-abs 0 (zeros, -0.0, NaNs: the reference's max skips NaN and the cast sends it to code 0) is
+    emitted by the tuned kernel itself; its decode fills without staging.  Mixed with ordinary groups."""
+    rng = np.random.default_rng(G)
+    n_groups = 12
+    x = rng.standard_normal(n_groups * G).astype(np.float16).reshape(n_groups, G)
+    x[1] = 0.0
+    x[4] = -0.0
+    x[7] = 0.0
+    x[7, rng.integers(0, G, 9)] = np.nan
+    x[10] = 0.0
+    x = x.reshape(-1)
+    xd = torch.from_numpy(x).to(DEV)
+    c = codec.compress(xd, G)
+    payload, scales, comp = Port.compress_batch(x, G, threads=8)
+    assert np.array_equal(f32_bits(c.scales.cpu().numpy()), f32_bits(scales))
+    assert np.array_equal(c.comp_bytes.cpu().numpy().view(np.uint32), comp)
+    gp = c.payload.cpu().numpy()
+    for g in range(n_groups):
+        assert np.array_equal(gp[g, :comp[g]], payload[g, :comp[g]]), g
+    oel = torch.zeros(n_groups, dtype=torch.int32, device=DEV)
+    y = torch.full((n_groups, G), 3.0, dtype=torch.float16, device=DEV)
+    codec.decompress(c, out=y, out_elems=oel)
+    want, want_n = Port.decompress_batch(payload, scales, comp, G, F16, threads=8)
+    assert np.array_equal(oel.cpu().numpy().view(np.uint32), want_n)
+    assert np.array_equal(out_bits(y), want.view(np.uint16))
+
+
+@pytest.mark.parametrize("tdt", [F16, BF16])
+def test_decode_zero_valued_regions(tdt):
+    """Hand-built payloads whose 2048-pair regions hold only zero values (long constant stretches starting
+    from a non-zero code, ragged element offsets, negative scales) between ordinary regions."""
+    rng = np.random.default_rng(5 + tdt)
+    G, n_groups = 131072, 6
+    sb = codec.slot_bytes(G)
+    payload = np.zeros((n_groups, sb), np.uint8)
+    comp = np.zeros(n_groups, np.uint32)
+    scales = rng.uniform(0.01, 2.0, n_groups).astype(np.float32)
+    scales[3] = -0.75
+    for g in range(n_groups):
+        parts = []
+        total = 0
+        for r in range(20):
+            if r % 3 == g % 3:        # a zero-valued region: counts 1..33 (region total 2048..~35000 elements)
+                cnt = rng.integers(1, 34 if g % 2 else 3, 2048).astype(np.uint8)
+                val = np.zeros(2048, np.uint8)
+            else:                     # an ordinary region: counts of 1, one count of 2 here and there
+                cnt = np.ones(2048, np.uint8)
+                cnt[rng.integers(0, 2048, 5)] = 2
+                val = rng.integers(0, 256, 2048, dtype=np.uint8)
+            if total + int(cnt.sum()) > G:
+                break
+            total += int(cnt.sum())
+            parts.append(np.stack([val, cnt], axis=1).reshape(-1))
+        p = np.concatenate(parts)
+        payload[g, :p.size] = p
+        comp[g] = p.size
+    c = codec.CompressedKV(torch.from_numpy(payload).to(DEV), torch.from_numpy(scales).to(DEV),
+                           torch.from_numpy(comp.view(np.int32)).to(DEV), G, TORCH_DT[tdt], COMP_INT8_DELTA_RLE)
+    out = torch.full((n_groups, G), 0x1234, dtype=torch.int16, device=DEV).view(TORCH_DT[tdt])
+    oel = torch.zeros(n_groups, dtype=torch.int32, device=DEV)
+    codec.decompress(c, out=out, out_elems=oel)
+    want, want_n = Port.decompress_batch(payload, scales, comp, G, tdt, threads=8)
+    got = out_bits(out)
+    want = want.view(np.uint16).reshape(n_groups, G)
+    assert np.array_equal(oel.cpu().numpy().view(np.uint32), want_n)
+    for g in range(n_groups):
+        n = int(want_n[g])
+        assert np.array_equal(got[g, :n], want[g, :n]), g
+        assert (got[g, n:] == 0x1234).all(), g
