@@ -85,6 +85,95 @@ struct Extent {
     uint64_t off, len;
 };
 
+// block id -> BlockRec: open addressing (key and record in one 32-byte entry: one cache line per probe),
+// linear probing, backward-shift deletion, software prefetch for batches.  One record per 4 KiB page at the
+// paged geometry (a million per offload call): with std::unordered_map the host bookkeeping (a node
+// allocation and several cache misses per page) took longer than the PCIe copy it overlaps.
+class BlockMap {
+public:
+    BlockRec* find(uint64_t key) {
+        if (cap_ == 0) return nullptr;
+        for (size_t i = slot_of(key);; i = (i + 1) & (cap_ - 1)) {
+            if (tab_[i].val.dtype == kEmpty) return nullptr;
+            if (tab_[i].key == key) return &tab_[i].val;
+        }
+    }
+    // insert or replace; returns true and the previous record when the key was present
+    bool exchange(uint64_t key, const BlockRec& r, BlockRec* old) {
+        if ((size_ + 1) * 10 > cap_ * 7) grow(cap_ ? cap_ * 2 : 1024);
+        for (size_t i = slot_of(key);; i = (i + 1) & (cap_ - 1)) {
+            if (tab_[i].val.dtype == kEmpty) {
+                tab_[i].key = key;
+                tab_[i].val = r;
+                ++size_;
+                return false;
+            }
+            if (tab_[i].key == key) {
+                if (old) *old = tab_[i].val;
+                tab_[i].val = r;
+                return true;
+            }
+        }
+    }
+    void put(uint64_t key, const BlockRec& r) { exchange(key, r, nullptr); }
+    bool erase(uint64_t key) {
+        if (cap_ == 0) return false;
+        size_t i = slot_of(key);
+        for (;; i = (i + 1) & (cap_ - 1)) {
+            if (tab_[i].val.dtype == kEmpty) return false;
+            if (tab_[i].key == key) break;
+        }
+        // backward shift: pull later entries of the probe run into the hole
+        for (size_t j = (i + 1) & (cap_ - 1);; j = (j + 1) & (cap_ - 1)) {
+            if (tab_[j].val.dtype == kEmpty) break;
+            const size_t home = slot_of(tab_[j].key);
+            if (((j - home) & (cap_ - 1)) >= ((j - i) & (cap_ - 1))) {
+                tab_[i] = tab_[j];
+                i = j;
+            }
+        }
+        tab_[i].val.dtype = kEmpty;
+        --size_;
+        return true;
+    }
+    void reserve(size_t n) {
+        size_t want = 1024;
+        while (want * 7 < n * 10) want *= 2;
+        if (want > cap_) grow(want);
+    }
+    void prefetch(uint64_t key) const {
+        if (cap_) __builtin_prefetch(&tab_[slot_of(key)]);
+    }
+    size_t size() const { return size_; }
+
+private:
+    static constexpr int kEmpty = -1;
+    struct Entry {
+        uint64_t key;
+        BlockRec val;
+    };
+    size_t slot_of(uint64_t k) const {
+        k ^= k >> 33;
+        k *= 0xff51afd7ed558ccdull;
+        k ^= k >> 33;
+        return (size_t)k & (cap_ - 1);
+    }
+    void grow(size_t ncap) {
+        std::vector<Entry> old;
+        old.swap(tab_);
+        Entry e{};
+        e.val.dtype = kEmpty;
+        tab_.assign(ncap, e);
+        cap_ = ncap;
+        size_ = 0;
+        for (const Entry& o : old)
+            if (o.val.dtype != kEmpty) exchange(o.key, o.val, nullptr);
+    }
+    std::vector<Entry> tab_;
+    size_t cap_ = 0, size_ = 0;
+};
+constexpr size_t kMapPrefetch = 16;   // look-ups in flight when a call walks a list of block ids
+
 }  // namespace
 
 struct Tier {
@@ -93,7 +182,7 @@ struct Tier {
     uint8_t* pool = nullptr;      // pinned host memory
     size_t pool_bytes = 0, bump = 0;
     std::vector<Extent> free_list;                       // sorted by offset, coalesced
-    std::unordered_map<uint64_t, BlockRec> blocks;
+    BlockMap blocks;
     // device staging, two buffers for chunk double-buffering
     static constexpr int kBuf = 2;
     cudaStream_t copy_st[kBuf] = {};
@@ -253,6 +342,7 @@ speckv_status_t speckv_ext_tier_offload(speckv_tier_t* tier, const void* d_in, s
     const auto t0 = std::chrono::steady_clock::now();
     uint64_t stored = 0;
     speckv_status_t rc = SPECKV_OK;
+    t.blocks.reserve(t.blocks.size() + n_groups);
 
     // finish chunk `c` that was staged in buffer b: wait for its metadata, place it in the pool,
     // start the payload copy and record the blocks
@@ -260,28 +350,28 @@ speckv_status_t speckv_ext_tier_offload(speckv_tier_t* tier, const void* d_in, s
         cudaError_t e2 = cudaStreamSynchronize(t.copy_st[b]);   // metadata (offsets, sizes, scales, total) on the host
         if (e2 != cudaSuccess) return status_of(e2);
         const uint64_t total = *t.h_total[b];
-        // re-offloading a block id replaces its previous copy
-        for (size_t i = 0; i < ng; ++i) {
-            auto it = t.blocks.find(h_block_ids[g0 + i]);
-            if (it != t.blocks.end()) {
-                t.free_pool(it->second.pool_off, ((uint64_t)it->second.comp_bytes + 15u) & ~15ull);
-                t.stats.used_bytes -= ((uint64_t)it->second.comp_bytes + 15u) & ~15ull;
-                t.blocks.erase(it);
-            }
-        }
         const size_t off = t.alloc_pool(total);
         if (off == SIZE_MAX) return SPECKV_ERR_NOMEM;
         e2 = cudaMemcpyAsync(t.pool + off, t.d_packed[b], total, cudaMemcpyDeviceToHost, t.copy_st[b]);
         if (e2 != cudaSuccess) return status_of(e2);
         cudaEventRecord(t.ev_copy[b], t.copy_st[b]);
+        // bookkeeping while the copy runs; re-offloading a block id replaces its previous copy (whose pool
+        // space becomes reusable from the next chunk on)
         for (size_t i = 0; i < ng; ++i) {
-            BlockRec r;
+            if (i + kMapPrefetch < ng) t.blocks.prefetch(h_block_ids[g0 + i + kMapPrefetch]);
+            BlockRec r, old;
             r.pool_off = off + t.h_offsets[b][i];
             r.comp_bytes = t.h_comp[b][i];
             r.scale = t.h_scales[b][i];
             r.group_elems = (uint32_t)group_elems;
             r.dtype = dtype;
-            t.blocks[h_block_ids[g0 + i]] = r;
+            if (t.blocks.exchange(h_block_ids[g0 + i], r, &old)) {
+                t.stats.used_bytes -= ((uint64_t)old.comp_bytes + 15u) & ~15ull;
+                // an id listed twice in this chunk: its first copy is part of the transfer in flight, so its
+                // bytes stay allocated until the tier is dropped (other streams must not write there yet)
+                if (old.pool_off < off || old.pool_off >= off + total)
+                    t.free_pool(old.pool_off, ((uint64_t)old.comp_bytes + 15u) & ~15ull);
+            }
         }
         stored += total;
         t.stats.used_bytes += total;
@@ -367,9 +457,10 @@ speckv_status_t speckv_ext_tier_restore(speckv_tier_t* tier, const uint64_t* h_b
         uint64_t dst = 0;
         uint64_t run_src = 0, run_dst = 0, run_len = 0;
         for (size_t i = 0; i < ng; ++i) {
-            auto it = t.blocks.find(h_block_ids[g0 + i]);
-            if (it == t.blocks.end() || it->second.group_elems != group_elems) return SPECKV_ERR_GENERAL;   // unknown, raw, or other geometry
-            const BlockRec& r = it->second;
+            if (i + kMapPrefetch < ng) t.blocks.prefetch(h_block_ids[g0 + i + kMapPrefetch]);
+            const BlockRec* rec = t.blocks.find(h_block_ids[g0 + i]);
+            if (!rec || rec->group_elems != group_elems) return SPECKV_ERR_GENERAL;   // unknown, raw, or other geometry
+            const BlockRec& r = *rec;
             const uint64_t len = ((uint64_t)r.comp_bytes + 15u) & ~15ull;
             t.h_offsets[b][i] = dst;
             t.h_comp[b][i] = r.comp_bytes;
@@ -422,12 +513,12 @@ speckv_status_t speckv_ext_tier_drop(speckv_tier_t* tier, const uint64_t* h_bloc
     Tier& t = tier->t;
     std::lock_guard<std::mutex> lk(t.mu);
     for (size_t i = 0; i < n; ++i) {
-        auto it = t.blocks.find(h_block_ids[i]);
-        if (it == t.blocks.end()) continue;   // like speckv_free: dropping an unknown block is not an error
-        const uint64_t len = ((uint64_t)it->second.comp_bytes + 15u) & ~15ull;
-        t.free_pool(it->second.pool_off, len);
+        const BlockRec* rec = t.blocks.find(h_block_ids[i]);
+        if (!rec) continue;   // like speckv_free: dropping an unknown block is not an error
+        const uint64_t len = ((uint64_t)rec->comp_bytes + 15u) & ~15ull;
+        t.free_pool(rec->pool_off, len);
         t.stats.used_bytes -= len;
-        t.blocks.erase(it);
+        t.blocks.erase(h_block_ids[i]);
     }
     t.stats.blocks = t.blocks.size();
     return SPECKV_OK;
@@ -461,12 +552,12 @@ speckv_status_t speckv_ext_submit_dma_batch(speckv_tier_t* tier, const speckv_dm
             rc = SPECKV_OK;
             for (uint32_t p = 0; p < pages && rc == SPECKV_OK; ++p) {
                 uint8_t* dev = static_cast<uint8_t*>(gpu) + (size_t)p * kTierPage;
-                auto it = t.blocks.find(ids[p]);
+                const BlockRec* it = t.blocks.find(ids[p]);
                 if (d.flags & SPECKV_DMA_WRITE) {
-                    if (it != t.blocks.end()) {
-                        t.free_pool(it->second.pool_off, ((uint64_t)it->second.comp_bytes + 15u) & ~15ull);
-                        t.stats.used_bytes -= ((uint64_t)it->second.comp_bytes + 15u) & ~15ull;
-                        t.blocks.erase(it);
+                    if (it) {
+                        t.free_pool(it->pool_off, ((uint64_t)it->comp_bytes + 15u) & ~15ull);
+                        t.stats.used_bytes -= ((uint64_t)it->comp_bytes + 15u) & ~15ull;
+                        t.blocks.erase(ids[p]);
                     }
                     const size_t off = t.alloc_pool(kTierPage);
                     if (off == SIZE_MAX) { rc = SPECKV_ERR_NOMEM; break; }
@@ -477,11 +568,11 @@ speckv_status_t speckv_ext_submit_dma_batch(speckv_tier_t* tier, const speckv_dm
                     r.scale = 1.0f;
                     r.group_elems = 0;
                     r.dtype = SPECKV_DTYPE_F16;
-                    t.blocks[ids[p]] = r;
+                    t.blocks.put(ids[p], r);
                     t.stats.used_bytes += kTierPage;
                 } else {
-                    if (it == t.blocks.end() || it->second.group_elems != 0) { rc = SPECKV_ERR_GENERAL; break; }
-                    rc = status_of(cudaMemcpyAsync(dev, t.pool + it->second.pool_off, kTierPage, cudaMemcpyHostToDevice, st));
+                    if (!it || it->group_elems != 0) { rc = SPECKV_ERR_GENERAL; break; }
+                    rc = status_of(cudaMemcpyAsync(dev, t.pool + it->pool_off, kTierPage, cudaMemcpyHostToDevice, st));
                 }
             }
             if (rc == SPECKV_OK) rc = status_of(cudaStreamSynchronize(st));
