@@ -102,6 +102,10 @@ def lib() -> C.CDLL:
     L.speckv_ext_tier_destroy.argtypes = [vp]; L.speckv_ext_tier_destroy.restype = None
     L.speckv_ext_tier_offload.argtypes = [vp, vp, C.c_int, sz, sz, vp, vp]; L.speckv_ext_tier_offload.restype = C.c_int
     L.speckv_ext_tier_restore.argtypes = [vp, vp, sz, sz, C.c_int, vp, vp]; L.speckv_ext_tier_restore.restype = C.c_int
+    L.speckv_ext_tier_offload_paged.argtypes = [vp, vp, vp, C.c_int, sz, sz, vp, vp]
+    L.speckv_ext_tier_offload_paged.restype = C.c_int
+    L.speckv_ext_tier_restore_paged.argtypes = [vp, vp, sz, sz, C.c_int, vp, vp, vp]
+    L.speckv_ext_tier_restore_paged.restype = C.c_int
     L.speckv_ext_tier_drop.argtypes = [vp, vp, sz]; L.speckv_ext_tier_drop.restype = C.c_int
     L.speckv_ext_tier_get_stats.argtypes = [vp, C.POINTER(TierStats)]; L.speckv_ext_tier_get_stats.restype = None
     L.speckv_ext_atu_create.argtypes = [C.c_uint32, C.POINTER(vp)]; L.speckv_ext_atu_create.restype = C.c_int

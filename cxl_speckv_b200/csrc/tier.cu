@@ -324,8 +324,9 @@ void speckv_ext_tier_destroy(speckv_tier_t* tier) {
     delete tier;
 }
 
-speckv_status_t speckv_ext_tier_offload(speckv_tier_t* tier, const void* d_in, speckv_dtype_t dtype, size_t group_elems,
-                                        size_t n_groups, const uint64_t* h_block_ids, void* cuda_stream) {
+static speckv_status_t tier_offload_impl(speckv_tier_t* tier, const void* d_in, const uint32_t* d_block_table,
+                                         speckv_dtype_t dtype, size_t group_elems, size_t n_groups,
+                                         const uint64_t* h_block_ids, void* cuda_stream) {
     if (device_count() <= 0) return SPECKV_ERR_DRIVER;
     if (!tier || !h_block_ids || (!d_in && n_groups) || dtype < 0 || dtype > 2 || group_elems == 0 ||
         group_elems >= (1ull << 31))
@@ -386,7 +387,9 @@ speckv_status_t speckv_ext_tier_offload(speckv_tier_t* tier, const void* d_in, s
         // buffer b is free once the payload copy of chunk - 2 has completed
         cudaStreamWaitEvent(st, t.ev_copy[b], 0);
         CodecArgs a;
-        a.in = (const char*)d_in + g0 * group_elems * esz;
+        // paged form: the chunk's groups are the cache blocks its slice of the block table names
+        a.in = d_block_table ? d_in : (const void*)((const char*)d_in + g0 * group_elems * esz);
+        a.elem_index = d_block_table ? d_block_table + g0 : nullptr;
         a.payload = t.d_slots[b];
         a.scales = t.d_scales[b];
         a.comp_bytes = t.d_comp[b];
@@ -429,8 +432,21 @@ speckv_status_t speckv_ext_tier_offload(speckv_tier_t* tier, const void* d_in, s
     return rc;
 }
 
-speckv_status_t speckv_ext_tier_restore(speckv_tier_t* tier, const uint64_t* h_block_ids, size_t n_groups,
-                                        size_t group_elems, speckv_dtype_t dtype, void* d_out, void* cuda_stream) {
+speckv_status_t speckv_ext_tier_offload(speckv_tier_t* tier, const void* d_in, speckv_dtype_t dtype, size_t group_elems,
+                                        size_t n_groups, const uint64_t* h_block_ids, void* cuda_stream) {
+    return tier_offload_impl(tier, d_in, nullptr, dtype, group_elems, n_groups, h_block_ids, cuda_stream);
+}
+
+speckv_status_t speckv_ext_tier_offload_paged(speckv_tier_t* tier, const void* d_cache, const uint32_t* d_block_table,
+                                              speckv_dtype_t dtype, size_t group_elems, size_t n_blocks,
+                                              const uint64_t* h_block_ids, void* cuda_stream) {
+    if (!d_block_table && n_blocks) return SPECKV_ERR_INVAL;
+    return tier_offload_impl(tier, d_cache, d_block_table, dtype, group_elems, n_blocks, h_block_ids, cuda_stream);
+}
+
+static speckv_status_t tier_restore_impl(speckv_tier_t* tier, const uint64_t* h_block_ids, size_t n_groups,
+                                         size_t group_elems, speckv_dtype_t dtype, void* d_out,
+                                         const uint32_t* d_block_table, void* cuda_stream) {
     if (device_count() <= 0) return SPECKV_ERR_DRIVER;
     if (!tier || !h_block_ids || (!d_out && n_groups) || dtype < 0 || dtype > 2 || group_elems == 0) return SPECKV_ERR_INVAL;
     if (n_groups == 0) return SPECKV_OK;
@@ -483,7 +499,8 @@ speckv_status_t speckv_ext_tier_restore(speckv_tier_t* tier, const uint64_t* h_b
         cudaEventRecord(t.ev_copy[b], t.copy_st[b]);
         cudaStreamWaitEvent(st, t.ev_copy[b], 0);
         CodecArgs a;
-        a.out = (char*)d_out + g0 * group_elems * esz;
+        a.out = d_block_table ? d_out : (void*)((char*)d_out + g0 * group_elems * esz);
+        a.elem_index = d_block_table ? d_block_table + g0 : nullptr;
         a.payload = t.d_packed[b];
         a.scales = t.d_scales[b];
         a.comp_bytes = t.d_comp[b];
@@ -506,6 +523,18 @@ speckv_status_t speckv_ext_tier_restore(speckv_tier_t* tier, const uint64_t* h_b
     t.stats.last_restore_ms = ms;
     t.stats.last_restore_stored_bytes = moved;
     return SPECKV_OK;
+}
+
+speckv_status_t speckv_ext_tier_restore(speckv_tier_t* tier, const uint64_t* h_block_ids, size_t n_groups,
+                                        size_t group_elems, speckv_dtype_t dtype, void* d_out, void* cuda_stream) {
+    return tier_restore_impl(tier, h_block_ids, n_groups, group_elems, dtype, d_out, nullptr, cuda_stream);
+}
+
+speckv_status_t speckv_ext_tier_restore_paged(speckv_tier_t* tier, const uint64_t* h_block_ids, size_t n_blocks,
+                                              size_t group_elems, speckv_dtype_t dtype, void* d_cache,
+                                              const uint32_t* d_block_table, void* cuda_stream) {
+    if (!d_block_table && n_blocks) return SPECKV_ERR_INVAL;
+    return tier_restore_impl(tier, h_block_ids, n_blocks, group_elems, dtype, d_cache, d_block_table, cuda_stream);
 }
 
 speckv_status_t speckv_ext_tier_drop(speckv_tier_t* tier, const uint64_t* h_block_ids, size_t n) {

@@ -48,6 +48,30 @@ class HostTier:
                                                 out.data_ptr(), _stream()), "speckv_ext_tier_restore")
         return out
 
+    def offload_blocks(self, cache: torch.Tensor, block_table: torch.Tensor, block_ids: np.ndarray) -> None:
+        """Paged form: compress the blocks of a paged KV cache ([num_blocks, ...], one block = one codec
+        group) named by `block_table` (CUDA int32) into the pool under `block_ids`, reading them in place."""
+        assert cache.is_cuda and cache.is_contiguous()
+        ids = np.ascontiguousarray(block_ids, dtype=np.uint64)
+        table = block_table.to(device=cache.device, dtype=torch.int32).contiguous()
+        assert ids.size == table.numel()
+        with torch.cuda.device(cache.device):
+            check(lib().speckv_ext_tier_offload_paged(self._h, cache.data_ptr(), table.data_ptr(), _DTYPES[cache.dtype],
+                                                      cache[0].numel(), ids.size, ids.ctypes.data, _stream()),
+                  "speckv_ext_tier_offload_paged")
+
+    def restore_blocks(self, block_ids: np.ndarray, cache: torch.Tensor, block_table: torch.Tensor) -> torch.Tensor:
+        """Paged form: decompress the stored blocks `block_ids` straight into cache blocks `block_table`."""
+        assert cache.is_cuda and cache.is_contiguous()
+        ids = np.ascontiguousarray(block_ids, dtype=np.uint64)
+        table = block_table.to(device=cache.device, dtype=torch.int32).contiguous()
+        assert ids.size == table.numel()
+        with torch.cuda.device(cache.device):
+            check(lib().speckv_ext_tier_restore_paged(self._h, ids.ctypes.data, ids.size, cache[0].numel(),
+                                                      _DTYPES[cache.dtype], cache.data_ptr(), table.data_ptr(), _stream()),
+                  "speckv_ext_tier_restore_paged")
+        return cache
+
     def drop(self, block_ids: np.ndarray) -> None:
         ids = np.ascontiguousarray(block_ids, dtype=np.uint64)
         check(lib().speckv_ext_tier_drop(self._h, ids.ctypes.data, ids.size), "speckv_ext_tier_drop")

@@ -93,6 +93,21 @@ class CxlSpeckvKVAllocator:
         if ret != 0:
             raise RuntimeError(f"speckv_ext_fetch_pages failed: {ret}")
 
+    # ---- additive: vLLM block tables ----
+    @staticmethod
+    def offload_kv_blocks(kv_cache, block_table, tier, block_ids=None):
+        """Compress the cache blocks `block_table` (CUDA int32 tensor of block numbers) of a paged KV cache
+        tensor ([num_blocks, block_size, kv_heads, head_dim], contiguous) out to the host tier, reading them
+        in place.  They are stored under `block_ids` (default: the block numbers themselves)."""
+        ids = block_table.cpu().numpy().astype("uint64") if block_ids is None else block_ids
+        tier.offload_blocks(kv_cache, block_table, ids)
+
+    @staticmethod
+    def restore_kv_blocks(kv_cache, block_table, tier, block_ids=None):
+        """Bring stored blocks back into the cache blocks `block_table` (decompressed in place)."""
+        ids = block_table.cpu().numpy().astype("uint64") if block_ids is None else block_ids
+        tier.restore_blocks(ids, kv_cache, block_table)
+
     # ---- additive: residency policy driving the data path (SURVEY.md section 8f row 2) ----
     def attach_policy(self, policy):
         """`policy`: a cxl_speckv_b200.tier.TierPolicy over this region's pages (page i of the policy =

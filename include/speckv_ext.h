@@ -195,6 +195,19 @@ SPECKV_API void speckv_ext_tier_destroy(speckv_tier_t* tier);
 SPECKV_API speckv_status_t speckv_ext_tier_offload(speckv_tier_t* tier, const void* d_in, speckv_dtype_t dtype,
                                                    size_t group_elems, size_t n_groups,
                                                    const uint64_t* h_block_ids, void* cuda_stream);
+/* Paged forms (the KV cache is a pool of blocks of group_elems elements, vLLM layout; d_block_table is a
+ * DEVICE array of n_blocks cache block numbers): block d_block_table[i] of d_cache is compressed and stored
+ * under h_block_ids[i] / block h_block_ids[i] is decompressed into cache block d_block_table[i].  The
+ * codec kernels gather / scatter through the table: no staging copy of the blocks on either side.
+ * Block numbers must be distinct within a restore call. */
+SPECKV_API speckv_status_t speckv_ext_tier_offload_paged(speckv_tier_t* tier, const void* d_cache,
+                                                         const uint32_t* d_block_table, speckv_dtype_t dtype,
+                                                         size_t group_elems, size_t n_blocks,
+                                                         const uint64_t* h_block_ids, void* cuda_stream);
+SPECKV_API speckv_status_t speckv_ext_tier_restore_paged(speckv_tier_t* tier, const uint64_t* h_block_ids,
+                                                         size_t n_blocks, size_t group_elems, speckv_dtype_t dtype,
+                                                         void* d_cache, const uint32_t* d_block_table,
+                                                         void* cuda_stream);
 /* Bring blocks back: output group i (d_out + i*group_elems) = decompressed block h_block_ids[i].
  * Unknown id -> SPECKV_ERR_GENERAL.  Returns when d_out is complete. */
 SPECKV_API speckv_status_t speckv_ext_tier_restore(speckv_tier_t* tier, const uint64_t* h_block_ids, size_t n_groups,

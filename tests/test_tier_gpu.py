@@ -185,3 +185,61 @@ def test_descriptor_interface_like_the_reference_ioctl_client():
             L.speckv_finalize()
     finally:
         tier.close()
+
+
+@pytest.mark.parametrize("G,num_blocks,n_sel", [(2048, 70000, 40000), (32768, 900, 555), (1000, 400, 123)])
+def test_paged_offload_restore_through_block_tables(G, num_blocks, n_sel):
+    """speckv_ext_tier_offload_paged / _restore_paged: blocks of a paged KV cache leave and come back through
+    block tables (vLLM layout), several chunks per call; the result equals the staged path bit for bit and
+    cache blocks that were not named stay untouched."""
+    torch.manual_seed(G + 1)
+    rng = np.random.default_rng(G)
+    cache = torch.randn(num_blocks, G, device=DEV).half()
+    cache[5] = 0
+    table = rng.permutation(num_blocks)[:n_sel].astype(np.int32)
+    if 5 not in table:
+        table[0] = 5
+    td = torch.from_numpy(table).to(DEV)
+    ids = (np.arange(n_sel, dtype=np.uint64) + np.uint64(7)) << np.uint64(12)
+    tier = HostTier(pool_bytes=int(n_sel * G * 2 * 1.6) + (1 << 20))
+    try:
+        tier.offload_blocks(cache, td, ids)
+        assert tier.stats()["blocks"] == n_sel
+        want = codec.decompress(codec.compress(cache[td.long()].contiguous(), G))   # staged path on the same blocks
+        # come back into another cache, through another table, in another order
+        dst = torch.full((num_blocks, G), 0x1234, dtype=torch.int16, device=DEV).view(torch.float16)
+        order = rng.permutation(n_sel)
+        dst_table = rng.permutation(num_blocks)[:n_sel].astype(np.int32)
+        tier.restore_blocks(ids[order], dst, torch.from_numpy(dst_table).to(DEV))
+        got = dst.view(torch.int16)
+        assert torch.equal(got[torch.from_numpy(dst_table).to(DEV).long()],
+                           want.view(torch.int16)[torch.from_numpy(order).to(DEV)])
+        untouched = np.setdiff1d(np.arange(num_blocks), dst_table)
+        assert (got[torch.from_numpy(untouched).to(DEV)] == 0x1234).all()
+        # the contiguous entry points see the same stored blocks
+        y = tier.restore(ids[:16], G, torch.float16)
+        assert torch.equal(y.view(torch.int16), want[:16].view(torch.int16))
+    finally:
+        tier.close()
+
+
+def test_allocator_block_table_helpers():
+    """CxlSpeckvKVAllocator.offload_kv_blocks / restore_kv_blocks on a vLLM-shaped cache
+    ([num_blocks, block_size 16, kv_heads 8, head_dim 128] fp16: one block = one 16384-element group)."""
+    from cxl_speckv_b200 import CxlSpeckvKVAllocator
+    torch.manual_seed(3)
+    cache = torch.randn(300, 16, 8, 128, device=DEV).half()
+    keep = cache.clone()
+    table = torch.tensor([7, 3, 250, 11, 12, 13, 299, 0], dtype=torch.int32, device=DEV)
+    tier = HostTier(pool_bytes=64 << 20)
+    try:
+        CxlSpeckvKVAllocator.offload_kv_blocks(cache, table, tier)
+        cache[table.long()] = 0                                      # the blocks are gone from HBM
+        CxlSpeckvKVAllocator.restore_kv_blocks(cache, table, tier)
+        want = codec.decompress(codec.compress(keep[table.long()].reshape(-1), 16 * 8 * 128)).view(8, 16, 8, 128)
+        assert torch.equal(cache[table.long()].view(torch.int16), want.view(torch.int16))
+        others = torch.ones(300, dtype=torch.bool, device=DEV)
+        others[table.long()] = False
+        assert torch.equal(cache[others].view(torch.int16), keep[others].view(torch.int16))
+    finally:
+        tier.close()
