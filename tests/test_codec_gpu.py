@@ -572,3 +572,14 @@ def test_decode_zero_valued_regions(tdt):
         n = int(want_n[g])
         assert np.array_equal(got[g, :n], want[g, :n]), g
         assert (got[g, n:] == 0x1234).all(), g
+
+
+def test_plain_c_host_program_on_the_gpu(tmp_path):
+    """tests/c/frozen_abi.c with a CUDA device: C host code -> C ABI -> kernels, no Python in the data path.
+    Checks the reference's KAT-1 bytes / scale / decompressed values and the three translate_address
+    results recorded from the reference."""
+    import subprocess
+    from tests.test_abi_cpu import _build_c_program
+    exe = _build_c_program(tmp_path, with_cuda=True)
+    r = subprocess.run([exe, "cuda:0"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
