@@ -15,7 +15,7 @@
 //   p = softmax(logits) (max-subtracted), top-k by p                                  :176-188,:72-92
 //   request i: va = (req << 32) | (layer << 16) | (i + 1)         speculative_prefetcher.cpp:153-160
 // Kernels:
-//   hidden_kernel   one thread per sequence (16 x 2 cell updates on scalars)
+//   hidden_kernel   one warp per sequence: gather the window's embedding rows, then 16 x 2 cell updates on scalars
 //   logits_kernel   CTA = 128 vocabulary rows staged in shared memory (W read once per batch
 //                   tile: 16.4 MB total, L2 resident), each thread keeps the sequential
 //                   j-order of the reference for BB sequences at a time
@@ -59,6 +59,40 @@ __global__ void hidden_kernel(const uint32_t* __restrict__ tokens, uint32_t batc
             const float* e = emb + (size_t)tok * emb_dim;
             for (uint32_t j = 0; j < nj; ++j) g = __fadd_rn(g, __fmul_rn(__ldg(e + j), 0.1f));
         }
+        const float tg = (float)tanh((double)g);
+        for (uint32_t l = 0; l < layers; ++l) {
+            c = __fadd_rn(__fmul_rn(0.5f, c), __fmul_rn(0.5f, tg));
+            h = __fmul_rn(0.5f, (float)tanh((double)c));
+        }
+    }
+    h_out[b] = h;
+}
+
+// Same recurrence, one WARP per sequence: the lanes first gather the window's embedding rows into shared
+// memory (hist_len x nj independent loads in flight instead of one dependent load per addition), then lane 0
+// runs the reference's sequential sums over them.  84 us -> a few us for 256 sequences.
+constexpr int kHiddenWarps = 4;
+__global__ void __launch_bounds__(kHiddenWarps * 32)
+hidden_warp_kernel(const uint32_t* __restrict__ tokens, uint32_t batch, uint32_t hist_len,
+                   const float* __restrict__ emb, uint32_t vocab, uint32_t emb_dim, uint32_t hidden, uint32_t layers,
+                   float* __restrict__ h_out) {
+    extern __shared__ float se[];   // [kHiddenWarps][hist_len][nj]
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t b = blockIdx.x * kHiddenWarps + warp;
+    if (b >= batch) return;
+    const uint32_t nj = emb_dim < hidden ? emb_dim : hidden;
+    float* my = se + (size_t)warp * hist_len * nj;
+    for (uint32_t idx = lane; idx < hist_len * nj; idx += 32) {
+        const uint32_t t = idx / nj, j = idx - t * nj;
+        const uint32_t tok = tokens[(size_t)b * hist_len + t];
+        my[idx] = tok < vocab ? __ldg(emb + (size_t)tok * emb_dim + j) : 0.0f;   // out-of-vocabulary ids embed to zeros
+    }
+    __syncwarp();
+    if (lane != 0) return;
+    float h = 0.0f, c = 0.0f;
+    for (uint32_t t = 0; t < hist_len; ++t) {
+        float g = 0.0f;
+        for (uint32_t j = 0; j < nj; ++j) g = __fadd_rn(g, __fmul_rn(my[t * nj + j], 0.1f));
         const float tg = (float)tanh((double)g);
         for (uint32_t l = 0; l < layers; ++l) {
             c = __fadd_rn(__fmul_rn(0.5f, c), __fmul_rn(0.5f, tg));
@@ -253,8 +287,15 @@ speckv_status_t speckv_ext_prefetch_score(const uint32_t* d_tokens, uint32_t bat
         if (e != cudaSuccess) return status_of(e);
         g_pred.max_batch = batch;
     }
-    hidden_kernel<<<(batch + 127) / 128, 128, 0, st>>>(d_tokens, batch, g_pred.hist_len, g_pred.d_emb, g_pred.vocab,
-                                                       g_pred.emb_dim, g_pred.hidden, g_pred.layers, g_pred.d_hidden);
+    const uint32_t nj = g_pred.emb_dim < g_pred.hidden ? g_pred.emb_dim : g_pred.hidden;
+    const size_t hsmem = (size_t)kHiddenWarps * g_pred.hist_len * nj * sizeof(float);
+    if (hsmem <= 48 * 1024)
+        hidden_warp_kernel<<<(batch + kHiddenWarps - 1) / kHiddenWarps, kHiddenWarps * 32, hsmem, st>>>(
+            d_tokens, batch, g_pred.hist_len, g_pred.d_emb, g_pred.vocab, g_pred.emb_dim, g_pred.hidden, g_pred.layers,
+            g_pred.d_hidden);
+    else   // very long windows / wide embeddings: the one-thread-per-sequence form needs no staging
+        hidden_kernel<<<(batch + 127) / 128, 128, 0, st>>>(d_tokens, batch, g_pred.hist_len, g_pred.d_emb, g_pred.vocab,
+                                                           g_pred.emb_dim, g_pred.hidden, g_pred.layers, g_pred.d_hidden);
     const size_t smem = (size_t)(g_pred.hidden + 1) * kRows * sizeof(float);
     e = cudaFuncSetAttribute(logits_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return status_of(e);

@@ -29,34 +29,42 @@ namespace {
 constexpr int kPackThreads = 256;
 constexpr uint32_t kTierPage = 4096;
 
-// exclusive scan of the 16-byte-rounded payload sizes: one CTA, sequential over tiles of 1024
+// exclusive scan of the 16-byte-rounded payload sizes, one CTA of 32 warps: every warp scans one contiguous
+// segment tile by tile with no block barrier in between (its loads do not depend on the running sum, so they
+// pipeline), the 32 segment totals are combined once and added in a second pass (the 44 us of a
+// tile-serial scan with three block barriers per 1024 sizes was 12 % of a paged offload chunk)
 __global__ void __launch_bounds__(1024)
 pack_offsets_kernel(const uint32_t* __restrict__ comp_bytes, uint32_t n, uint64_t* __restrict__ offsets,
                     uint64_t* __restrict__ total) {
-    __shared__ uint64_t warp_sum[32];
-    __shared__ uint64_t carry;
+    __shared__ uint64_t warp_total[32];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    if (tid == 0) carry = 0;
-    __syncthreads();
-    for (uint32_t base = 0; base < n; base += 1024) {
-        const uint32_t i = base + tid;
-        const uint64_t v = i < n ? (((uint64_t)comp_bytes[i] + 15u) & ~15ull) : 0ull;
+    const uint32_t seg = ((n + 31u) / 32u + 31u) & ~31u;          // per-warp segment, a multiple of 32
+    const uint32_t s0 = min(n, (uint32_t)wid * seg), s1 = min(n, s0 + seg);
+    uint64_t carry = 0;
+#pragma unroll 4
+    for (uint32_t base = s0; base < s1; base += 32) {
+        const uint32_t i = base + lane;
+        const uint64_t v = i < s1 ? (((uint64_t)comp_bytes[i] + 15u) & ~15ull) : 0ull;
         uint64_t inc = v;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             const uint64_t t = __shfl_up_sync(0xffffffffu, inc, o);
             if (lane >= o) inc += t;
         }
-        if (lane == 31) warp_sum[wid] = inc;
-        __syncthreads();
-        uint64_t before = carry;
-        for (int w = 0; w < wid; ++w) before += warp_sum[w];
-        if (i < n) offsets[i] = before + inc - v;
-        __syncthreads();
-        if (tid == 1023) carry = before + inc;
-        __syncthreads();
+        if (i < s1) offsets[i] = carry + inc - v;
+        carry += __shfl_sync(0xffffffffu, inc, 31);
     }
-    if (tid == 0) *total = carry;
+    if (lane == 0) warp_total[wid] = carry;
+    __syncthreads();
+    uint64_t before = 0, all = 0;
+    for (int w = 0; w < 32; ++w) {
+        const uint64_t t = warp_total[w];
+        if (w < wid) before += t;
+        all += t;
+    }
+    if (before)
+        for (uint32_t i = s0 + lane; i < s1; i += 32) offsets[i] += before;   // this warp's own writes: no barrier needed
+    if (tid == 0) *total = all;
 }
 
 // one warp per block: copy its payload (rounded up to 16 B) from the slot into the packed stream
