@@ -491,47 +491,83 @@ def run_cfg4(args, local_rank):
                       "verified": "restored pages == device compress->decompress, bit for bit"}), flush=True)
 
 
-def run_cfg5(args, local_rank):
-    """Batch-256 decode step: LSTM prefetch scoring (k = 4) + decompress of the predicted blocks."""
+def run_cfg5(args, rank, world, local_rank):
+    """Batch-256 decode step: LSTM prefetch scoring (k = 4) + decompress of the predicted blocks.
+    N GPUs: the 256 sequences split over the ranks; every rank scores its share, the PrefetchRequest records
+    (32 bytes each) are all-gathered over NCCL -- the only collective -- and every rank
+    decodes the predicted blocks it owns (stored blocks shard round-robin, like layers)."""
     import numpy as np
     import torch
+    import torch.distributed as dist
 
-    from cxl_speckv_b200 import codec, prefetch
+    from cxl_speckv_b200 import codec, prefetch, sharding
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
     rng = np.random.default_rng(1)
     emb = ((rng.random((32000, 64), dtype=np.float32) - 0.5) * 0.1).astype(np.float32)
     wout = ((rng.random((32000, 128), dtype=np.float32) - 0.5) * 0.1).astype(np.float32)
     prefetch.load_predictor(emb, wout)
-    toks = torch.from_numpy(np.random.default_rng(7).integers(0, 32000, (256, 16)).astype(np.int32)).to(dev)
-    G, n_blocks = 131072, 4096                                    # 1 GiB of stored blocks to pick from
-    x = torch.randn(n_blocks * G, device=dev).half()
+    batch, k = 256, 4
+    all_toks = np.random.default_rng(7).integers(0, 32000, (batch, 16)).astype(np.int32)
+    per = (batch + world - 1) // world
+    toks = torch.from_numpy(all_toks[rank * per:(rank + 1) * per]).to(dev)
+    G, n_blocks = 131072, 4096                                    # 1 GiB of stored blocks to pick from, in all
+    local_blocks = n_blocks // world                              # block b lives on rank b % world as local block b // world
+    x = torch.empty(local_blocks * G, device=dev, dtype=torch.float16).normal_()
     c = codec.compress(x, G)
-    out = torch.empty((1024, G), dtype=torch.float16, device=dev)
+    out = torch.empty((batch * k, G), dtype=torch.float16, device=dev)   # worst case: every prediction lands here
 
     def step():
-        ids, conf, va = prefetch.score(toks, k=4, layer_id=0)
-        codec.decompress_indexed(c, (ids.view(-1) % n_blocks).to(torch.int32), out=out)
+        ids, conf, va = prefetch.score(toks, k=k, layer_id=0)
+        if world == 1:
+            blocks = (ids.view(-1) % n_blocks).to(torch.int32)
+            codec.decompress_indexed(c, blocks, out=out[:blocks.numel()])
+            return blocks.numel()
+        rec = sharding.pack_prefetch_requests(va, 0, ids, conf)
+        allrec = sharding.gather_records(rec, sharding.PREFETCH_RECORD_BYTES)          # [world, per * k, 32]
+        _, _, tok, _ = sharding.unpack_prefetch_requests(allrec.view(-1, sharding.PREFETCH_RECORD_BYTES))
+        blocks = tok.to(torch.int64) % n_blocks
+        mine = blocks[blocks % world == rank] // world
+        n = int(mine.numel())                                      # host sync: the size of this rank's decode batch
+        if n:
+            codec.decompress_indexed(c, mine.to(torch.int32), out=out[:n])
+        return n
 
     for _ in range(3):
         step()
     torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
     a, b, m = (torch.cuda.Event(enable_timing=True) for _ in range(3))
     reps = 10
     a.record()
     for _ in range(reps):
-        ids, conf, va = prefetch.score(toks, k=4, layer_id=0)
+        prefetch.score(toks, k=k, layer_id=0)
     m.record()
+    decoded = 0
     for _ in range(reps):
-        step()
+        decoded += step()
     b.record(); torch.cuda.synchronize()
-    t_score = a.elapsed_time(m) / reps
-    t_step = m.elapsed_time(b) / reps
-    print(json.dumps({"report": "cfg5", "workload": "256 sequences x 16-token history, vocab 32000, k=4 -> 1024 predicted blocks of 1024x128 fp16",
-                      "score_ms": t_score, "score_seq_per_s": 256 / t_score * 1e3, "reference_cpu_ms_per_sequence": 17.8,
-                      "step_ms(score+decompress 1024 blocks)": t_step,
-                      "decompress_kv_GB/s": 1024 * G * 2 / ((t_step - t_score) * 1e-3) / 1e9}), flush=True)
+    t = torch.tensor([a.elapsed_time(m) / reps, m.elapsed_time(b) / reps, float(decoded) / reps], device=dev, dtype=torch.float64)
+    tot = t.clone()
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)                    # times: max over ranks
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)                  # decoded blocks: sum over ranks
+    t_score, t_step, n_dec = float(t[0]), float(t[1]), float(tot[2])
+    if rank == 0:
+        print(json.dumps({"report": "cfg5", "n_gpus": world,
+                          "workload": "256 sequences x 16-token history, vocab 32000, k=4 -> 1024 predicted blocks of 1024x128 fp16",
+                          "score_ms": t_score, "score_seq_per_s": batch / t_score * 1e3, "reference_cpu_ms_per_sequence": 17.8,
+                          "step_ms(score+exchange+decompress)": t_step, "blocks_decoded_per_step": n_dec,
+                          "step_seq_per_s": batch / t_step * 1e3,
+                          "decompress_kv_GB/s": n_dec * G * 2 / (max(t_step - t_score, 1e-9) * 1e-3) / 1e9,
+                          "exchange": "none (1 GPU)" if world == 1 else f"all-gather of {batch * k} PrefetchRequest records (32 B) over NCCL"}),
+              flush=True)
+    if world > 1:
+        dist.destroy_process_group()
 
 
 def run_ratios(args, local_rank):
@@ -595,7 +631,7 @@ def main():
     if args.workload == "cfg4":
         run_cfg4(args, local_rank)
     elif args.workload == "cfg5":
-        run_cfg5(args, local_rank)
+        run_cfg5(args, rank, world, local_rank)
     elif args.workload == "ratios":
         run_ratios(args, local_rank)
     elif args.impl == "reference":

@@ -62,3 +62,48 @@ def test_single_process_paths():
     assert torch.equal(sharding.gather_page_metadata(t), t.view(1, 6))
     with pytest.raises(ValueError):
         sharding.shard_layers(4, 2, 2)
+
+
+def _record_worker(rank, world, port, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        # prefetch requests of this rank's sequences (PrefetchRequest records)
+        n = 12
+        va = (torch.arange(n, dtype=torch.int64) + 1) | (rank << 32) | (5 << 16)
+        ids = torch.arange(n, dtype=torch.int32) * 7 + rank
+        conf = torch.linspace(0.9, 0.1, n) / (rank + 1)
+        rec = sharding.pack_prefetch_requests(va, 5, ids, conf, timestamp=1000 + rank)
+        allrec = sharding.gather_records(rec, sharding.PREFETCH_RECORD_BYTES)
+        ok = allrec.shape == (world, n, 32)
+        for r in range(world):
+            v, l, t, c = sharding.unpack_prefetch_requests(allrec[r])
+            ok &= torch.equal(v, (torch.arange(n, dtype=torch.int64) + 1) | (r << 32) | (5 << 16))
+            ok &= bool((l == 5).all()) and torch.equal(t, torch.arange(n, dtype=torch.int32) * 7 + r)
+            ok &= torch.equal(c, torch.linspace(0.9, 0.1, n) / (r + 1))
+            ok &= int(allrec[r].view(torch.int64).view(n, 4)[0, 3]) == 1000 + r
+        # page-table deltas: 24-byte KvPageHandle records {virt, phys, size, flags}
+        pages = torch.zeros((4, 3), dtype=torch.int64)
+        pages[:, 0] = ((rank + 1) << 32) | (torch.arange(4) << 12)
+        pages[:, 1] = 0x4000000000 + ((rank + 1) << 20) + (torch.arange(4) << 12)
+        pages[:, 2] = 4096 | (0b101 << 32)
+        allpages = sharding.gather_records(pages.view(torch.uint8).view(4, 24), sharding.PAGE_RECORD_BYTES)
+        for r in range(world):
+            p = allpages[r].contiguous().view(torch.int64).view(4, 3)
+            ok &= int(p[2, 0]) == ((r + 1) << 32) | (2 << 12) and int(p[3, 1]) == 0x4000000000 + ((r + 1) << 20) + (3 << 12)
+            ok &= int(p[0, 2]) & 0xFFFFFFFF == 4096 and int(p[0, 2]) >> 32 == 0b101
+        ret[rank] = bool(ok)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_fixed_size_record_allgather():
+    """The per-step metadata exchange of SURVEY.md section 8e: PrefetchRequest (32 B) and KvPageHandle (24 B)
+    records, one all-gather each, world size 2 over gloo."""
+    world = 2
+    port = _free_port()
+    with mp.Manager() as mgr:
+        ret = mgr.dict()
+        mp.spawn(_record_worker, args=(world, port, ret), nprocs=world, join=True)
+        assert dict(ret) == {0: True, 1: True}
