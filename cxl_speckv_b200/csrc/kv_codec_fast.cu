@@ -27,6 +27,7 @@
 #include <cooperative_groups.h>
 
 #include <cstdlib>
+#include <type_traits>
 
 #include "codec_math.cuh"
 #include "device_ctx.h"
@@ -663,6 +664,25 @@ decompress_fast_kernel(const uint8_t* __restrict__ payload, size_t slot_bytes, c
     __syncwarp();
     exchange_init<R>(sm, 2, 0);
 
+    // ---- dequantiser choice (while the tile is in flight).  y = ((float) q / 127.0f) * s costs four operations per
+    // element (codec_math.cuh); q * RN(s / 127) costs two and, after the final rounding to fp16 / bf16, gives the same
+    // bits for almost every scale.  "Almost" is settled exactly: there are only 256 codes, so the regions of a group
+    // check them all against the reference form for this group's scale (256 / R codes per region) and the group
+    // takes the short form only if every code agrees -- the output stays bit-identical either way (decompress +3 %;
+    // ~95 % of the scales qualify).
+    constexpr bool kTryShort = R >= 8;   // at most one code per lane to check; smaller groups keep the reference form
+    const float kq = __fdiv_rn(s, 127.0f);
+    bool deq_differs = !kTryShort;
+    if (kTryShort && active && !cplx) {
+        constexpr int CPR = 256 / R;   // codes checked by each region
+        for (int c = lane; c < CPR; c += 32) {
+            const uint32_t code = (uint32_t)(ridx * CPR + c);
+            const float qf = (float)(int)(int8_t)code;
+            deq_differs |= out_bits<T>(dequantize(code, s)) != out_bits<T>(__fmul_rn(qf, kq));
+        }
+        deq_differs = __any_sync(kFull, deq_differs);
+    }
+
     // ---- A. region totals: elements produced (sum of counts) and code advance (sum of value*count) ----
     uint32_t csum = 0, ssum = 0, nnz = 0;
     bool fill = false;   // region decoded as a constant fill (all pair values zero) instead of through the staging area
@@ -716,13 +736,16 @@ decompress_fast_kernel(const uint8_t* __restrict__ payload, size_t slot_bytes, c
     }
     if (C > 1) cluster_wait();   // all CTAs of the cluster are running: their shared memory may be written
     group_publish<R>(sm, sm.xa, 0, warp, lane, ridx, min(csum, G + 1u));   // saturated: sums stay < 2^32, "> G" still shows
-    group_publish<R>(sm, sm.xb, 0, warp, lane, ridx, ssum | (cplx ? (1u << 24) : 0u));
+    // xb: code advance (8 bits; the sum over <= 128 regions stays below bit 16) | "needs the generic kernel" counted
+    // in bits 16..23 | "short dequantiser differs" counted in bits 24..31
+    group_publish<R>(sm, sm.xb, 0, warp, lane, ridx, ssum | (cplx ? (1u << 16) : 0u) | (deq_differs ? (1u << 24) : 0u));
     group_sync<R>(sm, 0);
     uint32_t e_before, e_total, q_before, xb_total, t0;
     group_reduce<R>(sm.xa, warp, lane, ridx, e_before, e_total, t0);
     group_reduce<R>(sm.xb, warp, lane, ridx, q_before, xb_total, t0);
     if (!active) return;
-    const bool any_cplx = (xb_total >> 24) != 0 || e_total > G;   // output longer than the group: generic kernel clips
+    const bool any_cplx = ((xb_total >> 16) & 0xffu) != 0 || e_total > G;   // output longer than the group: generic kernel clips
+    const bool short_deq = (xb_total >> 24) == 0;
     if (ridx == 0 && lane == 0) {
         needs_generic[g] = any_cplx ? 1u : 0u;
         if (out_elems && !any_cplx) out_elems[g] = e_total;
@@ -753,6 +776,11 @@ decompress_fast_kernel(const uint8_t* __restrict__ payload, size_t slot_bytes, c
 #define SPECKV_UNROLL_C 1
 #endif
     constexpr int kUnrollC = SPECKV_UNROLL_C;
+    auto expand = [&](auto short_tag) {
+    constexpr bool kShort = decltype(short_tag)::value;
+    auto deq = [&](uint32_t code) -> float {
+        return kShort ? __fmul_rn((float)(int)(int8_t)code, kq) : dequantize(code, s);
+    };
 #pragma unroll kUnrollC
     for (uint32_t pk = 0; pk < np; pk += 256u, rd_s += 512u) {
         const uint4 w = lds128s(rd_s);
@@ -784,16 +812,16 @@ decompress_fast_kernel(const uint8_t* __restrict__ payload, size_t slot_bytes, c
             // codes = running byte sums: dp4a against 0x01, 0x0101, ... adds the first 1..4 bytes
             float y[9];
             const uint32_t q4 = __dp4a(v0, 0x01010101u, qb);
-            y[0] = dequantize(__dp4a(v0, 0x00000001u, qb), s);
-            y[1] = dequantize(__dp4a(v0, 0x00000101u, qb), s);
-            y[2] = dequantize(__dp4a(v0, 0x00010101u, qb), s);
-            y[3] = dequantize(q4, s);
-            y[4] = dequantize(__dp4a(v1, 0x00000001u, q4), s);
-            y[5] = dequantize(__dp4a(v1, 0x00000101u, q4), s);
-            y[6] = dequantize(__dp4a(v1, 0x00010101u, q4), s);
+            y[0] = deq(__dp4a(v0, 0x00000001u, qb));
+            y[1] = deq(__dp4a(v0, 0x00000101u, qb));
+            y[2] = deq(__dp4a(v0, 0x00010101u, qb));
+            y[3] = deq(q4);
+            y[4] = deq(__dp4a(v1, 0x00000001u, q4));
+            y[5] = deq(__dp4a(v1, 0x00000101u, q4));
+            y[6] = deq(__dp4a(v1, 0x00010101u, q4));
             const uint32_t q8 = __dp4a(v1, 0x01010101u, q4);
-            y[7] = dequantize(q8, s);
-            y[8] = dequantize(q8 + v2, s);
+            y[7] = deq(q8);
+            y[8] = deq(q8 + v2);
             store_units9(sbase + 2u * idx, pack2_out<T>(y[0], y[1]), pack2_out<T>(y[2], y[3]), pack2_out<T>(y[4], y[5]),
                          pack2_out<T>(y[6], y[7]), pack2_out<T>(y[8], 0.0f), 8 + ntwo);
             ecur += 256u + __popc(bal);
@@ -820,6 +848,9 @@ decompress_fast_kernel(const uint8_t* __restrict__ payload, size_t slot_bytes, c
             qcur = (qcur + (tot >> 24)) & 0xffu;
         }
     }
+    };
+    if (kTryShort && short_deq) expand(std::integral_constant<bool, kTryShort>{});
+    else expand(std::false_type{});
     __syncwarp();
     flush_region(sbase, gout, (int)e0, (int)ecur, lane);   // (an early partial flush, as in compress, measured slower here)
 }
