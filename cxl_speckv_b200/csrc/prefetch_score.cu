@@ -19,9 +19,10 @@
 //   logits_kernel   CTA = 128 vocabulary rows staged in shared memory (W read once per batch
 //                   tile: 16.4 MB total, L2 resident), each thread keeps the sequential
 //                   j-order of the reference for BB sequences at a time
-//   topk_kernel     CTA per sequence: max, sum of exp, k rounds of block arg-max
-// tanh/exp are evaluated in fp64 and rounded once to fp32 (glibc's float versions are within
-// 1 ulp of that); parity is therefore "same top-k ids, confidences within 1e-7", not bitwise
+//   topk_kernel     CTA per sequence: one pass for the max and per-thread best-k lists, k block arg-max rounds over
+//                   the list heads, one pass for the sum of exp
+// tanh and the k reported exp values are evaluated in fp64 and rounded once to fp32 (glibc's float versions are
+// within 1 ulp of that), the 32000 terms of the softmax sum with expf; parity is therefore "same top-k ids, confidences within 1e-7", not bitwise
 // (SURVEY.md section 8a A11).
 #include <cfloat>
 #include <mutex>
@@ -105,22 +106,24 @@ hidden_warp_kernel(const uint32_t* __restrict__ tokens, uint32_t batch, uint32_t
 constexpr int kRows = 128;   // vocabulary rows per CTA
 constexpr int kBB = 8;       // sequences per inner pass
 
-__global__ void __launch_bounds__(kRows)
+constexpr int kLogitSplit = 2;   // threads per vocabulary row: each takes kBB of the kLogitSplit * kBB sequences of a pass
+
+__global__ void __launch_bounds__(kRows * kLogitSplit)
 logits_kernel(const float* __restrict__ wout, uint32_t vocab, uint32_t hidden, const float* __restrict__ h,
               uint32_t batch, float* __restrict__ logits) {
     extern __shared__ float wt[];   // [kRows][hidden + 1]
     const uint32_t v0 = blockIdx.x * kRows;
     const uint32_t ld = hidden + 1;
     const uint32_t rows = min((uint32_t)kRows, vocab - v0);
-    for (uint32_t i = threadIdx.x; i < rows * hidden; i += kRows) {
+    for (uint32_t i = threadIdx.x; i < rows * hidden; i += kRows * kLogitSplit) {
         const uint32_t r = i / hidden, j = i - r * hidden;
         wt[r * ld + j] = __ldg(wout + (size_t)(v0 + r) * hidden + j);
     }
     __syncthreads();
-    const uint32_t r = threadIdx.x;
+    const uint32_t r = threadIdx.x % kRows, part = threadIdx.x / kRows;
     if (r >= rows) return;
     const float* w = wt + r * ld;
-    for (uint32_t b0 = blockIdx.y * kBB; b0 < batch; b0 += gridDim.y * kBB) {
+    for (uint32_t b0 = (blockIdx.y * kLogitSplit + part) * kBB; b0 < batch; b0 += gridDim.y * kLogitSplit * kBB) {
         float hb[kBB], acc[kBB];
 #pragma unroll
         for (int i = 0; i < kBB; ++i) {
@@ -141,6 +144,19 @@ logits_kernel(const float* __restrict__ wout, uint32_t vocab, uint32_t hidden, c
 constexpr int kTopThreads = 256;
 constexpr int kMaxK = 16;
 
+// a > b in the order of the reference's sort by confidence (softmax is monotone in the logit); ties -> lower id
+__device__ __forceinline__ bool better(float av, uint32_t ai, float bv, uint32_t bi) {
+    return av > bv || (av == bv && ai < bi);
+}
+
+// CTA per sequence, two passes over its logits instead of k + 2:
+//   pass 1  every thread keeps the best K of its strided share in registers (sorted insertion) and the max;
+//           K rounds of block arg-max over the heads of the per-thread lists then give the global top-k
+//           (the winner pops its head), identical to k rounds of arg-max over all logits;
+//   pass 2  sum of exp(logit - max) (expf per term, accumulated in fp64, rounded once).
+// The k confidences are exp(best - max) / sum with exp evaluated in fp64 and rounded once (glibc's expf is within
+// 1 ulp of that).
+template <int K>
 __global__ void __launch_bounds__(kTopThreads)
 topk_kernel(const float* __restrict__ logits, uint32_t vocab, uint32_t k, uint32_t req_id, uint32_t layer_id,
             uint32_t* __restrict__ ids, float* __restrict__ conf, uint64_t* __restrict__ va) {
@@ -150,12 +166,34 @@ topk_kernel(const float* __restrict__ logits, uint32_t vocab, uint32_t k, uint32
     __shared__ uint32_t s_idx[kTopThreads / 32];
     __shared__ float s_bcast;
     __shared__ double s_sum;
-    __shared__ uint32_t s_taken[kMaxK];
+    __shared__ float s_win_v[kMaxK];
+    __shared__ uint32_t s_win_i[kMaxK];
     const uint32_t b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const float* lg = logits + (size_t)b * vocab;
-    // max logit (max_element, :176)
+    // ---- pass 1: max logit (max_element, :176) and the thread's best K ----
+    float bv[K];
+    uint32_t bi[K];
+#pragma unroll
+    for (int i = 0; i < K; ++i) {
+        bv[i] = -FLT_MAX;
+        bi[i] = 0xffffffffu;
+    }
     float m = -FLT_MAX;
-    for (uint32_t v = tid; v < vocab; v += kTopThreads) m = fmaxf(m, lg[v]);
+    for (uint32_t v = tid; v < vocab; v += kTopThreads) {
+        const float x = lg[v];
+        m = fmaxf(m, x);
+        if (better(x, v, bv[K - 1], bi[K - 1])) {
+            bv[K - 1] = x;
+            bi[K - 1] = v;
+#pragma unroll
+            for (int i = K - 1; i > 0; --i) {
+                if (better(bv[i], bi[i], bv[i - 1], bi[i - 1])) {
+                    const float tv = bv[i]; bv[i] = bv[i - 1]; bv[i - 1] = tv;
+                    const uint32_t ti = bi[i]; bi[i] = bi[i - 1]; bi[i - 1] = ti;
+                }
+            }
+        }
+    }
     for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
     if (lane == 0) sf[wid] = m;
     __syncthreads();
@@ -166,9 +204,48 @@ topk_kernel(const float* __restrict__ logits, uint32_t vocab, uint32_t k, uint32
     }
     __syncthreads();
     const float mx = s_bcast;
-    // sum of exp (:178-181); accumulated in fp64, rounded once
+    // ---- global top-k: k rounds of block arg-max over the list heads ----
+    for (uint32_t r = 0; r < k; ++r) {
+        float best = bv[0];
+        uint32_t idx = bi[0];
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+            const uint32_t oi = __shfl_xor_sync(0xffffffffu, idx, o);
+            if (better(ob, oi, best, idx)) {
+                best = ob;
+                idx = oi;
+            }
+        }
+        if (lane == 0) {
+            s_best[wid] = best;
+            s_idx[wid] = idx;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            float bb = s_best[0];
+            uint32_t ii = s_idx[0];
+            for (int w = 1; w < kTopThreads / 32; ++w)
+                if (better(s_best[w], s_idx[w], bb, ii)) {
+                    bb = s_best[w];
+                    ii = s_idx[w];
+                }
+            s_win_v[r] = bb;
+            s_win_i[r] = ii;
+        }
+        __syncthreads();
+        if (bi[0] == s_win_i[r] && bi[0] != 0xffffffffu) {   // the winner pops its head
+#pragma unroll
+            for (int i = 0; i + 1 < K; ++i) {
+                bv[i] = bv[i + 1];
+                bi[i] = bi[i + 1];
+            }
+            bv[K - 1] = -FLT_MAX;
+            bi[K - 1] = 0xffffffffu;
+        }
+    }
+    // ---- pass 2: sum of exp (:178-181); accumulated in fp64, rounded once ----
     double sum = 0.0;
-    for (uint32_t v = tid; v < vocab; v += kTopThreads) sum += (double)(float)exp((double)__fsub_rn(lg[v], mx));
+    for (uint32_t v = tid; v < vocab; v += kTopThreads) sum += (double)expf(__fsub_rn(lg[v], mx));
     for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
     if (lane == 0) sd[wid] = sum;
     __syncthreads();
@@ -179,47 +256,11 @@ topk_kernel(const float* __restrict__ logits, uint32_t vocab, uint32_t k, uint32
     }
     __syncthreads();
     const float denom = (float)s_sum;
-    // top-k: k rounds of block arg-max over the logits (softmax is monotone); ties -> lower id
-    for (uint32_t r = 0; r < k; ++r) {
-        float best = -FLT_MAX;
-        uint32_t bi = 0xffffffffu;
-        for (uint32_t v = tid; v < vocab; v += kTopThreads) {
-            bool taken = false;
-            for (uint32_t q = 0; q < r; ++q) taken |= (s_taken[q] == v);
-            const float x = lg[v];
-            if (!taken && (x > best || (x == best && v < bi))) {
-                best = x;
-                bi = v;
-            }
-        }
-        for (int o = 16; o > 0; o >>= 1) {
-            const float ob = __shfl_xor_sync(0xffffffffu, best, o);
-            const uint32_t oi = __shfl_xor_sync(0xffffffffu, bi, o);
-            if (ob > best || (ob == best && oi < bi)) {
-                best = ob;
-                bi = oi;
-            }
-        }
-        if (lane == 0) {
-            s_best[wid] = best;
-            s_idx[wid] = bi;
-        }
-        __syncthreads();
-        if (tid == 0) {
-            float bb = s_best[0];
-            uint32_t ii = s_idx[0];
-            for (int w = 1; w < kTopThreads / 32; ++w)
-                if (s_best[w] > bb || (s_best[w] == bb && s_idx[w] < ii)) {
-                    bb = s_best[w];
-                    ii = s_idx[w];
-                }
-            s_taken[r] = ii;
-            const float e = (float)exp((double)__fsub_rn(bb, mx));
-            ids[(size_t)b * k + r] = ii;
-            conf[(size_t)b * k + r] = __fdiv_rn(e, denom);                                   // logits[i] /= sum_exp, :183-185
-            va[(size_t)b * k + r] = ((uint64_t)req_id << 32) | ((uint64_t)layer_id << 16) | (uint64_t)(r + 1);
-        }
-        __syncthreads();
+    if (tid < k) {
+        const float e = (float)exp((double)__fsub_rn(s_win_v[tid], mx));
+        ids[(size_t)b * k + tid] = s_win_i[tid];
+        conf[(size_t)b * k + tid] = __fdiv_rn(e, denom);                                  // logits[i] /= sum_exp, :183-185
+        va[(size_t)b * k + tid] = ((uint64_t)req_id << 32) | ((uint64_t)layer_id << 16) | (uint64_t)(tid + 1);
     }
 }
 
@@ -300,11 +341,16 @@ speckv_status_t speckv_ext_prefetch_score(const uint32_t* d_tokens, uint32_t bat
     e = cudaFuncSetAttribute(logits_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return status_of(e);
     const unsigned vtiles = (g_pred.vocab + kRows - 1) / kRows;
-    unsigned ysplit = (batch + kBB - 1) / kBB;
+    unsigned ysplit = (batch + kBB * kLogitSplit - 1) / (kBB * kLogitSplit);
     if (ysplit > 4) ysplit = 4;   // a few batch slices per vocabulary tile keep all SMs busy
-    logits_kernel<<<dim3(vtiles, ysplit), kRows, smem, st>>>(g_pred.d_wout, g_pred.vocab, g_pred.hidden, g_pred.d_hidden,
+    logits_kernel<<<dim3(vtiles, ysplit), kRows * kLogitSplit, smem, st>>>(g_pred.d_wout, g_pred.vocab, g_pred.hidden, g_pred.d_hidden,
                                                              batch, g_pred.d_logits);
-    topk_kernel<<<batch, kTopThreads, 0, st>>>(g_pred.d_logits, g_pred.vocab, k, req_id, layer_id, d_ids, d_conf, d_va);
+    if (k <= 4)
+        topk_kernel<4><<<batch, kTopThreads, 0, st>>>(g_pred.d_logits, g_pred.vocab, k, req_id, layer_id, d_ids, d_conf, d_va);
+    else if (k <= 8)
+        topk_kernel<8><<<batch, kTopThreads, 0, st>>>(g_pred.d_logits, g_pred.vocab, k, req_id, layer_id, d_ids, d_conf, d_va);
+    else
+        topk_kernel<kMaxK><<<batch, kTopThreads, 0, st>>>(g_pred.d_logits, g_pred.vocab, k, req_id, layer_id, d_ids, d_conf, d_va);
     count_launch(3);
     return status_of(cudaGetLastError());
 }
