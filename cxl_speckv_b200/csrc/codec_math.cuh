@@ -144,6 +144,22 @@ __device__ __forceinline__ float dequantize(uint32_t code, float s) {
 // produces the "real indefinite" NaN 0xFFC00000 for 0*inf and propagates a NaN
 // operand quieted, whereas the GPU would return its canonical 0x7FFFFFFF.  Keep
 // the fp32 output bit-identical to the reference in those groups too.
+// Narrowing of those results at the fp16 / bf16 boundary: a NaN keeps its sign and the top bits of its payload,
+// quieted (what x86's vcvtps2ph and the oracle's bf16 truncation produce: 0xFFC00000 -> 0xFE00 / 0xFFC0), where
+// cvt.rn.f16.f32 / cvt.rn.bf16.f32 would return the canonical 0x7FFF.  Everything else rounds as narrow<T> does.
+template <typename T> __device__ __forceinline__ T narrow_special(float v) { return narrow<T>(v); }
+template <> __device__ __forceinline__ __half narrow_special<__half>(float v) {
+    if (v != v) {
+        const uint32_t b = __float_as_uint(v);
+        return __ushort_as_half((unsigned short)(((b >> 16) & 0x8000u) | 0x7c00u | 0x0200u | ((b >> 13) & 0x03ffu)));
+    }
+    return __float2half_rn(v);
+}
+template <> __device__ __forceinline__ __nv_bfloat16 narrow_special<__nv_bfloat16>(float v) {
+    if (v != v) return __ushort_as_bfloat16((unsigned short)((__float_as_uint(v) >> 16) | 0x0040u));
+    return __float2bfloat16_rn(v);
+}
+
 __device__ __forceinline__ bool scale_is_special(float s) { return !(fabsf(s) < __int_as_float(0x7f800000)); }
 __device__ __forceinline__ float dequantize_special(uint32_t code_u8, float s) {
     const int q = (int)(int8_t)code_u8;

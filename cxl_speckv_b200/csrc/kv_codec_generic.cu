@@ -399,7 +399,7 @@ decompress_rle_generic_kernel(const uint8_t* __restrict__ payload, size_t slot_b
                     if (e >= lo && e < hi) {
                         while (e >= en.x + (en.y >> 16)) en = s_ent[++j];   // next pair (skips empty ones)
                         const uint32_t code = en.y + ((en.y >> 8) & 0xffu) * (e - en.x + 1u);
-                        vals[i] = narrow<T>(special ? dequantize_special(code & 0xffu, s) : dequantize(code, s));
+                        vals[i] = special ? narrow_special<T>(dequantize_special(code & 0xffu, s)) : narrow<T>(dequantize(code, s));
                     } else {
                         vals[i] = narrow<T>(0.0f);
                     }
@@ -482,7 +482,7 @@ decompress_int8_generic_kernel(const uint8_t* __restrict__ payload, size_t slot_
         T* gout = out + (size_t)(elem_index ? elem_index[g] : g) * G;
         const bool special = scale_is_special(s);
         for (uint32_t i = tid; i < n; i += kThreads)
-            gout[i] = narrow<T>(special ? dequantize_special(gp[i], s) : dequantize(gp[i], s));
+            gout[i] = special ? narrow_special<T>(dequantize_special(gp[i], s)) : narrow<T>(dequantize(gp[i], s));
         if (tid == 0 && out_elems) out_elems[g] = n;
     }
 }

@@ -606,3 +606,34 @@ def test_tuned_and_generic_kernels_agree_at_scale(G, n_groups, dtype):
     for k in ("comp_sum", "comp_xor", "scale_bits_sum", "payload_weighted_sum", "output_weighted_sum"):
         assert a[k] == b[k], (k, a[k], b[k])
     assert a["launches"] > b["launches"]      # the tuned path really ran (fast kernel + flagged second pass)
+
+
+@pytest.mark.parametrize("tdt", [F16, BF16])
+def test_infinite_group_decodes_to_the_oracles_nan_bits(tdt):
+    """A group that contains +-inf has an infinite scale; the reference then decodes 0 * inf = NaN (x86's real
+    indefinite 0xFFC00000) and +-inf.  At the fp16 / bf16 boundary the NaN keeps its sign and payload bits
+    (0xFE00 / 0xFFC0, what x86 F16C and the oracle give), not the GPU's canonical 0x7FFF."""
+    rng = np.random.default_rng(77)
+    G, n_groups = 2048, 6
+    x = rng.standard_normal(n_groups * G).astype(np.float32).reshape(n_groups, G)
+    x[1, 5] = np.inf
+    x[3, 100] = -np.inf
+    x[4, 7] = np.inf
+    x[4, 9] = np.nan
+    if tdt == F16:
+        raw = x.astype(np.float16).reshape(-1)
+    else:
+        raw = bf16_from_f32(x.reshape(-1))
+    c = codec.compress(to_dev(raw, tdt), G)
+    y = codec.decompress(c)
+    payload, scales, comp = Port.compress_batch(raw, G, dtype=tdt, threads=4)
+    want, _ = Port.decompress_batch(payload, scales, comp, G, tdt, threads=4)
+    got = out_bits(y)
+    assert np.array_equal(got, want.view(np.uint16).reshape(n_groups, G))
+    assert (got[1] == (0xFE00 if tdt == F16 else 0xFFC0)).any()
+
+
+def test_randomised_differential_run():
+    """tests/fuzz_codec.py for a few seconds: random geometries, dtypes and value structures against the oracle."""
+    from tests import fuzz_codec
+    fuzz_codec.main(seconds=8.0, seed=11)
