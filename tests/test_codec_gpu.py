@@ -637,3 +637,4 @@ def test_randomised_differential_run():
     """tests/fuzz_codec.py for a few seconds: random geometries, dtypes and value structures against the oracle."""
     from tests import fuzz_codec
     fuzz_codec.main(seconds=8.0, seed=11)
+    fuzz_codec.main_decode(seconds=6.0, seed=12)
