@@ -683,6 +683,126 @@ decompress_fast_kernel(const uint8_t* __restrict__ payload, size_t slot_bytes, c
         deq_differs = __any_sync(kFull, deq_differs);
     }
 
+    // ---- the expansion loop (phase C), defined here because one-region groups run it without phase A ----
+    uint32_t ecur = 0;                                     // next element index to produce
+    uint32_t qcur = 0;                                     // code of element ecur - 1
+    uint32_t sbase = reg_s - (uint32_t)kPadBytes;          // element i is staged at sbase + 2*i
+    uint32_t rd_s = reg_s + 16u * (uint32_t)lane;          // this lane's slot of the current iteration
+#ifndef SPECKV_UNROLL_C
+#define SPECKV_UNROLL_C 1
+#endif
+    constexpr int kUnrollC = SPECKV_UNROLL_C;
+    // kShort: the verified two-operation dequantiser.  kSingle: no phase A ran -- pairs past the end of the payload are
+    // blanked here and the staging bound is enforced on the fly; returns false when the region has to go to the
+    // generic kernel instead (it expands beyond what in-place staging can hold).
+    auto expand = [&](auto short_tag, auto single_tag) -> bool {
+    constexpr bool kShort = decltype(short_tag)::value;
+    constexpr bool kSingle = decltype(single_tag)::value;
+    auto deq = [&](uint32_t code) -> float {
+        return kShort ? __fmul_rn((float)(int)(int8_t)code, kq) : dequantize(code, s);
+    };
+#pragma unroll kUnrollC
+    for (uint32_t pk = 0; pk < np; pk += 256u, rd_s += 512u) {
+        uint4 w = lds128s(rd_s);
+        __syncwarp();
+        if (kSingle && pk + 256u > np) {   // the last, partial iteration: blank the pairs past the end (count 0 emits nothing)
+            const int nv = min(max((int)np - (int)pk - lane * 8, 0), 8);
+            uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                if (2 * i >= nv) ww[i] = 0u;
+                else if (2 * i + 1 >= nv) ww[i] &= 0x0000ffffu;
+            }
+            w = make_uint4(ww[0], ww[1], ww[2], ww[3]);
+        }
+        const uint32_t va = __byte_perm(w.x, w.y, 0x6420), ca = __byte_perm(w.x, w.y, 0x7531);
+        const uint32_t vb = __byte_perm(w.z, w.w, 0x6420), cb = __byte_perm(w.z, w.w, 0x7531);
+        // counts: c - 1 is 0 for a count of 1 and 1 for a count of 2; a count of 0 borrows and any
+        // other count leaves higher bits, so "every count is 1 or 2" is one mask test
+        const uint32_t ta = ca - 0x01010101u, tb = cb - 0x01010101u;   // byte j = 1 iff count j is 2
+        const bool small = ((ta | tb) & 0xfefefefeu) == 0;
+        const int ntwo = __popc(ta) + __popc(tb);
+        const bool slow = __any_sync(kFull, !small || ntwo > 1);
+        const uint32_t sl = __dp4a(vb, cb, __dp4a(va, ca, 0u));
+        if (!slow) {
+            // every lane: 8 pairs -> 8 or 9 elements
+            const unsigned bal = __ballot_sync(kFull, ntwo != 0);
+            // in-place staging: the elements of this iteration must end before the slots still to be read (an
+            // earlier iteration with long counts may have used up the slack)
+            if (kSingle && ecur + 256u + (uint32_t)__popc(bal) > pk + 512u - 8u) return false;
+            const uint32_t idx = ecur + 8u * lane + __popc(bal & lt_mask);
+            const uint32_t inc = warp_scan_inclusive(sl);
+            const uint32_t tot = __shfl_sync(kFull, inc, 31);
+            const uint32_t qb = qcur + inc - sl;
+            // Branch-free duplication of the value whose count is 2 (ta / tb hold 1 << (8 * its byte)):
+            // bytes up to and including it stay, the bytes above move up by one; the ninth value is
+            // byte 7 either way (it is only stored when there was a duplicate).
+            const uint32_t keep0 = (ta << 8) - 1u;                  // all ones when the pair is not in word a
+            const uint32_t keep1 = ta ? 0u : (tb << 8) - 1u;
+            const uint32_t up0 = va << 8, up1 = __funnelshift_l(va, vb, 8);
+            const uint32_t v0 = (va & keep0) | (up0 & ~keep0), v1 = (vb & keep1) | (up1 & ~keep1);
+            const uint32_t v2 = vb >> 24;
+            // codes = running byte sums: dp4a against 0x01, 0x0101, ... adds the first 1..4 bytes
+            float y[9];
+            const uint32_t q4 = __dp4a(v0, 0x01010101u, qb);
+            y[0] = deq(__dp4a(v0, 0x00000001u, qb));
+            y[1] = deq(__dp4a(v0, 0x00000101u, qb));
+            y[2] = deq(__dp4a(v0, 0x00010101u, qb));
+            y[3] = deq(q4);
+            y[4] = deq(__dp4a(v1, 0x00000001u, q4));
+            y[5] = deq(__dp4a(v1, 0x00000101u, q4));
+            y[6] = deq(__dp4a(v1, 0x00010101u, q4));
+            const uint32_t q8 = __dp4a(v1, 0x01010101u, q4);
+            y[7] = deq(q8);
+            y[8] = deq(q8 + v2);
+            store_units9(sbase + 2u * idx, pack2_out<T>(y[0], y[1]), pack2_out<T>(y[2], y[3]), pack2_out<T>(y[4], y[5]),
+                         pack2_out<T>(y[6], y[7]), pack2_out<T>(y[8], 0.0f), 8 + ntwo);
+            ecur += 256u + __popc(bal);
+            qcur = (qcur + tot) & 0xffu;
+        } else {
+            // any counts: exclusive scan of (elements, code advance), then per-pair loops
+            const uint32_t cl = __dp4a(cb, 0x01010101u, __dp4a(ca, 0x01010101u, 0u));
+            const uint32_t inc = warp_scan_inclusive(cl | (sl << 24));
+            const uint32_t tot = __shfl_sync(kFull, inc, 31);
+            const uint32_t excl = inc - (cl | (sl << 24));
+            // in-place staging: the elements of this iteration must end before the slots still to be read
+            if (kSingle && ecur + (tot & 0xffffffu) > pk + 512u - 8u) return false;
+            uint32_t p = ecur + (excl & 0xffffffu);
+            uint32_t q = qcur + (excl >> 24);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const uint32_t v = (j < 4 ? va >> (8 * j) : vb >> (8 * (j - 4))) & 0xffu;
+                const uint32_t c = (j < 4 ? ca >> (8 * j) : cb >> (8 * (j - 4))) & 0xffu;
+                for (uint32_t t = 0; t < c; ++t) {
+                    q += v;
+                    sts16(sbase + 2u * (p + t), out_bits<T>(dequantize(q & 0xffu, s)));
+                }
+                p += c;
+            }
+            ecur += tot & 0xffffffu;
+            qcur = (qcur + (tot >> 24)) & 0xffu;
+        }
+    }
+    return true;
+    };
+
+    // ---- one-region groups (4 KiB pages): a single pass.  The region starts at element 0 with code 0, so nothing has
+    // to be known from phase A; its bookkeeping (decoded length, "expands too far for in-place staging", "longer than the
+    // group") falls out of the expansion itself.  Tiny payloads (zero pages are 9 pairs) keep the two-phase path, which
+    // decodes them as a constant fill.
+    if (R == 1 && active && !cplx && np > 64) {
+        mbar_wait(mb, 0);
+        const bool ok = expand(std::false_type{}, std::true_type{}) && ecur <= G;
+        if (lane == 0) {
+            needs_generic[g] = ok ? 0u : 1u;
+            if (out_elems && ok) out_elems[g] = ecur;
+        }
+        if (!ok) return;
+        __syncwarp();
+        flush_region(sbase, reinterpret_cast<uint8_t*>(out + (size_t)(elem_index ? elem_index[g] : g) * G), 0, (int)ecur, lane);
+        return;
+    }
+
     // ---- A. region totals: elements produced (sum of counts) and code advance (sum of value*count) ----
     uint32_t csum = 0, ssum = 0, nnz = 0;
     bool fill = false;   // region decoded as a constant fill (all pair values zero) instead of through the staging area
@@ -768,89 +888,11 @@ decompress_fast_kernel(const uint8_t* __restrict__ payload, size_t slot_bytes, c
         for (uint32_t e = a0 + 8u * lane; e < a1; e += 256u) *reinterpret_cast<uint4*>(go16 + e) = v4;
         return;
     }
-    uint32_t ecur = e0;                       // next element index to produce
-    uint32_t qcur = q_before & 0xffu;         // code of element ecur - 1
-    const uint32_t sbase = reg_s - (uint32_t)kPadBytes - 2u * (e0 & ~7u);   // element i is staged at sbase + 2*i
-    uint32_t rd_s = reg_s + 16u * (uint32_t)lane;   // this lane's slot of the current iteration
-#ifndef SPECKV_UNROLL_C
-#define SPECKV_UNROLL_C 1
-#endif
-    constexpr int kUnrollC = SPECKV_UNROLL_C;
-    auto expand = [&](auto short_tag) {
-    constexpr bool kShort = decltype(short_tag)::value;
-    auto deq = [&](uint32_t code) -> float {
-        return kShort ? __fmul_rn((float)(int)(int8_t)code, kq) : dequantize(code, s);
-    };
-#pragma unroll kUnrollC
-    for (uint32_t pk = 0; pk < np; pk += 256u, rd_s += 512u) {
-        const uint4 w = lds128s(rd_s);
-        __syncwarp();
-        const uint32_t va = __byte_perm(w.x, w.y, 0x6420), ca = __byte_perm(w.x, w.y, 0x7531);
-        const uint32_t vb = __byte_perm(w.z, w.w, 0x6420), cb = __byte_perm(w.z, w.w, 0x7531);
-        // counts: c - 1 is 0 for a count of 1 and 1 for a count of 2; a count of 0 borrows and any
-        // other count leaves higher bits, so "every count is 1 or 2" is one mask test
-        const uint32_t ta = ca - 0x01010101u, tb = cb - 0x01010101u;   // byte j = 1 iff count j is 2
-        const bool small = ((ta | tb) & 0xfefefefeu) == 0;
-        const int ntwo = __popc(ta) + __popc(tb);
-        const bool slow = __any_sync(kFull, !small || ntwo > 1);
-        const uint32_t sl = __dp4a(vb, cb, __dp4a(va, ca, 0u));
-        if (!slow) {
-            // every lane: 8 pairs -> 8 or 9 elements
-            const unsigned bal = __ballot_sync(kFull, ntwo != 0);
-            const uint32_t idx = ecur + 8u * lane + __popc(bal & lt_mask);
-            const uint32_t inc = warp_scan_inclusive(sl);
-            const uint32_t tot = __shfl_sync(kFull, inc, 31);
-            const uint32_t qb = qcur + inc - sl;
-            // Branch-free duplication of the value whose count is 2 (ta / tb hold 1 << (8 * its byte)):
-            // bytes up to and including it stay, the bytes above move up by one; the ninth value is
-            // byte 7 either way (it is only stored when there was a duplicate).
-            const uint32_t keep0 = (ta << 8) - 1u;                  // all ones when the pair is not in word a
-            const uint32_t keep1 = ta ? 0u : (tb << 8) - 1u;
-            const uint32_t up0 = va << 8, up1 = __funnelshift_l(va, vb, 8);
-            const uint32_t v0 = (va & keep0) | (up0 & ~keep0), v1 = (vb & keep1) | (up1 & ~keep1);
-            const uint32_t v2 = vb >> 24;
-            // codes = running byte sums: dp4a against 0x01, 0x0101, ... adds the first 1..4 bytes
-            float y[9];
-            const uint32_t q4 = __dp4a(v0, 0x01010101u, qb);
-            y[0] = deq(__dp4a(v0, 0x00000001u, qb));
-            y[1] = deq(__dp4a(v0, 0x00000101u, qb));
-            y[2] = deq(__dp4a(v0, 0x00010101u, qb));
-            y[3] = deq(q4);
-            y[4] = deq(__dp4a(v1, 0x00000001u, q4));
-            y[5] = deq(__dp4a(v1, 0x00000101u, q4));
-            y[6] = deq(__dp4a(v1, 0x00010101u, q4));
-            const uint32_t q8 = __dp4a(v1, 0x01010101u, q4);
-            y[7] = deq(q8);
-            y[8] = deq(q8 + v2);
-            store_units9(sbase + 2u * idx, pack2_out<T>(y[0], y[1]), pack2_out<T>(y[2], y[3]), pack2_out<T>(y[4], y[5]),
-                         pack2_out<T>(y[6], y[7]), pack2_out<T>(y[8], 0.0f), 8 + ntwo);
-            ecur += 256u + __popc(bal);
-            qcur = (qcur + tot) & 0xffu;
-        } else {
-            // any counts: exclusive scan of (elements, code advance), then per-pair loops
-            const uint32_t cl = __dp4a(cb, 0x01010101u, __dp4a(ca, 0x01010101u, 0u));
-            const uint32_t inc = warp_scan_inclusive(cl | (sl << 24));
-            const uint32_t tot = __shfl_sync(kFull, inc, 31);
-            const uint32_t excl = inc - (cl | (sl << 24));
-            uint32_t p = ecur + (excl & 0xffffffu);
-            uint32_t q = qcur + (excl >> 24);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const uint32_t v = (j < 4 ? va >> (8 * j) : vb >> (8 * (j - 4))) & 0xffu;
-                const uint32_t c = (j < 4 ? ca >> (8 * j) : cb >> (8 * (j - 4))) & 0xffu;
-                for (uint32_t t = 0; t < c; ++t) {
-                    q += v;
-                    sts16(sbase + 2u * (p + t), out_bits<T>(dequantize(q & 0xffu, s)));
-                }
-                p += c;
-            }
-            ecur += tot & 0xffffffu;
-            qcur = (qcur + (tot >> 24)) & 0xffu;
-        }
-    }
-    };
-    if (kTryShort && short_deq) expand(std::integral_constant<bool, kTryShort>{});
-    else expand(std::false_type{});
+    ecur = e0;
+    qcur = q_before & 0xffu;
+    sbase = reg_s - (uint32_t)kPadBytes - 2u * (e0 & ~7u);
+    if (kTryShort && short_deq) expand(std::integral_constant<bool, kTryShort>{}, std::false_type{});
+    else expand(std::false_type{}, std::false_type{});
     __syncwarp();
     flush_region(sbase, gout, (int)e0, (int)ecur, lane);   // (an early partial flush, as in compress, measured slower here)
 }
