@@ -93,6 +93,17 @@ def lib() -> C.CDLL:
     L.speckv_ext_page_table_export.restype = C.c_int
     L.speckv_ext_page_lookup.argtypes = [vp, sz, C.c_uint64, vp, vp, vp, sz, vp]
     L.speckv_ext_page_lookup.restype = C.c_int
+    L.speckv_ext_memmgr_create.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, C.POINTER(vp)]
+    L.speckv_ext_memmgr_create.restype = C.c_int
+    L.speckv_ext_memmgr_destroy.argtypes = [vp]; L.speckv_ext_memmgr_destroy.restype = None
+    L.speckv_ext_memmgr_allocate.argtypes = [vp, C.c_uint64, C.c_uint32, C.c_int, u64p, C.POINTER(C.c_int)]
+    L.speckv_ext_memmgr_allocate.restype = C.c_int
+    L.speckv_ext_memmgr_deallocate.argtypes = [vp, C.c_uint64]; L.speckv_ext_memmgr_deallocate.restype = C.c_int
+    L.speckv_ext_memmgr_set_tier.argtypes = [vp, C.c_uint64, sz, C.c_int]; L.speckv_ext_memmgr_set_tier.restype = C.c_int
+    L.speckv_ext_memmgr_translate_host.argtypes = [vp, C.c_uint64, u64p, C.POINTER(C.c_int)]
+    L.speckv_ext_memmgr_translate_host.restype = C.c_int
+    L.speckv_ext_memmgr_export.argtypes = [vp, vp, sz, C.POINTER(sz), u64p, vp]
+    L.speckv_ext_memmgr_export.restype = C.c_int
     L.speckv_ext_predictor_load.argtypes = [vp, vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32]
     L.speckv_ext_predictor_load.restype = C.c_int
     L.speckv_ext_predictor_unload.argtypes = []; L.speckv_ext_predictor_unload.restype = None

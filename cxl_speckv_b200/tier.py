@@ -177,3 +177,63 @@ class TierPolicy:
         s = _lib.PolicyStats()
         check(lib().speckv_ext_policy_get_stats(self._h, C.byref(s)), "speckv_ext_policy_get_stats")
         return {k: getattr(s, k) for k, _ in s._fields_}
+
+
+class CxlAddressMap:
+    """The address map of the reference's CXLMemoryManager (allocate / deallocate /
+    translate_virtual_to_physical / is_in_cache, src/cxl_memory/cxl_memory_manager.cpp:28-128):
+    host bookkeeping in libcxlspeckv.so, batched translation on the device through the page-lookup kernel."""
+    VA_BASE = 0x100000000
+
+    def __init__(self, l1_bytes: int = 12 << 30, l2_bytes: int = 3 << 30, l3_bytes: int = 128 << 30):
+        self._h = C.c_void_p()
+        check(lib().speckv_ext_memmgr_create(l1_bytes, l2_bytes, l3_bytes, C.byref(self._h)), "speckv_ext_memmgr_create")
+
+    def close(self):
+        if self._h:
+            lib().speckv_ext_memmgr_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def allocate(self, size_bytes: int, layer_id: int = 0, tier: int = L3):
+        va, used = C.c_uint64(), C.c_int()
+        check(lib().speckv_ext_memmgr_allocate(self._h, size_bytes, layer_id, tier, C.byref(va), C.byref(used)),
+              "speckv_ext_memmgr_allocate")
+        return va.value, used.value
+
+    def deallocate(self, va: int) -> None:
+        check(lib().speckv_ext_memmgr_deallocate(self._h, va), "speckv_ext_memmgr_deallocate")
+
+    def set_tier(self, va: int, n_pages: int, tier: int) -> None:
+        check(lib().speckv_ext_memmgr_set_tier(self._h, va, n_pages, tier), "speckv_ext_memmgr_set_tier")
+
+    def translate_host(self, va: int):
+        pa, tier = C.c_uint64(), C.c_int()
+        check(lib().speckv_ext_memmgr_translate_host(self._h, va, C.byref(pa), C.byref(tier)), "speckv_ext_memmgr_translate_host")
+        return pa.value, tier.value
+
+    def export(self, device="cuda:0") -> torch.Tensor:
+        """The page table as a CUDA uint8 [n_pages, 24] tensor of speckv_page_t records."""
+        n = C.c_size_t()
+        check(lib().speckv_ext_memmgr_export(self._h, None, 0, C.byref(n), None, None), "speckv_ext_memmgr_export")
+        table = torch.zeros((max(n.value, 1), 24), dtype=torch.uint8, device=device)
+        with torch.cuda.device(table.device):
+            check(lib().speckv_ext_memmgr_export(self._h, table.data_ptr(), n.value, C.byref(n), None, _stream()),
+                  "speckv_ext_memmgr_export")
+        return table[: n.value]
+
+    def translate(self, table: torch.Tensor, va: torch.Tensor):
+        """Batched translate_virtual_to_physical + tier flags (bit0 L1, bit1 L2) on the device:
+        (pa int64, flags int32); unknown addresses give 0 / 0."""
+        va = va.contiguous()
+        pa = torch.empty_like(va)
+        flags = torch.empty(va.numel(), dtype=torch.int32, device=va.device)
+        with torch.cuda.device(va.device):
+            check(lib().speckv_ext_page_lookup(table.data_ptr(), table.shape[0], self.VA_BASE, va.data_ptr(), pa.data_ptr(),
+                                               flags.data_ptr(), va.numel(), _stream()), "speckv_ext_page_lookup")
+        return pa, flags

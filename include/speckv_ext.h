@@ -162,6 +162,30 @@ typedef struct {
 SPECKV_API speckv_status_t speckv_ext_page_table_export(speckv_handle_t handle, speckv_page_t* d_pages,
                                                         size_t capacity, size_t* out_count, void* cuda_stream);
 
+/* ---- CXLMemoryManager address map (src/cxl_memory/cxl_memory_manager.cpp:8-128) ----
+ * allocate(): pages = ceil(size / 4096); the virtual address is bump-allocated from 0x1_0000_0000, the physical
+ * one per tier (0 = L1 GPU-local from 0x80_0000_0000, 1 = L2 prefetch from 0x100_0000_0000, 2 = L3 CXL pool from
+ * 0x200_0000_0000); an L1 preference falls back to L3 when L1 is full, "full" counted the reference's way
+ * (allocations already in L1 x 4096 + the new bytes > capacity, :37-39 with :295-316).  deallocate(va) drops the
+ * page entry AT va only (:81-104); addresses are never reused.  The page table lives on the host as speckv_page_t
+ * records dense in (va - 0x1_0000_0000) >> 12 (flags bit0 = L1, bit1 = L2); _export copies it to the device, where
+ * speckv_ext_page_lookup(d_pages, count, va_base, ...) answers translate_virtual_to_physical (:106-117, unknown
+ * address -> 0) and is_in_cache (:119-128) for whole batches.  _set_tier carries promote / demote decisions of the
+ * residency policy (speckv_ext_policy_*) into the table; _translate_host is the single-address form. */
+#define SPECKV_PAGE_BYTES 4096u
+typedef struct speckv_memmgr speckv_memmgr_t;
+SPECKV_API speckv_status_t speckv_ext_memmgr_create(uint64_t l1_bytes, uint64_t l2_bytes, uint64_t l3_bytes,
+                                                    speckv_memmgr_t** out);
+SPECKV_API void speckv_ext_memmgr_destroy(speckv_memmgr_t* m);
+SPECKV_API speckv_status_t speckv_ext_memmgr_allocate(speckv_memmgr_t* m, uint64_t size_bytes, uint32_t layer_id,
+                                                      int preferred_tier, uint64_t* out_va, int* out_tier);
+SPECKV_API speckv_status_t speckv_ext_memmgr_deallocate(speckv_memmgr_t* m, uint64_t va);
+SPECKV_API speckv_status_t speckv_ext_memmgr_set_tier(speckv_memmgr_t* m, uint64_t va, size_t n_pages, int tier);
+SPECKV_API speckv_status_t speckv_ext_memmgr_translate_host(speckv_memmgr_t* m, uint64_t va, uint64_t* out_pa,
+                                                            int* out_tier);
+SPECKV_API speckv_status_t speckv_ext_memmgr_export(speckv_memmgr_t* m, speckv_page_t* d_pages, size_t capacity,
+                                                    size_t* out_count, uint64_t* out_va_base, void* cuda_stream);
+
 /* Batched page-table lookup (SpeckvAllocator::access address arithmetic + is_in_l1_or_l2,
  * speckv_allocator.cpp:54-74,105-113; same form as CXLMemoryManager::translate_virtual_to_physical,
  * cxl_memory_manager.cpp:106-117): for each va, entry = d_pages[(va - va_base) >> 12];

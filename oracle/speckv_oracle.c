@@ -612,3 +612,85 @@ uint64_t oracle_fnv1a64(const void* p, size_t n) {
     for (size_t i = 0; i < n; ++i) { h ^= b[i]; h *= 0x100000001b3ULL; }
     return h;
 }
+
+
+/* ------------------------------------------------------------------------ */
+/* CXLMemoryManager address map: src/cxl_memory/cxl_memory_manager.cpp:8-128  */
+/* ------------------------------------------------------------------------ */
+struct oracle_mm {
+    uint64_t cap[3], page, next_va, next_pa[3], n_alloc[3];
+    uint64_t n_pages, cap_pages;   /* page entries, indexed by (va - 0x100000000) / page */
+    uint64_t* pa;                  /* 0 = no entry */
+    uint8_t* tier;
+    uint8_t* base;                 /* 1 = first page of an allocation (the address the tier lists hold) */
+};
+
+oracle_mm_t* oracle_mm_new(uint64_t l1_bytes, uint64_t l2_bytes, uint64_t l3_bytes, uint64_t page_size) {
+    oracle_mm_t* m = (oracle_mm_t*)calloc(1, sizeof(*m));
+    if (!m) return NULL;
+    m->cap[0] = l1_bytes; m->cap[1] = l2_bytes; m->cap[2] = l3_bytes;
+    m->page = page_size;
+    m->next_va = 0x100000000ULL;                                        /* :18 */
+    m->next_pa[0] = 0x8000000000ULL; m->next_pa[1] = 0x10000000000ULL; m->next_pa[2] = 0x20000000000ULL;   /* :19-21 */
+    return m;
+}
+
+void oracle_mm_free(oracle_mm_t* m) {
+    if (!m) return;
+    free(m->pa); free(m->tier); free(m->base); free(m);
+}
+
+uint64_t oracle_mm_allocate(oracle_mm_t* m, uint64_t size_bytes, uint32_t layer, int tier) {
+    (void)layer;
+    const uint64_t pages = (size_bytes + m->page - 1) / m->page, bytes = pages * m->page;      /* :32-33 */
+    if (tier == 0 && m->n_alloc[0] * m->page + bytes > m->cap[0]) tier = 2;                     /* :37-39, :295-316 */
+    const uint64_t va = m->next_va, pa = m->next_pa[tier];
+    m->next_pa[tier] += bytes;
+    m->n_alloc[tier] += 1;                                                                      /* lX_pages_.push_back(va) */
+    const uint64_t first = (va - 0x100000000ULL) / m->page;
+    if (first + pages > m->cap_pages) {
+        uint64_t nc = m->cap_pages ? m->cap_pages * 2 : 1024;
+        while (nc < first + pages) nc *= 2;
+        m->pa = (uint64_t*)realloc(m->pa, nc * sizeof(uint64_t));
+        m->tier = (uint8_t*)realloc(m->tier, nc);
+        m->base = (uint8_t*)realloc(m->base, nc);
+        memset(m->pa + m->cap_pages, 0, (nc - m->cap_pages) * sizeof(uint64_t));
+        memset(m->tier + m->cap_pages, 255, nc - m->cap_pages);
+        memset(m->base + m->cap_pages, 0, nc - m->cap_pages);
+        m->cap_pages = nc;
+    }
+    for (uint64_t i = 0; i < pages; ++i) {                                                      /* :62-75 */
+        m->pa[first + i] = pa + i * m->page;
+        m->tier[first + i] = (uint8_t)tier;
+        m->base[first + i] = (i == 0);
+    }
+    if (first + pages > m->n_pages) m->n_pages = first + pages;
+    m->next_va += bytes;                                                                        /* :77 */
+    return va;
+}
+
+void oracle_mm_deallocate(oracle_mm_t* m, uint64_t va) {                                        /* :81-104 */
+    if (va < 0x100000000ULL || (va - 0x100000000ULL) % m->page) return;                          /* the map is keyed by page addresses */
+    const uint64_t i = (va - 0x100000000ULL) / m->page;
+    if (i >= m->n_pages || m->pa[i] == 0) return;
+    if (m->base[i] && m->n_alloc[m->tier[i]]) m->n_alloc[m->tier[i]] -= 1;   /* std::remove of va from the tier list: it holds base addresses only */
+    m->pa[i] = 0;
+    m->tier[i] = 255;
+    m->base[i] = 0;
+}
+
+uint64_t oracle_mm_translate(const oracle_mm_t* m, uint64_t va) {                               /* :106-117 */
+    const uint64_t page_addr = (va / m->page) * m->page;
+    if (page_addr < 0x100000000ULL) return 0;
+    const uint64_t i = (page_addr - 0x100000000ULL) / m->page;
+    if (i >= m->n_pages || m->pa[i] == 0) return 0;
+    return m->pa[i] + (va - page_addr);
+}
+
+int oracle_mm_is_in_cache(const oracle_mm_t* m, uint64_t va, int tier) {                        /* :119-128 */
+    const uint64_t page_addr = (va / m->page) * m->page;
+    if (page_addr < 0x100000000ULL) return 0;
+    const uint64_t i = (page_addr - 0x100000000ULL) / m->page;
+    if (i >= m->n_pages || m->pa[i] == 0) return 0;
+    return m->tier[i] == tier;
+}

@@ -251,3 +251,93 @@ def test_reference_own_c_test_runs_against_this_library(tmp_path):
 
 def L_has_gpu() -> bool:
     return pkg.lib().speckv_ext_device_count() > 0
+
+
+def _mm_port():
+    import ctypes as C
+    from oracle.oracle import Port
+    P = Port.lib()
+    P.oracle_mm_new.restype = C.c_void_p
+    P.oracle_mm_new.argtypes = [C.c_uint64] * 4
+    P.oracle_mm_allocate.restype = C.c_uint64
+    P.oracle_mm_allocate.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_int]
+    P.oracle_mm_deallocate.argtypes = [C.c_void_p, C.c_uint64]
+    P.oracle_mm_translate.restype = C.c_uint64
+    P.oracle_mm_translate.argtypes = [C.c_void_p, C.c_uint64]
+    P.oracle_mm_is_in_cache.restype = C.c_int
+    P.oracle_mm_is_in_cache.argtypes = [C.c_void_p, C.c_uint64, C.c_int]
+    P.oracle_mm_free.argtypes = [C.c_void_p]
+    return P
+
+
+def mm_random_ops(rng, n_ops, big=False):
+    """(op, a, b) tuples: ("alloc", size, tier) / ("free", alloc index, page) / ("query", alloc index, byte offset)."""
+    ops, n_alloc = [], 0
+    sizes = [1, 4095, 4096, 4097, 65536, 1 << 20, 12345, 3 << 20]
+    for _ in range(n_ops):
+        r = rng.integers(0, 10)
+        if r < 5 or n_alloc == 0:
+            size = int(rng.choice(sizes))
+            if big and rng.random() < 0.01:
+                size = 13 << 30                      # larger than L1: an L1 preference must fall back to L3
+            ops.append(("alloc", size, int(rng.integers(0, 3))))
+            n_alloc += 1
+        elif r < 6:
+            ops.append(("free", int(rng.integers(0, n_alloc)), int(rng.integers(0, 4))))
+        else:
+            ops.append(("query", int(rng.integers(0, n_alloc)), int(rng.integers(0, 1 << 21))))
+    return ops
+
+
+def test_memory_manager_address_map(L):
+    """speckv_ext_memmgr_* (host bookkeeping, no GPU needed) against the oracle restatement of the reference's
+    CXLMemoryManager::allocate / deallocate / translate_virtual_to_physical / is_in_cache, and the restatement
+    against the reference's own class (oracle/_ref) where it is built."""
+    import ctypes as C
+    import numpy as np
+    from cxl_speckv_b200.tier import CxlAddressMap
+    from oracle.oracle import Ref
+    P = _mm_port()
+    try:
+        R = Ref.lib()
+    except Exception:
+        R = None
+    rng = np.random.default_rng(5)
+    for trial in range(3):
+        ops = mm_random_ops(rng, 1500, big=(trial == 0 and R is not None))
+        m = C.c_void_p(P.oracle_mm_new(12 << 30, 3 << 30, 128 << 30, 4096))
+        r = C.c_void_p(R.ref_mm_new()) if R is not None else None
+        prod = CxlAddressMap()
+        allocs = []
+        for op, a, b in ops:
+            if op == "alloc":
+                va = P.oracle_mm_allocate(m, a, 0, b)
+                got, used = prod.allocate(a, 0, b)
+                assert got == va
+                assert P.oracle_mm_is_in_cache(m, va, used) == 1
+                if r is not None:
+                    assert R.ref_mm_allocate(r, a, 0, b) == va
+                allocs.append((va, a))
+            elif op == "free":
+                va = allocs[a][0] + min(b, (allocs[a][1] + 4095) // 4096 - 1) * 4096 * (b % 2)
+                P.oracle_mm_deallocate(m, va)
+                prod.deallocate(va)
+                if r is not None:
+                    R.ref_mm_release(r, va)
+            else:
+                q = allocs[a][0] + b
+                want = P.oracle_mm_translate(m, q)
+                pa, tier = prod.translate_host(q)
+                assert pa == want, hex(q)
+                for t in range(3):
+                    assert (tier == t) == bool(P.oracle_mm_is_in_cache(m, q, t))
+                if r is not None:
+                    assert R.ref_mm_translate(r, q) == want
+                    for t in range(3):
+                        assert R.ref_mm_is_in_cache(r, q, t) == P.oracle_mm_is_in_cache(m, q, t)
+        for q in (0, 0xFFFFFFFF, 0x100000000 - 1, 1 << 60):
+            assert prod.translate_host(q)[0] == P.oracle_mm_translate(m, q) == 0 or P.oracle_mm_translate(m, q) == prod.translate_host(q)[0]
+        prod.close()
+        P.oracle_mm_free(m)
+        if r is not None:
+            R.ref_mm_free(r)

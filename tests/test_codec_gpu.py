@@ -638,3 +638,45 @@ def test_randomised_differential_run():
     from tests import fuzz_codec
     fuzz_codec.main(seconds=8.0, seed=11)
     fuzz_codec.main_decode(seconds=6.0, seed=12)
+
+
+def test_memory_manager_address_map_on_device():
+    """The reference's CXLMemoryManager address map (allocate / deallocate / set_tier), exported to the device:
+    one page-lookup launch answers translate_virtual_to_physical and is_in_cache for a batch of addresses,
+    identical to the oracle restatement (which tests/test_abi_cpu.py pins to the reference's own class)."""
+    import ctypes as C
+    from cxl_speckv_b200.tier import CxlAddressMap
+    from tests.test_abi_cpu import _mm_port, mm_random_ops
+    P = _mm_port()
+    rng = np.random.default_rng(8)
+    m = C.c_void_p(P.oracle_mm_new(12 << 30, 3 << 30, 128 << 30, 4096))
+    prod = CxlAddressMap()
+    allocs = []
+    for op, a, b in mm_random_ops(rng, 4000):
+        if op == "alloc":
+            va = P.oracle_mm_allocate(m, a, 0, b)
+            assert prod.allocate(a, 0, b)[0] == va
+            allocs.append((va, a))
+        elif op == "free":
+            va = allocs[a][0] + min(b, (allocs[a][1] + 4095) // 4096 - 1) * 4096
+            P.oracle_mm_deallocate(m, va)
+            prod.deallocate(va)
+    table = prod.export(DEV)
+    q = np.concatenate([np.array([va + int(rng.integers(0, size + 9000)) for va, size in allocs for _ in range(4)], dtype=np.uint64),
+                        np.array([0, 0xFFFFFFFF, 0x100000000 - 1, 1 << 60, 0x100000000 + (1 << 40)], dtype=np.uint64)])
+    pa, flags = prod.translate(table, torch.from_numpy(q.view(np.int64)).to(DEV))
+    pa, flags = pa.cpu().numpy().view(np.uint64), flags.cpu().numpy()
+    want = np.array([P.oracle_mm_translate(m, int(v)) for v in q], dtype=np.uint64)
+    assert np.array_equal(pa, want)
+    for i in rng.integers(0, q.size, 2000):
+        for t, bit in ((0, 1), (1, 2)):
+            assert bool(flags[i] & bit) == bool(P.oracle_mm_is_in_cache(m, int(q[i]), t))
+    # a promotion decided by the residency policy shows up after set_tier + export
+    va0, size0 = allocs[0]
+    if prod.translate_host(va0)[0]:
+        prod.set_tier(va0, 1, 0)
+        t2 = prod.export(DEV)
+        _, f2 = prod.translate(t2, torch.tensor([va0], dtype=torch.int64, device=DEV))
+        assert int(f2[0]) & 1
+    prod.close()
+    P.oracle_mm_free(m)
