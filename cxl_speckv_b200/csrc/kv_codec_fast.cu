@@ -199,11 +199,18 @@ __device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.w
 template <int R>
 __device__ __forceinline__ void exchange_init(FastSmem& sm, int words0, int words1) {
     if (R > kW) {
-        if (threadIdx.x == 0) {
-            mbar_init_cluster(smem_u32(&sm.xmbar[0]), 1);
-            mbar_init_cluster(smem_u32(&sm.xmbar[1]), 1);
-            mbar_expect_tx(smem_u32(&sm.xmbar[0]), (uint32_t)(R * 4 * words0));
-            if (words1) mbar_expect_tx(smem_u32(&sm.xmbar[1]), (uint32_t)(R * 4 * words1));
+        if (threadIdx.x < 32) {
+            // ptxas turns the initialisation into a warp-uniform operation (executed once for warp 0) while the
+            // expect_tx stays with thread 0: the __syncwarp in between states their order explicitly
+            if (threadIdx.x == 0) {
+                mbar_init_cluster(smem_u32(&sm.xmbar[0]), 1);
+                mbar_init_cluster(smem_u32(&sm.xmbar[1]), 1);
+            }
+            __syncwarp();
+            if (threadIdx.x == 0) {
+                mbar_expect_tx(smem_u32(&sm.xmbar[0]), (uint32_t)(R * 4 * words0));
+                if (words1) mbar_expect_tx(smem_u32(&sm.xmbar[1]), (uint32_t)(R * 4 * words1));
+            }
         }
         cluster_arrive();
     }
