@@ -501,7 +501,10 @@ compress_fast_kernel(const T* __restrict__ in, uint32_t n_groups, uint8_t* __res
     const bool any_cplx = (h_total >> 20) != 0;
     h_before &= 0xfffffu;
     if (!active) return;
-    if (ridx == 0 && lane == 0) needs_generic[g] = any_cplx ? 1u : 0u;
+    if (ridx == 0 && lane == 0) {
+        needs_generic[g] = any_cplx ? 1u : 0u;
+        if (any_cplx) comp_bytes[g] = gmax_bits;   // hand the group max to the generic kernel: it skips its own max pass
+    }
     if (any_cplx) return;
     if (zero_group) {
         if (ridx == 0) {

@@ -197,7 +197,9 @@ compress_rle_generic_kernel(const T* __restrict__ in, uint32_t G, uint32_t n_gro
         uint8_t* gout = payload + (size_t)g * slot_bytes;
         const bool vec_ok = (reinterpret_cast<uintptr_t>(gin) & 15) == 0;
 
-        const float m = group_absmax<T>(gin, G, vec_ok, fbuf);
+        // second pass behind the tuned kernel: that kernel already took the group max and left its bits in
+        // comp_bytes[g] (overwritten with the size below), so the input is read once here, not twice
+        const float m = only_flagged ? __uint_as_float(comp_bytes[g]) : group_absmax<T>(gin, G, vec_ok, fbuf);
         const float s = scale_from_max(m);
         const bool fast = fast_quant_ok<T>(m);
         float r = 0.0f, rl = 0.0f;
