@@ -58,7 +58,7 @@ constexpr int kBlockBytes = kPadBytes + kRegionBytes;
 struct FastSmem {
     alignas(128) uint8_t tile[kW][kBlockBytes];   // [pad][4 KiB region]; outputs are staged in place, 16 B..512 B behind the reads
     alignas(8) unsigned long long mbar[kW];
-    alignas(8) unsigned long long xmbar[2];   // cluster groups: one per exchange round, completed by the peers' st.async bytes
+    alignas(8) unsigned long long xmbar[3];   // cluster groups: one per exchange round, completed by the peers' st.async bytes
     // exchange words of ALL regions of the group (every region pushes its word into every CTA of the
     // cluster), indexed by region for cluster groups and by warp for groups inside one CTA
     uint32_t xa[kMaxR];   // region max bits | head count + flags | sum of counts
@@ -197,19 +197,22 @@ __device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.w
 
 // arm the exchange mbarriers of this CTA (one thread), `words` arrays of R words in round 0
 template <int R>
-__device__ __forceinline__ void exchange_init(FastSmem& sm, int words0, int words1) {
+__device__ __forceinline__ void exchange_init(FastSmem& sm, int words0, int words1, int words2 = 0) {
     if (R > kW) {
         if (threadIdx.x < 32) {
             // ptxas turns the initialisation into a warp-uniform operation (executed once for warp 0) while the
             // expect_tx stays with thread 0: the __syncwarp in between states their order explicitly
-            if (threadIdx.x == 0) {
-                mbar_init_cluster(smem_u32(&sm.xmbar[0]), 1);
-                mbar_init_cluster(smem_u32(&sm.xmbar[1]), 1);
+            if (threadIdx.x == 0) {   // one release fence for all of them
+                const int n = words2 ? 3 : 2;
+                for (int i = 0; i < n; ++i)
+                    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&sm.xmbar[i])), "r"(1u) : "memory");
+                asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
             }
             __syncwarp();
             if (threadIdx.x == 0) {
                 mbar_expect_tx(smem_u32(&sm.xmbar[0]), (uint32_t)(R * 4 * words0));
                 if (words1) mbar_expect_tx(smem_u32(&sm.xmbar[1]), (uint32_t)(R * 4 * words1));
+                if (words2) mbar_expect_tx(smem_u32(&sm.xmbar[2]), (uint32_t)(R * 4 * words2));   // only long-run groups complete it
             }
         }
         cluster_arrive();
@@ -237,6 +240,16 @@ template <int R>
 __device__ __forceinline__ void group_sync(FastSmem& sm, int round) {
     if (R == 1) __syncwarp();
     else if (R <= kW) __syncthreads();
+    else mbar_wait(smem_u32(&sm.xmbar[round]), 0);
+}
+
+// Synchronisation of a round that only SOME groups of a CTA run (the long-run exchange): groups smaller than a CTA
+// use a named barrier of their own (ids 1 .. 8, R * 32 threads) instead of __syncthreads.
+template <int R>
+__device__ __forceinline__ void group_sync_own(FastSmem& sm, int round, int warp) {
+    if (R == 1) __syncwarp();
+    else if (R < kW) asm volatile("bar.sync %0, %1;" ::"r"(1 + warp / R), "r"(R * 32) : "memory");
+    else if (R == kW) __syncthreads();
     else mbar_wait(smem_u32(&sm.xmbar[round]), 0);
 }
 
@@ -357,6 +370,188 @@ __device__ __forceinline__ void flush_region(uint32_t sbase, uint8_t* gout, int 
 }
 
 // ===================================================================================
+// compress: groups with long runs
+// ===================================================================================
+// A lane chunk without any run boundary (9+ equal deltas: constant stretches, zero tails of partially filled blocks)
+// takes its group off the 7-or-8-pairs-per-lane path.  Everything such a group needs follows from one quantity per
+// chunk: nb, the position of the last NATURAL head (delta[p] != delta[p-1]) before the chunk.
+//   * forced heads (the 255 cap, cache_engine.cpp:223): positions nb + 255 k that are not natural heads; a chunk of 8
+//     holds at most one, and only before its first natural head;
+//   * a head h closes a run that started at the previous emitted head nb + 255 * floor((h - 1 - nb) / 255).
+// nb is an exclusive max-scan of head positions: warp shuffles inside an iteration, a warp-uniform carry across
+// iterations, and across regions the exchange of (first, last) natural head per region.  A region counts its natural
+// and "interior" forced heads (those after its first natural head) itself; the forced heads in the stretch before the
+// first natural head of a region depend on lower regions and are derived by every region for all lower regions from
+// the exchanged words (long_reduce).  The kernel reaches all of this through two calls that are deliberately NOT
+// inlined (long_region_interior, long_path): inlined, the long-run code costs the common path 5 %.
+__device__ __forceinline__ uint32_t head_mask8(uint32_t nz0, uint32_t nz1) {   // bit j = position j of the chunk starts a run
+    const uint32_t lo = (((nz0 >> 7) & 0x01010101u) * 0x01020408u) >> 24;
+    const uint32_t hi = (((nz1 >> 7) & 0x01010101u) * 0x01020408u) >> 24;
+    return (lo & 0xfu) | ((hi & 0xfu) << 4);
+}
+// inclusive max-scan over the lanes (values >= -1)
+__device__ __forceinline__ int warp_scan_max(int v, int lane) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(kFull, v, o);
+        if (lane >= o) v = max(v, t);
+    }
+    return v;
+}
+// the forced head of a chunk [c, c + lead_len) whose last natural head before it is nb (nb < c): position or -1
+__device__ __forceinline__ int forced_head_in(int c, int lead_len, int nb) {
+    if (nb < 0 || lead_len <= 0) return -1;
+    const int r = (c - nb) % 255;
+    const int pf = r == 0 ? c : c + 255 - r;
+    return pf < c + lead_len ? pf : -1;
+}
+
+// Second look at a region that has a chunk without a head (phase 2a parked {dsh0, dsh1, nz0, nz1} per lane and
+// iteration): counts the interior forced heads and finds the first / last natural head (positions relative to the
+// region; first = 2048 and last = -1 when there is none).
+__device__ __forceinline__ void long_region_scan(const uint8_t* reg, int lane, uint32_t& interior_forced, int& reg_first,
+                                                 int& reg_last) {
+    interior_forced = 0;
+    reg_first = 2048;
+    reg_last = -1;
+    for (int k = 0; k < kIters; ++k) {
+        const uint4 st = lds128(reg + k * 512 + lane * 16);
+        const uint32_t m = head_mask8(st.z, st.w);
+        const int c = k * 256 + lane * 8;
+        const int own_last = m ? c + (31 - __clz((int)m)) : -1;
+        const int incl = warp_scan_max(own_last, lane);
+        const int excl = __shfl_up_sync(kFull, incl, 1);
+        const int nb = lane == 0 ? reg_last : max(reg_last, excl);
+        const int lead_len = m ? __ffs((int)m) - 1 : 8;
+        const bool forced = forced_head_in(c, lead_len, nb) >= 0;
+        interior_forced += (uint32_t)__popc(__ballot_sync(kFull, forced));
+        const int fpos = m ? c + lead_len : 2048;
+        reg_first = min(reg_first, __reduce_min_sync(kFull, fpos));
+        reg_last = max(reg_last, __shfl_sync(kFull, incl, 31));
+    }
+}
+
+// the same for the kernel body: results by value (interior forced heads), no locals whose address escapes
+__device__ __noinline__ uint32_t long_region_interior(const uint8_t* reg, int lane) {
+    uint32_t interior;
+    int f, l;
+    long_region_scan(reg, lane, interior, f, l);
+    return interior;
+}
+
+// Round-2 reduce of a group with long runs.  A: interior head count (low 20 bits) per region, B: first | (last + 1) << 12.
+// Gives the number of pairs emitted by lower regions and nb_in, the group position of the last natural head before
+// this region (-1 for region 0).
+template <int R>
+__device__ __forceinline__ void long_reduce(const uint32_t* A, const uint32_t* B, int warp, int lane, int ridx,
+                                            uint32_t& h_before, int& nb_in) {
+    const int base = R <= kW ? (warp / R) * R : 0;
+    int carry = -1;          // last natural head over the regions of earlier blocks of 32
+    uint32_t before = 0;
+    int mine = -1;
+#pragma unroll
+    for (int i = 0; i < (R + 31) / 32; ++i) {
+        const int j = i * 32 + lane;
+        const bool valid = j < R;
+        const uint32_t a = valid ? (A[base + j] & 0xfffffu) : 0u;
+        const uint32_t b = valid ? B[base + j] : 2048u;
+        const int first = (int)(b & 0xfffu), lastp1 = (int)((b >> 12) & 0xfffu);
+        const int lastg = lastp1 ? j * kRegion + lastp1 - 1 : -1;
+        const int incl = warp_scan_max(lastg, lane);
+        const int excl = __shfl_up_sync(kFull, incl, 1);
+        const int nb = lane == 0 ? carry : max(carry, excl);
+        uint32_t lead = 0;
+        if (valid && j > 0 && nb >= 0) {
+            const int a0 = j * kRegion, bnd = a0 + min(first, kRegion);
+            lead = (uint32_t)((bnd - 1 - nb) / 255 - (a0 - 1 - nb) / 255);
+        }
+        if (valid && j < ridx) before += a + lead;
+        if (valid && j == ridx) mine = nb;
+        carry = max(carry, __shfl_sync(kFull, incl, 31));
+    }
+    h_before = __reduce_add_sync(kFull, before);
+    nb_in = (int)__reduce_max_sync(kFull, (unsigned)(mine + 1)) - 1;
+}
+
+// Phase 2b of a region of a group with long runs: every iteration through the general routine.  Returns the pair
+// index after the region; prev_end = the last emitted head before the end of the region (for the final pair).
+__device__ __forceinline__ int long_emit(const uint8_t* reg, uint32_t sbase, int lane, int rstart, int pidx, int nb_in,
+                                         int& prev_end) {
+    int ln = nb_in;   // last natural head before the current iteration (group position)
+    int prev31 = 0;
+    for (int k = 0; k < kIters; ++k) {
+        const uint4 st = lds128(reg + k * 512 + lane * 16);
+        __syncwarp();   // every lane has read its slot before any pair of this iteration lands on it
+        const uint32_t m = head_mask8(st.z, st.w);
+        const int c = rstart + k * 256 + lane * 8;
+        const int own_last = m ? c + (31 - __clz((int)m)) : -1;
+        const int incl = warp_scan_max(own_last, lane);
+        const int excl = __shfl_up_sync(kFull, incl, 1);
+        const int nb = lane == 0 ? ln : max(ln, excl);
+        const int lead_len = m ? __ffs((int)m) - 1 : 8;
+        const int pf = forced_head_in(c, lead_len, nb);
+        const int n = __popc(m) + (pf >= 0 ? 1 : 0);
+        const int inc = (int)warp_scan_inclusive((uint32_t)n);
+        int idx = pidx + inc - n;
+        int prev = nb >= 0 ? nb + 255 * ((c - 1 - nb) / 255) : 0;   // previous emitted head
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const uint32_t v = (j < 4 ? st.x >> (8 * j) : st.y >> (8 * (j - 4))) & 0xffu;   // delta[c + j - 1]
+            const int p = c + j;
+            if (((m >> j) & 1u) || p == pf) {
+                sts16(sbase + 2u * (uint32_t)idx, v | ((uint32_t)((p - prev) & 0xff) << 8));
+                ++idx;
+                prev = p;
+            }
+        }
+        pidx += __shfl_sync(kFull, inc, 31);
+        ln = max(ln, __shfl_sync(kFull, incl, 31));
+        prev31 = __shfl_sync(kFull, prev, 31);
+    }
+    prev_end = prev31;
+    return pidx;
+}
+
+// Phase 2b of a group with long runs, as ONE routine outside the kernel body (the common path keeps its code and
+// register allocation): a third exchange (first / last natural head per region), offsets from long_reduce, every
+// iteration through the general routine, the final pair, the flush.
+template <int R>
+__device__ __noinline__ void long_path(FastSmem& sm, uint8_t* reg, uint32_t reg_s, int warp, int lane, int ridx, bool longr,
+                                       uint32_t carry_d1, float s, uint8_t* gout, float* scale_out, uint32_t* comp_out) {
+    constexpr uint32_t G = (uint32_t)R * kRegion;
+    int reg_first, reg_last;
+    if (longr) {
+        uint32_t unused;
+        long_region_scan(reg, lane, unused, reg_first, reg_last);
+    } else {   // without a head-less chunk they sit in the first and the last lane chunk
+        const uint2 e = *reinterpret_cast<const uint2*>(reg + (lane == 31 ? (kIters - 1) * 512 + 31 * 16 : 0) + 8);
+        const uint32_t m = head_mask8(e.x, e.y);
+        reg_first = __shfl_sync(kFull, __ffs((int)m) - 1, 0);
+        reg_last = __shfl_sync(kFull, (kIters - 1) * 256 + 31 * 8 + 31 - __clz((int)m), 31);
+    }
+    group_publish<R>(sm, sm.xb, 2, warp, lane, ridx, (uint32_t)reg_first | ((uint32_t)(reg_last + 1) << 12));
+    group_sync_own<R>(sm, 2, warp);
+    uint32_t hb;
+    int nb_in;
+    long_reduce<R>(sm.xc, sm.xb, warp, lane, ridx, hb, nb_in);
+    int pl = (int)hb - 1;
+    const int pl0 = max(pl, 0);
+    const uint32_t sb = reg_s - 16u - 2u * (uint32_t)(pl0 & ~7);
+    int prev_end;
+    pl = long_emit(reg, sb, lane, ridx * kRegion, pl, nb_in, prev_end);
+    if (ridx == R - 1) {
+        if (lane == 0) {
+            sts16(sb + 2u * (uint32_t)pl, (carry_d1 >> 24) | ((uint32_t)((int)G - prev_end) << 8));   // cache_engine.cpp:235-236
+            *scale_out = s;
+            *comp_out = 2u * (uint32_t)(pl + 1);
+        }
+        ++pl;
+    }
+    __syncwarp();
+    flush_region(sb, gout, pl0, pl, lane);
+}
+
+// ===================================================================================
 // compress
 // ===================================================================================
 template <typename T, int R>
@@ -398,7 +593,7 @@ compress_fast_kernel(const T* __restrict__ in, uint32_t n_groups, uint8_t* __res
         }
     }
     __syncwarp();
-    exchange_init<R>(sm, 1, 1);
+    exchange_init<R>(sm, 1, 1, 1);
     // halo: the 16 elements in front of the region, fetched now so that the latency hides behind phase 1
     T halo_x = narrow<T>(0.0f);
     if (active && ridx > 0 && lane < 16) halo_x = __ldg(rin + lane - 16);
@@ -433,6 +628,7 @@ compress_fast_kernel(const T* __restrict__ in, uint32_t n_groups, uint8_t* __res
     //          nz0,  nz1  : bit 7 of byte j set iff position j starts a run (delta[j] != delta[j-1]) }
     uint32_t heads = 0;
     bool cplx = !fast && !zero_group;
+    bool longr = false;       // a chunk (or the halo) without any run boundary: the group takes the long-run path
     uint32_t carry_q = 0, carry_d1 = 0, halo_nz0 = 0u, halo_nz1 = 0x80000000u;
     if (active && fast) {
         if (ridx > 0) {
@@ -448,7 +644,7 @@ compress_fast_kernel(const T* __restrict__ in, uint32_t n_groups, uint8_t* __res
             halo_nz1 = ((chg & 16u) << 3) | ((chg & 32u) << 10) | ((chg & 64u) << 17) | ((chg & 128u) << 24);
             carry_q = __shfl_sync(kFull, qh, 15);
             carry_d1 = __shfl_sync(kFull, dh, 15) << 24;
-            if (chg == 0) cplx = true;   // a run of 9+ equal deltas reaches the region edge
+            if (chg == 0) longr = true;   // a run of 9+ equal deltas reaches the region edge
         }
         const int src_lane = (lane + 31) & 31;
         uint32_t half_k = HalfConst<T>::k;
@@ -484,7 +680,7 @@ compress_fast_kernel(const T* __restrict__ in, uint32_t n_groups, uint8_t* __res
             const uint32_t nz1 = (((x1 & 0x7f7f7f7fu) + 0x7f7f7f7fu) | x1) & 0x80808080u;
             if (ridx == 0 && k == 0 && lane == 0) nz0 |= 0x80u;   // position 0 always starts a run
             const int nh = __popc(nz0) + __popc(nz1);
-            cplx |= (nh == 0);                                    // a run of 9+ equal deltas: generic kernel
+            longr |= (nh == 0);                                   // a run of 9+ equal deltas: long-run path
             heads += nh;
             *reinterpret_cast<uint4*>(slot) = make_uint4(dsh0, dsh1, nz0, nz1);
         }
@@ -492,13 +688,17 @@ compress_fast_kernel(const T* __restrict__ in, uint32_t n_groups, uint8_t* __res
         carry_d1 = __shfl_sync(kFull, carry_d1, 0);
         heads = __reduce_add_sync(kFull, heads);
     }
-    cplx = __any_sync(kFull, cplx);
-    // one word per region: head count (<= 2048) in the low 20 bits, "needs the generic kernel" above
-    group_publish<R>(sm, sm.xc, 1, warp, lane, ridx, active ? (heads | (cplx ? (1u << 20) : 0u)) : 0u);
+    longr = __any_sync(kFull, longr);
+    if (longr && active && fast) heads += long_region_interior(reg, lane);   // forced heads behind the region's first natural head
+    // one word per region: head count (natural + interior forced, <= 2056) in the low 20 bits, "has long runs" counted
+    // above.  "Needs the generic kernel" (a scale outside the fast quantiser's domain) follows from the group max,
+    // which every region already has: no exchange needed.
+    group_publish<R>(sm, sm.xc, 1, warp, lane, ridx, active ? (heads | (longr ? (1u << 20) : 0u)) : 0u);
     group_sync<R>(sm, 1);
     uint32_t h_before, h_total;
     group_reduce<R>(sm.xc, warp, lane, ridx, h_before, h_total, t0);
-    const bool any_cplx = (h_total >> 20) != 0;
+    const bool any_cplx = cplx;
+    const bool any_long = (h_total >> 20) != 0;
     h_before &= 0xfffffu;
     if (!active) return;
     if (ridx == 0 && lane == 0) {
@@ -519,10 +719,15 @@ compress_fast_kernel(const T* __restrict__ in, uint32_t n_groups, uint8_t* __res
         return;
     }
 
+    uint8_t* gout = payload + (size_t)g * slot_bytes;
+    if (any_long) {   // groups with long runs: everything else happens in long_path (not inlined)
+        long_path<R>(sm, reg, reg_s, warp, lane, ridx, longr, carry_d1, s, gout, scales + g, comp_bytes + g);
+        return;
+    }
+
     // ---- 2b. emit: a head at position p closes the previous run -> pair (delta[p-1], p - previous head).
     //          Pairs are staged IN PLACE (behind the slots still to be read) at the alignment they
     //          will have in global memory, then the region goes out with one bulk-TMA store.
-    uint8_t* gout = payload + (size_t)g * slot_bytes;
     // Region 0 starts at pair index -1: the head at position 0 closes nothing, so its "pair" is
     // staged in the pad in front of the tile and never flushed.
     int pidx = (int)h_before - 1;
