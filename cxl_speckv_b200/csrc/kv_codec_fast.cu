@@ -524,7 +524,9 @@ __device__ __noinline__ void long_path(FastSmem& sm, uint8_t* reg, uint32_t reg_
         uint32_t unused;
         long_region_scan(reg, lane, unused, reg_first, reg_last);
     } else {   // without a head-less chunk they sit in the first and the last lane chunk
-        const uint2 e = *reinterpret_cast<const uint2*>(reg + (lane == 31 ? (kIters - 1) * 512 + 31 * 16 : 0) + 8);
+        uint2 e = make_uint2(0u, 0u);   // lane 0 and lane 31 read the flags they parked themselves
+        if (lane == 0) e = *reinterpret_cast<const uint2*>(reg + 8);
+        else if (lane == 31) e = *reinterpret_cast<const uint2*>(reg + (kIters - 1) * 512 + 31 * 16 + 8);
         const uint32_t m = head_mask8(e.x, e.y);
         reg_first = __shfl_sync(kFull, __ffs((int)m) - 1, 0);
         reg_last = __shfl_sync(kFull, (kIters - 1) * 256 + 31 * 8 + 31 - __clz((int)m), 31);
