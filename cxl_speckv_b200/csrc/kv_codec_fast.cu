@@ -886,7 +886,7 @@ decompress_fast_kernel(const uint8_t* __restrict__ payload, size_t slot_bytes, c
     // bits for almost every scale.  "Almost" is settled exactly: there are only 256 codes, so the regions of a group
     // check them all against the reference form for this group's scale (256 / R codes per region) and the group
     // takes the short form only if every code agrees -- the output stays bit-identical either way (decompress +3 %;
-    // ~95 % of the scales qualify).
+    // more than 99 % of the scales qualify).
     constexpr bool kTryShort = R >= 8;   // at most one code per lane to check; smaller groups keep the reference form
     const float kq = __fdiv_rn(s, 127.0f);
     bool deq_differs = !kTryShort;
