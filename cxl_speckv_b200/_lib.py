@@ -40,6 +40,25 @@ class PolicyStats(C.Structure):
                [(n, C.c_uint64) for n in ("l1_pages", "l2_pages", "l3_pages")]
 
 
+class EngineStats(C.Structure):
+    _fields_ = [("total_compressions", C.c_uint64), ("total_decompressions", C.c_uint64),
+                ("avg_compression_ratio", C.c_double), ("avg_compression_latency_ns", C.c_double),
+                ("avg_decompression_latency_ns", C.c_double), ("throughput_gbps", C.c_double),
+                ("compress_calls_timed", C.c_uint64), ("decompress_calls_timed", C.c_uint64),
+                ("compress_ns_per_group", C.c_double), ("decompress_ns_per_group", C.c_double)]
+
+
+class PrefetchStats(C.Structure):
+    _fields_ = [("total_prefetches", C.c_uint64), ("successful_prefetches", C.c_uint64), ("mispredictions", C.c_uint64),
+                ("hit_rate", C.c_double), ("precision", C.c_double), ("avg_prediction_latency_us", C.c_double)]
+
+
+class PrefetchRequest(C.Structure):
+    """PrefetchRequest, src/prefetcher/speculative_prefetcher.h:23-29 (32 bytes)."""
+    _fields_ = [("virtual_addr", C.c_uint64), ("layer_id", C.c_uint32), ("predicted_token_id", C.c_uint32),
+                ("confidence", C.c_float), ("reserved", C.c_uint32), ("timestamp", C.c_uint64)]
+
+
 def lib_path() -> str:
     return os.environ.get("SPECKV_LIB", os.path.join(PKG, "libcxlspeckv.so"))
 
@@ -147,6 +166,19 @@ def lib() -> C.CDLL:
     L.speckv_ext_policy_get_tiers.argtypes = [vp, vp, sz, vp]; L.speckv_ext_policy_get_tiers.restype = C.c_int
     L.speckv_ext_policy_lru_order.argtypes = [vp, vp, sz, C.POINTER(sz)]; L.speckv_ext_policy_lru_order.restype = C.c_int
     L.speckv_ext_policy_get_stats.argtypes = [vp, C.POINTER(PolicyStats)]; L.speckv_ext_policy_get_stats.restype = C.c_int
+    L.speckv_ext_decompress_routed.argtypes = [vp, sz, vp, vp, vp, vp, sz, sz, C.c_int, vp, vp, C.c_int, vp]
+    L.speckv_ext_decompress_routed.restype = C.c_int
+    L.speckv_ext_route_requests.argtypes = [vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, vp, vp, vp, vp]
+    L.speckv_ext_route_requests.restype = C.c_int
+    L.speckv_ext_prefetch_emit.argtypes = [vp, C.c_uint32, C.c_uint32, vp, C.c_uint32, C.c_uint32, vp, sz, C.c_uint64,
+                                           C.c_uint64, vp, vp, vp, vp]
+    L.speckv_ext_prefetch_emit.restype = C.c_int
+    L.speckv_ext_prefetch_handle_misprediction.argtypes = [C.c_uint32, u32p, sz, C.POINTER(C.c_int)]
+    L.speckv_ext_prefetch_handle_misprediction.restype = C.c_int
+    L.speckv_ext_prefetch_stats.argtypes = [C.POINTER(PrefetchStats), C.c_int]; L.speckv_ext_prefetch_stats.restype = C.c_int
+    L.speckv_ext_prefetch_outstanding.argtypes = [u64p, sz, C.POINTER(C.c_uint8), C.POINTER(PrefetchRequest), u32p, vp]
+    L.speckv_ext_prefetch_outstanding.restype = C.c_int
+    L.speckv_ext_engine_stats.argtypes = [C.POINTER(EngineStats), C.c_int]; L.speckv_ext_engine_stats.restype = None
     L.speckv_ext_get_stats.argtypes = [C.POINTER(Stats)]; L.speckv_ext_get_stats.restype = None
     L.speckv_ext_reset_stats.argtypes = []; L.speckv_ext_reset_stats.restype = None
     _LIB = L

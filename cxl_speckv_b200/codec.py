@@ -94,6 +94,27 @@ def decompress_indexed(c: CompressedKV, block_index: torch.Tensor, out: Optional
     return out
 
 
+def decompress_routed(c: CompressedKV, block_index: torch.Tensor, count: torch.Tensor, out: torch.Tensor,
+                      dtype: Optional[torch.dtype] = None) -> torch.Tensor:
+    """decompress_indexed with the request count on the device (count: int32 [1], from prefetch.route): out has
+    room for block_index.numel() blocks, the first count[0] of them are written.  No host synchronisation."""
+    dtype = dtype or c.dtype
+    cap = min(block_index.numel(), out.shape[0])
+    with torch.cuda.device(c.payload.device):
+        st = lib().speckv_ext_decompress_routed(c.payload.data_ptr(), c.payload.shape[1], c.scales.data_ptr(),
+                                                c.comp_bytes.data_ptr(), block_index.data_ptr(), count.data_ptr(), cap,
+                                                c.group_elems, _DTYPES[dtype], out.data_ptr(), None, c.scheme, _stream())
+    check(st, "speckv_ext_decompress_routed")
+    return out
+
+
+def engine_stats(wait: bool = True) -> dict:
+    """FPGACacheEngine::get_statistics (EngineStatistics, cache_engine.h:65-72)."""
+    s = _lib.EngineStats()
+    lib().speckv_ext_engine_stats(C.byref(s), int(wait))
+    return {k: getattr(s, k) for k, _ in s._fields_}
+
+
 def compress_gather(cache: torch.Tensor, block_table: torch.Tensor, scheme: int = COMP_INT8_DELTA_RLE,
                     out: Optional[CompressedKV] = None) -> CompressedKV:
     """Compress the blocks of a paged KV cache named by block_table, reading them where they lie.

@@ -106,14 +106,44 @@ template <> __device__ __forceinline__ float add_rz_mixed<__nv_bfloat16>(uint16_
     asm("add.rz.f32.bf16 %0, %1, %2;" : "=f"(a) : "h"(h), "f"(t));
     return a;
 }
+// Packed fp32 pairs (sm_100: mul / fma .f32x2, SASS FMUL2 / FFMA2): two IEEE operations per instruction, each half
+// rounded exactly like the scalar form -- the same arithmetic in half the issue slots (measured: FMUL2 sustains the
+// fp32 lane rate of FMUL).  ptxas treats mul.rn.f32x2 followed by add.rn.f32x2 as contractable even under
+// --fmad=false (profiles/micro/f32x2_probe.cu), so the packed forms are used only where no such pair is adjacent:
+// here the chain is mul -> fma -> mul -> (mixed-precision add, round toward zero).
+typedef unsigned long long f32x2_t;
+__device__ __forceinline__ f32x2_t pack_f32x2(float lo, float hi) {
+    f32x2_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack_f32x2(f32x2_t v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2_t mul_f32x2(f32x2_t a, f32x2_t b) {
+    f32x2_t r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f32x2_t fma_f32x2(f32x2_t a, f32x2_t b, f32x2_t c) {
+    f32x2_t r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+
 // w = two packed elements, x0 / x1 = the same elements widened; half_k = HalfConst<T>::k held in a register
 template <typename T>
 __device__ __forceinline__ void quantize_fast_pair_i(uint32_t w, float x0, float x1, float rh, float rl, uint32_t half_k,
                                                      uint32_t& q0, uint32_t& q1) {
     uint32_t hs;
     asm("lop3.b32 %0, %1, 0x80008000, %2, 0xEA;" : "=r"(hs) : "r"(w), "r"(half_k));   // (w & signs) | halves
+#ifdef SPECKV_SCALAR_QUANT
     const float t0 = __fmul_rn(__fmaf_rn(x0, rh, __fmul_rn(x0, rl)), 127.0f);
     const float t1 = __fmul_rn(__fmaf_rn(x1, rh, __fmul_rn(x1, rl)), 127.0f);
+#else
+    const f32x2_t x = pack_f32x2(x0, x1);
+    const f32x2_t y = fma_f32x2(x, pack_f32x2(rh, rh), mul_f32x2(x, pack_f32x2(rl, rl)));
+    float t0, t1;
+    unpack_f32x2(mul_f32x2(y, pack_f32x2(127.0f, 127.0f)), t0, t1);
+#endif
     q0 = (uint32_t)__float2int_rz(add_rz_mixed<T>((uint16_t)(hs & 0xffffu), t0));
     q1 = (uint32_t)__float2int_rz(add_rz_mixed<T>((uint16_t)(hs >> 16), t1));
 }

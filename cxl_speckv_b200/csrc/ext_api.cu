@@ -99,6 +99,141 @@ void count_launch(unsigned n) { g_kernel_launches += n; }
 
 static size_t elem_bytes(int dtype) { return dtype == DT_F32 ? 4 : 2; }
 
+// Per-stream scratch that stays allocated across calls (the codec's per-group flag words): a call inside a
+// serving loop then issues no allocation at all, and the launches can be captured into a CUDA graph.  The
+// buffer of a (device, stream) pair only grows; growing is a plain cudaMalloc, which is refused while the
+// stream is being captured -- run the call once before capturing it.
+struct ScratchEntry {
+    int device;
+    cudaStream_t stream;
+    void* ptr;
+    size_t cap;
+};
+static std::mutex g_scratch_mu;
+static std::vector<ScratchEntry> g_scratch;
+
+cudaError_t scratch_persistent(void** p, size_t bytes, cudaStream_t st) {
+    if (device_count() <= 0) return cudaErrorNoDevice;
+    int d = 0;
+    cudaError_t e = cudaGetDevice(&d);
+    if (e != cudaSuccess) return e;
+    std::lock_guard<std::mutex> lk(g_scratch_mu);
+    ScratchEntry* hit = nullptr;
+    for (ScratchEntry& s : g_scratch)
+        if (s.device == d && s.stream == st) hit = &s;
+    if (hit && hit->cap >= bytes) {
+        *p = hit->ptr;
+        return cudaSuccess;
+    }
+    size_t cap = 4096;
+    while (cap < bytes) cap *= 2;
+    void* np = nullptr;
+    if ((e = cudaMalloc(&np, cap)) != cudaSuccess) return e;
+    if (hit) {
+        cudaFree(hit->ptr);   // synchronises: earlier launches on the stream that use the old buffer have finished
+        hit->ptr = np;
+        hit->cap = cap;
+    } else {
+        if (g_scratch.size() >= 256) {   // streams come and go: recycle the oldest entry
+            cudaFree(g_scratch.front().ptr);
+            g_scratch.erase(g_scratch.begin());
+        }
+        g_scratch.push_back(ScratchEntry{d, st, np, cap});
+    }
+    *p = np;
+    return cudaSuccess;
+}
+
+// ---- engine latency statistics (EngineStatistics::avg_*_latency_ns, cache_engine.cpp:65-79,103-112) ----
+// The reference brackets every compress() / decompress() call with a steady_clock pair and keeps a running mean.
+// The calls here are asynchronous, so the bracket is a pair of CUDA events on the caller's stream; finished
+// pairs are harvested lazily (no synchronisation on the call path).  Calls made while the stream is being
+// captured into a graph are not timed (events recorded in a capture cannot be queried).
+struct LatencyPair {
+    cudaEvent_t a = nullptr, b = nullptr;
+    int device = -1;
+    bool decompress = false, busy = false;
+    uint64_t groups = 0, bytes = 0;
+};
+static std::mutex g_lat_mu;
+static LatencyPair g_lat[64];
+static double g_lat_ns[2] = {0.0, 0.0}, g_lat_mean_ns[2] = {0.0, 0.0};   // [0] compress, [1] decompress
+static uint64_t g_lat_calls[2] = {0, 0}, g_lat_groups[2] = {0, 0}, g_lat_bytes[2] = {0, 0};
+static double g_ratio_mean = 0.0;      // running mean of original_size / compressed_size over groups
+static uint64_t g_ratio_groups = 0;
+static const bool g_lat_enabled = [] {
+    const char* e = std::getenv("SPECKV_LATENCY_STATS");
+    return !(e && e[0] == '0');
+}();
+
+static void latency_harvest_locked(bool wait) {
+    for (LatencyPair& p : g_lat) {
+        if (!p.busy) continue;
+        cudaError_t q = wait ? cudaEventSynchronize(p.b) : cudaEventQuery(p.b);
+        if (q == cudaErrorNotReady) continue;
+        float ms = 0.0f;
+        if (q == cudaSuccess && cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess) {
+            const int k = p.decompress ? 1 : 0;
+            g_lat_ns[k] += (double)ms * 1e6;
+            ++g_lat_calls[k];
+            g_lat_groups[k] += p.groups;
+            g_lat_bytes[k] += p.bytes;
+            // the reference's update rule, one step per call (cache_engine.cpp:76-79)
+            g_lat_mean_ns[k] = (g_lat_mean_ns[k] * (double)(g_lat_calls[k] - 1) + (double)ms * 1e6) / (double)g_lat_calls[k];
+        } else {
+            cudaGetLastError();
+        }
+        p.busy = false;
+    }
+}
+
+class LatencyScope {
+public:
+    LatencyScope(bool decompress, cudaStream_t st, uint64_t groups = 0, uint64_t bytes = 0) : st_(st) {
+        if (!g_lat_enabled) return;
+        cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+        if (cudaStreamIsCapturing(st, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) {
+            cudaGetLastError();
+            return;
+        }
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess) return;
+        std::lock_guard<std::mutex> lk(g_lat_mu);
+        for (int pass = 0; pass < 2 && !p_; ++pass) {
+            for (LatencyPair& p : g_lat)
+                if (!p.busy && (p.device == dev || p.device < 0)) {
+                    p_ = &p;
+                    break;
+                }
+            if (!p_) latency_harvest_locked(false);
+        }
+        if (!p_) return;   // every pair still in flight: this call goes untimed
+        if (!p_->a) {
+            if (cudaEventCreate(&p_->a) != cudaSuccess || cudaEventCreate(&p_->b) != cudaSuccess) {
+                cudaGetLastError();
+                p_ = nullptr;
+                return;
+            }
+            p_->device = dev;
+        }
+        p_->busy = true;
+        p_->decompress = decompress;
+        p_->groups = groups;
+        p_->bytes = bytes;
+        cudaEventRecord(p_->a, st_);
+    }
+    ~LatencyScope() {
+        if (p_) cudaEventRecord(p_->b, st_);
+    }
+    void set_groups(uint64_t g) {
+        if (p_) p_->groups = g;
+    }
+
+private:
+    cudaStream_t st_;
+    LatencyPair* p_ = nullptr;
+};
+
 static bool valid_common(int dtype, size_t group_elems, size_t n_groups, size_t slot_bytes, int scheme) {
     if (dtype < 0 || dtype > 2 || scheme < 0 || scheme > 2) return false;
     if (group_elems >= (1ull << 31) || n_groups >= (1ull << 32)) return false;
@@ -233,6 +368,11 @@ speckv_status_t speckv_ext_ratio_stats(const uint32_t* d_comp_bytes, size_t n_gr
     cudaFreeAsync(d_acc, st);
     *out_total_comp_bytes = h[0];
     *out_mean_ratio = h[1] / (double)n_groups;
+    if (e == cudaSuccess) {   // EngineStatistics::avg_compression_ratio: running mean over every group reported here
+        std::lock_guard<std::mutex> lk(g_lat_mu);
+        g_ratio_mean = (g_ratio_mean * (double)g_ratio_groups + h[1]) / (double)(g_ratio_groups + n_groups);
+        g_ratio_groups += n_groups;
+    }
     return status_of(e);
 }
 
@@ -245,119 +385,109 @@ size_t speckv_ext_slot_bytes(size_t group_elems, speckv_comp_scheme_t scheme) {
     return (b + 15) / 16 * 16;
 }
 
-speckv_status_t speckv_ext_compress(const void* d_in, speckv_dtype_t dtype, size_t group_elems, size_t n_groups,
-                                    void* d_payload, size_t slot_bytes, float* d_scales, uint32_t* d_comp_bytes,
-                                    speckv_comp_scheme_t scheme, void* cuda_stream) {
+// ---- device-buffer codec entry points: one marshalling routine for all of them ----------------------
+}  // extern "C"
+
+namespace speckv {
+// validation shared by every codec call + the fields every call fills the same way
+static speckv_status_t codec_args(CodecArgs& a, int dtype, size_t group_elems, size_t n_groups, const void* d_payload,
+                                  size_t slot_bytes, const float* d_scales, const uint32_t* d_comp_bytes, int scheme,
+                                  const void* d_elems) {
     if (device_count() <= 0) return SPECKV_ERR_DRIVER;
     if (!valid_common(dtype, group_elems, n_groups, slot_bytes, scheme)) return SPECKV_ERR_INVAL;
     if (n_groups == 0) return SPECKV_OK;
-    if (!d_payload || !d_scales || !d_comp_bytes || (!d_in && group_elems)) return SPECKV_ERR_INVAL;
+    if (!d_payload || !d_scales || !d_comp_bytes || (!d_elems && group_elems)) return SPECKV_ERR_INVAL;
     if (reinterpret_cast<uintptr_t>(d_payload) & 15) return SPECKV_ERR_INVAL;
-    CodecArgs a;
-    a.in = d_in;
-    a.payload = d_payload;
-    a.scales = d_scales;
-    a.comp_bytes = d_comp_bytes;
+    a.payload = const_cast<void*>(d_payload);
+    a.scales = const_cast<float*>(d_scales);
+    a.comp_bytes = const_cast<uint32_t*>(d_comp_bytes);
     a.slot_bytes = slot_bytes;
     a.group_elems = (uint32_t)group_elems;
     a.n_groups = (uint32_t)n_groups;
     a.dtype = dtype;
     a.scheme = scheme;
     a.sm_count = current_sm_count();
-    cudaError_t e = launch_compress(a, static_cast<cudaStream_t>(cuda_stream));
+    return SPECKV_OK;
+}
+static speckv_status_t codec_run(bool decompress, const CodecArgs& a, void* cuda_stream) {
+    if (a.n_groups == 0) return SPECKV_OK;
+    cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+    LatencyScope lat(decompress, st, a.n_groups, (uint64_t)a.n_groups * a.group_elems * elem_bytes(a.dtype));
+    const cudaError_t e = decompress ? launch_decompress(a, st) : launch_compress(a, st);
     if (e == cudaSuccess) {
-        g_n_comp += n_groups;
-        g_b_comp += (uint64_t)n_groups * group_elems * elem_bytes(dtype);
+        (decompress ? g_n_decomp : g_n_comp) += a.n_groups;
+        (decompress ? g_b_decomp : g_b_comp) += (uint64_t)a.n_groups * a.group_elems * elem_bytes(a.dtype);
     }
     return status_of(e);
+}
+}  // namespace speckv
+
+extern "C" {
+
+speckv_status_t speckv_ext_compress(const void* d_in, speckv_dtype_t dtype, size_t group_elems, size_t n_groups,
+                                    void* d_payload, size_t slot_bytes, float* d_scales, uint32_t* d_comp_bytes,
+                                    speckv_comp_scheme_t scheme, void* cuda_stream) {
+    CodecArgs a;
+    const speckv_status_t rc = codec_args(a, dtype, group_elems, n_groups, d_payload, slot_bytes, d_scales, d_comp_bytes, scheme, d_in);
+    if (rc != SPECKV_OK) return rc;
+    a.in = d_in;
+    return codec_run(false, a, cuda_stream);
 }
 
 speckv_status_t speckv_ext_decompress(const void* d_payload, size_t slot_bytes, const float* d_scales,
                                       const uint32_t* d_comp_bytes, size_t group_elems, size_t n_groups,
                                       speckv_dtype_t dtype, void* d_out, uint32_t* d_out_elems,
                                       speckv_comp_scheme_t scheme, void* cuda_stream) {
-    if (device_count() <= 0) return SPECKV_ERR_DRIVER;
-    if (!valid_common(dtype, group_elems, n_groups, slot_bytes, scheme)) return SPECKV_ERR_INVAL;
-    if (n_groups == 0) return SPECKV_OK;
-    if (!d_payload || !d_scales || !d_comp_bytes || (!d_out && group_elems)) return SPECKV_ERR_INVAL;
-    if (reinterpret_cast<uintptr_t>(d_payload) & 15) return SPECKV_ERR_INVAL;
     CodecArgs a;
+    const speckv_status_t rc = codec_args(a, dtype, group_elems, n_groups, d_payload, slot_bytes, d_scales, d_comp_bytes, scheme, d_out);
+    if (rc != SPECKV_OK) return rc;
     a.out = d_out;
-    a.payload = const_cast<void*>(d_payload);
-    a.scales = const_cast<float*>(d_scales);
-    a.comp_bytes = const_cast<uint32_t*>(d_comp_bytes);
     a.out_elems = d_out_elems;
-    a.slot_bytes = slot_bytes;
-    a.group_elems = (uint32_t)group_elems;
-    a.n_groups = (uint32_t)n_groups;
-    a.dtype = dtype;
-    a.scheme = scheme;
-    a.sm_count = current_sm_count();
-    cudaError_t e = launch_decompress(a, static_cast<cudaStream_t>(cuda_stream));
-    if (e == cudaSuccess) {
-        g_n_decomp += n_groups;
-        g_b_decomp += (uint64_t)n_groups * group_elems * elem_bytes(dtype);
-    }
-    return status_of(e);
+    return codec_run(true, a, cuda_stream);
 }
 
 speckv_status_t speckv_ext_decompress_indexed(const void* d_payload, size_t slot_bytes, const float* d_scales,
                                               const uint32_t* d_comp_bytes, const uint32_t* d_block_index,
                                               size_t n_requests, size_t group_elems, speckv_dtype_t dtype, void* d_out,
                                               uint32_t* d_out_elems, speckv_comp_scheme_t scheme, void* cuda_stream) {
-    if (device_count() <= 0) return SPECKV_ERR_DRIVER;
-    if (!valid_common(dtype, group_elems, n_requests, slot_bytes, scheme)) return SPECKV_ERR_INVAL;
-    if (n_requests == 0) return SPECKV_OK;
-    if (!d_payload || !d_scales || !d_comp_bytes || !d_block_index || (!d_out && group_elems)) return SPECKV_ERR_INVAL;
-    if (reinterpret_cast<uintptr_t>(d_payload) & 15) return SPECKV_ERR_INVAL;
     CodecArgs a;
+    const speckv_status_t rc = codec_args(a, dtype, group_elems, n_requests, d_payload, slot_bytes, d_scales, d_comp_bytes, scheme, d_out);
+    if (rc != SPECKV_OK) return rc;
+    if (n_requests && !d_block_index) return SPECKV_ERR_INVAL;
     a.out = d_out;
-    a.payload = const_cast<void*>(d_payload);
-    a.scales = const_cast<float*>(d_scales);
-    a.comp_bytes = const_cast<uint32_t*>(d_comp_bytes);
     a.out_elems = d_out_elems;
     a.src_index = d_block_index;
-    a.slot_bytes = slot_bytes;
-    a.group_elems = (uint32_t)group_elems;
-    a.n_groups = (uint32_t)n_requests;
-    a.dtype = dtype;
-    a.scheme = scheme;
-    a.sm_count = current_sm_count();
-    cudaError_t e = launch_decompress(a, static_cast<cudaStream_t>(cuda_stream));
-    if (e == cudaSuccess) {
-        g_n_decomp += n_requests;
-        g_b_decomp += (uint64_t)n_requests * group_elems * elem_bytes(dtype);
-    }
-    return status_of(e);
+    return codec_run(true, a, cuda_stream);
+}
+
+speckv_status_t speckv_ext_decompress_routed(const void* d_payload, size_t slot_bytes, const float* d_scales,
+                                             const uint32_t* d_comp_bytes, const uint32_t* d_block_index,
+                                             const uint32_t* d_n_requests, size_t max_requests, size_t group_elems,
+                                             speckv_dtype_t dtype, void* d_out, uint32_t* d_out_elems,
+                                             speckv_comp_scheme_t scheme, void* cuda_stream) {
+    CodecArgs a;
+    const speckv_status_t rc = codec_args(a, dtype, group_elems, max_requests, d_payload, slot_bytes, d_scales, d_comp_bytes, scheme, d_out);
+    if (rc != SPECKV_OK) return rc;
+    if (max_requests && (!d_block_index || !d_n_requests)) return SPECKV_ERR_INVAL;
+    a.out = d_out;
+    a.out_elems = d_out_elems;
+    a.src_index = d_block_index;
+    a.n_groups_dev = d_n_requests;
+    return codec_run(true, a, cuda_stream);
 }
 
 speckv_status_t speckv_ext_compress_gather(const void* d_cache, const uint32_t* d_block_table, speckv_dtype_t dtype,
                                            size_t group_elems, size_t n_groups, void* d_payload, size_t slot_bytes,
                                            float* d_scales, uint32_t* d_comp_bytes, speckv_comp_scheme_t scheme,
                                            void* cuda_stream) {
-    if (device_count() <= 0) return SPECKV_ERR_DRIVER;
-    if (!valid_common(dtype, group_elems, n_groups, slot_bytes, scheme) || scheme == SPECKV_COMP_FP16) return SPECKV_ERR_INVAL;
-    if (n_groups == 0) return SPECKV_OK;
-    if (!d_payload || !d_scales || !d_comp_bytes || !d_block_table || (!d_cache && group_elems)) return SPECKV_ERR_INVAL;
-    if (reinterpret_cast<uintptr_t>(d_payload) & 15) return SPECKV_ERR_INVAL;
+    if (scheme == SPECKV_COMP_FP16) return device_count() <= 0 ? SPECKV_ERR_DRIVER : SPECKV_ERR_INVAL;
     CodecArgs a;
+    const speckv_status_t rc = codec_args(a, dtype, group_elems, n_groups, d_payload, slot_bytes, d_scales, d_comp_bytes, scheme, d_cache);
+    if (rc != SPECKV_OK) return rc;
+    if (n_groups && !d_block_table) return SPECKV_ERR_INVAL;
     a.in = d_cache;
     a.elem_index = d_block_table;
-    a.payload = d_payload;
-    a.scales = d_scales;
-    a.comp_bytes = d_comp_bytes;
-    a.slot_bytes = slot_bytes;
-    a.group_elems = (uint32_t)group_elems;
-    a.n_groups = (uint32_t)n_groups;
-    a.dtype = dtype;
-    a.scheme = scheme;
-    a.sm_count = current_sm_count();
-    cudaError_t e = launch_compress(a, static_cast<cudaStream_t>(cuda_stream));
-    if (e == cudaSuccess) {
-        g_n_comp += n_groups;
-        g_b_comp += (uint64_t)n_groups * group_elems * elem_bytes(dtype);
-    }
-    return status_of(e);
+    return codec_run(false, a, cuda_stream);
 }
 
 speckv_status_t speckv_ext_decompress_scatter(const void* d_payload, size_t slot_bytes, const float* d_scales,
@@ -365,31 +495,16 @@ speckv_status_t speckv_ext_decompress_scatter(const void* d_payload, size_t slot
                                               const uint32_t* d_block_table, size_t n_requests, size_t group_elems,
                                               speckv_dtype_t dtype, void* d_cache, uint32_t* d_out_elems,
                                               speckv_comp_scheme_t scheme, void* cuda_stream) {
-    if (device_count() <= 0) return SPECKV_ERR_DRIVER;
-    if (!valid_common(dtype, group_elems, n_requests, slot_bytes, scheme) || scheme == SPECKV_COMP_FP16) return SPECKV_ERR_INVAL;
-    if (n_requests == 0) return SPECKV_OK;
-    if (!d_payload || !d_scales || !d_comp_bytes || !d_block_table || (!d_cache && group_elems)) return SPECKV_ERR_INVAL;
-    if (reinterpret_cast<uintptr_t>(d_payload) & 15) return SPECKV_ERR_INVAL;
+    if (scheme == SPECKV_COMP_FP16) return device_count() <= 0 ? SPECKV_ERR_DRIVER : SPECKV_ERR_INVAL;
     CodecArgs a;
+    const speckv_status_t rc = codec_args(a, dtype, group_elems, n_requests, d_payload, slot_bytes, d_scales, d_comp_bytes, scheme, d_cache);
+    if (rc != SPECKV_OK) return rc;
+    if (n_requests && !d_block_table) return SPECKV_ERR_INVAL;
     a.out = d_cache;
     a.elem_index = d_block_table;
-    a.payload = const_cast<void*>(d_payload);
-    a.scales = const_cast<float*>(d_scales);
-    a.comp_bytes = const_cast<uint32_t*>(d_comp_bytes);
     a.out_elems = d_out_elems;
     a.src_index = d_src_index;
-    a.slot_bytes = slot_bytes;
-    a.group_elems = (uint32_t)group_elems;
-    a.n_groups = (uint32_t)n_requests;
-    a.dtype = dtype;
-    a.scheme = scheme;
-    a.sm_count = current_sm_count();
-    cudaError_t e = launch_decompress(a, static_cast<cudaStream_t>(cuda_stream));
-    if (e == cudaSuccess) {
-        g_n_decomp += n_requests;
-        g_b_decomp += (uint64_t)n_requests * group_elems * elem_bytes(dtype);
-    }
-    return status_of(e);
+    return codec_run(true, a, cuda_stream);
 }
 
 speckv_status_t speckv_ext_compress_host(const void* h_in, speckv_dtype_t dtype, size_t group_elems, size_t n_groups,
@@ -518,7 +633,37 @@ void speckv_ext_get_stats(speckv_ext_stats_t* out) {
     out->kernel_launches = g_kernel_launches.load();
 }
 
+void speckv_ext_engine_stats(speckv_engine_stats_t* out, int wait) {
+    if (!out) return;
+    std::memset(out, 0, sizeof(*out));
+    std::lock_guard<std::mutex> lk(g_lat_mu);
+    if (device_count() > 0) latency_harvest_locked(wait != 0);
+    out->total_compressions = g_n_comp.load();
+    out->total_decompressions = g_n_decomp.load();
+    out->avg_compression_ratio = g_ratio_mean;
+    out->avg_compression_latency_ns = g_lat_mean_ns[0];
+    out->avg_decompression_latency_ns = g_lat_mean_ns[1];
+    out->compress_calls_timed = g_lat_calls[0];
+    out->decompress_calls_timed = g_lat_calls[1];
+    out->compress_ns_per_group = g_lat_groups[0] ? g_lat_ns[0] / (double)g_lat_groups[0] : 0.0;
+    out->decompress_ns_per_group = g_lat_groups[1] ? g_lat_ns[1] / (double)g_lat_groups[1] : 0.0;
+    const double ns = g_lat_ns[0] + g_lat_ns[1];
+    // the reference returns a constant here (512 bit x 800 MHz, cache_engine.cpp:291-296); this is measured:
+    // uncompressed bytes through the timed calls per second of device time
+    out->throughput_gbps = ns > 0.0 ? (double)(g_lat_bytes[0] + g_lat_bytes[1]) * 8.0 / ns : 0.0;
+}
+
 void speckv_ext_reset_stats(void) {
+    {
+        std::lock_guard<std::mutex> lk(g_lat_mu);
+        if (device_count() > 0) latency_harvest_locked(false);
+        for (int k = 0; k < 2; ++k) {
+            g_lat_ns[k] = g_lat_mean_ns[k] = 0.0;
+            g_lat_calls[k] = g_lat_groups[k] = g_lat_bytes[k] = 0;
+        }
+        g_ratio_mean = 0.0;
+        g_ratio_groups = 0;
+    }
     g_n_comp = 0;
     g_n_decomp = 0;
     g_n_xlate = 0;

@@ -20,6 +20,8 @@ struct CodecArgs {
     const uint32_t* elem_index = nullptr;    // optional paged gather / scatter: group i's elements are block
                                              // elem_index[i] of the element buffer (compress reads `in` there,
                                              // decompress writes `out` there) instead of block i
+    const uint32_t* n_groups_dev = nullptr;  // decompress, optional: device word holding the number of valid requests
+                                             // (<= n_groups, which then is the capacity the grid is sized for)
     size_t slot_bytes = 0;
     uint32_t group_elems = 0;
     uint32_t n_groups = 0;

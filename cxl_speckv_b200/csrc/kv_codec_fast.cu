@@ -827,7 +827,7 @@ decompress_fast_kernel(const uint8_t* __restrict__ payload, size_t slot_bytes, c
                        const uint32_t* __restrict__ comp_bytes, uint32_t n_groups, T* __restrict__ out,
                        uint32_t* __restrict__ out_elems, uint32_t* __restrict__ needs_generic,
                        const uint32_t* __restrict__ src_index, const uint64_t* __restrict__ slot_offsets,
-                       const uint32_t* __restrict__ elem_index) {
+                       const uint32_t* __restrict__ elem_index, const uint32_t* __restrict__ n_groups_dev) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     FastSmem& sm = *reinterpret_cast<FastSmem*>(smem_raw);
     constexpr int C = R > kW ? R / kW : 1;
@@ -846,7 +846,10 @@ decompress_fast_kernel(const uint8_t* __restrict__ payload, size_t slot_bytes, c
         g = blockIdx.x * GPC + warp / R;
         ridx = warp % R;
     }
-    const bool active = g < n_groups;
+    // the request count may live on the device (prefetch requests routed by a kernel): the grid covers the
+    // capacity n_groups, groups at or above the count only clear their flag for the generic second pass
+    const bool in_grid = g < n_groups;
+    const bool active = in_grid && (!n_groups_dev || g < *n_groups_dev);
     uint8_t* reg = sm.tile[warp] + kPadBytes;
     const uint32_t reg_s = smem_u32(reg);
     const uint32_t mb = smem_u32(&sm.mbar[warp]);
@@ -1080,7 +1083,10 @@ decompress_fast_kernel(const uint8_t* __restrict__ payload, size_t slot_bytes, c
     uint32_t e_before, e_total, q_before, xb_total, t0;
     group_reduce<R>(sm.xa, warp, lane, ridx, e_before, e_total, t0);
     group_reduce<R>(sm.xb, warp, lane, ridx, q_before, xb_total, t0);
-    if (!active) return;
+    if (!active) {
+        if (in_grid && ridx == 0 && lane == 0) needs_generic[g] = 0u;
+        return;
+    }
     const bool any_cplx = ((xb_total >> 16) & 0xffu) != 0 || e_total > G;   // output longer than the group: generic kernel clips
     const bool short_deq = (xb_total >> 24) == 0;
     if (ridx == 0 && lane == 0) {
@@ -1178,7 +1184,8 @@ cudaError_t decompress_fast_t(int R, const CodecArgs& a, uint32_t* flags, cudaSt
     const uint32_t* si = a.src_index;
     const uint64_t* so = a.slot_offsets;
     const uint32_t* ei = a.elem_index;
-    void* args[] = {&pay, &sb, &sc, &cb, &n, &out, &oe, &flags, &si, &so, &ei};
+    const uint32_t* nd = a.n_groups_dev;
+    void* args[] = {&pay, &sb, &sc, &cb, &n, &out, &oe, &flags, &si, &so, &ei, &nd};
     switch (R) {
 #define SPECKV_CASE(RR) case RR: return launch_clustered(decompress_fast_kernel<T, RR>, RR, n, st, args);
         SPECKV_CASE(1) SPECKV_CASE(2) SPECKV_CASE(4) SPECKV_CASE(8) SPECKV_CASE(16) SPECKV_CASE(32) SPECKV_CASE(64) SPECKV_CASE(128)

@@ -323,7 +323,8 @@ decompress_rle_generic_kernel(const uint8_t* __restrict__ payload, size_t slot_b
                               uint32_t G, uint32_t n_groups, T* __restrict__ out,
                               uint32_t* __restrict__ out_elems, const uint32_t* __restrict__ only_flagged,
                               const uint32_t* __restrict__ src_index, const uint64_t* __restrict__ slot_offsets,
-                              const uint32_t* __restrict__ elem_index) {
+                              const uint32_t* __restrict__ elem_index, const uint32_t* __restrict__ n_groups_dev) {
+    if (n_groups_dev) n_groups = min(n_groups, *n_groups_dev);   // request count held on the device
     // Output-stationary expansion: a chunk of 2048 pairs is scanned once (start position and
     // starting code of every pair go to shared memory); then every thread produces 16 consecutive
     // output elements at a time -- binary search for the pair covering its first element, then a
@@ -474,8 +475,9 @@ decompress_int8_generic_kernel(const uint8_t* __restrict__ payload, size_t slot_
                                const float* __restrict__ scales, const uint32_t* __restrict__ comp_bytes,
                                uint32_t G, uint32_t n_groups, T* __restrict__ out,
                                uint32_t* __restrict__ out_elems, const uint32_t* __restrict__ src_index,
-                               const uint32_t* __restrict__ elem_index) {
+                               const uint32_t* __restrict__ elem_index, const uint32_t* __restrict__ n_groups_dev) {
     const int tid = threadIdx.x;
+    if (n_groups_dev) n_groups = min(n_groups, *n_groups_dev);
     for (uint32_t g = blockIdx.x; g < n_groups; g += gridDim.x) {
         const uint32_t gi = src_index ? src_index[g] : g;
         const uint8_t* gp = payload + (size_t)gi * slot_bytes;
@@ -504,7 +506,8 @@ __global__ void __launch_bounds__(kThreads)
 passthrough_out_kernel(const uint8_t* __restrict__ payload, size_t slot_bytes,
                        const uint32_t* __restrict__ comp_bytes, uint32_t G, uint32_t n_groups,
                        uint16_t* __restrict__ out, uint32_t* __restrict__ out_elems,
-                       const uint32_t* __restrict__ src_index) {
+                       const uint32_t* __restrict__ src_index, const uint32_t* __restrict__ n_groups_dev) {
+    if (n_groups_dev) n_groups = min(n_groups, *n_groups_dev);
     for (uint32_t g = blockIdx.x; g < n_groups; g += gridDim.x) {
         const uint32_t gi = src_index ? src_index[g] : g;
         const uint16_t* gp = reinterpret_cast<const uint16_t*>(payload + (size_t)gi * slot_bytes);
@@ -545,11 +548,11 @@ static cudaError_t launch_decompress_t(const CodecArgs& a, cudaStream_t st, cons
     if (a.scheme == 2) {
         decompress_rle_generic_kernel<T><<<grid, kThreads, 0, st>>>(pay, a.slot_bytes, a.scales, a.comp_bytes,
                                                                     a.group_elems, a.n_groups, out, a.out_elems, only_flagged, a.src_index,
-                                                                    a.slot_offsets, a.elem_index);
+                                                                    a.slot_offsets, a.elem_index, a.n_groups_dev);
     } else {
         decompress_int8_generic_kernel<T><<<grid, kThreads, 0, st>>>(pay, a.slot_bytes, a.scales, a.comp_bytes,
                                                                      a.group_elems, a.n_groups, out, a.out_elems,
-                                                                     a.src_index, a.elem_index);
+                                                                     a.src_index, a.elem_index, a.n_groups_dev);
     }
     count_launch();
     return cudaGetLastError();
@@ -581,7 +584,7 @@ cudaError_t launch_decompress_generic(const CodecArgs& a, cudaStream_t st, const
         if (a.elem_index) return cudaErrorInvalidValue;
         passthrough_out_kernel<<<grid_for(a.n_groups, a.sm_count, 8), kThreads, 0, st>>>(
             static_cast<const uint8_t*>(a.payload), a.slot_bytes, a.comp_bytes, a.group_elems, a.n_groups,
-            static_cast<uint16_t*>(a.out), a.out_elems, a.src_index);
+            static_cast<uint16_t*>(a.out), a.out_elems, a.src_index, a.n_groups_dev);
         count_launch();
         return cudaGetLastError();
     }

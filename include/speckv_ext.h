@@ -86,6 +86,16 @@ SPECKV_API speckv_status_t speckv_ext_decompress_indexed(const void* d_payload, 
                                               uint32_t* d_out_elems, speckv_comp_scheme_t scheme,
                                               void* cuda_stream);
 
+/* The same with the request list produced on the device (speckv_ext_route_requests): the number of valid
+ * entries of d_block_index is read from *d_n_requests by the kernels, max_requests is the capacity the launch
+ * is sized for.  No host synchronisation between routing and decoding; capturable into a CUDA graph. */
+SPECKV_API speckv_status_t speckv_ext_decompress_routed(const void* d_payload, size_t slot_bytes,
+                                             const float* d_scales, const uint32_t* d_comp_bytes,
+                                             const uint32_t* d_block_index, const uint32_t* d_n_requests,
+                                             size_t max_requests, size_t group_elems, speckv_dtype_t dtype,
+                                             void* d_out, uint32_t* d_out_elems, speckv_comp_scheme_t scheme,
+                                             void* cuda_stream);
+
 /* Paged gather / scatter fused with the codec: the element buffer is a paged KV cache made of
  * blocks of group_elems elements (vLLM layout: one block = block_size tokens x kv_heads x
  * head_dim, contiguous), and a block table says which blocks take part.
@@ -364,6 +374,68 @@ SPECKV_API speckv_status_t speckv_ext_prefetch_score(const uint32_t* d_tokens, u
                                                      uint32_t req_id, uint32_t layer_id, uint32_t* d_ids,
                                                      float* d_conf, uint64_t* d_va, void* cuda_stream);
 
+/* One prefetch request: the reference's PrefetchRequest (src/prefetcher/speculative_prefetcher.h:23-29), 32 bytes
+ * with natural alignment.  This is the fixed-size record ranks exchange. */
+typedef struct {
+    uint64_t virtual_addr;
+    uint32_t layer_id;
+    uint32_t predicted_token_id;
+    float    confidence;
+    uint32_t reserved;          /* the padding before `timestamp` in the reference's struct; written as 0 */
+    uint64_t timestamp;
+} speckv_prefetch_request_t;
+
+/* SpeculativePrefetcher::prefetch for `batch` sequences, entirely on the device: scoring as speckv_ext_prefetch_score,
+ * then for every prediction i of every sequence the request address (req << 32) | (layer << 16) | (i + 1) with
+ * req = d_req_ids[sequence] (or req_id for all when d_req_ids is NULL; the reference always uses 0), the residency
+ * filter -- a request whose page is in L1 or L2 of the page table (d_pages / num_pages / va_base as in
+ * speckv_ext_page_lookup; flags bit0 | bit1) is skipped, speculative_prefetcher.cpp:51-54; d_pages NULL = no filter --
+ * and the emission of PrefetchRequest records (:57-66).  d_table receives 1 + batch * k records: record 0 is a
+ * header whose virtual_addr field holds the number n of requests emitted, records 1 .. n are the requests in
+ * sequence order, prediction order within a sequence; the rest is left untouched.  The table is what
+ * speckv_ext_route_requests consumes, here or (all-gathered) on every rank.  `timestamp` is stored in every record
+ * (the reference stores steady_clock::now()).  d_ids / d_conf (optional, [batch][k]) receive the unfiltered
+ * predictions.  The 16 most recent requests stay queued on the device (issue_dma_prefetch, :162-172). */
+SPECKV_API speckv_status_t speckv_ext_prefetch_emit(const uint32_t* d_tokens, uint32_t batch, uint32_t k,
+                                                    const uint32_t* d_req_ids, uint32_t req_id, uint32_t layer_id,
+                                                    const speckv_page_t* d_pages, size_t num_pages, uint64_t va_base,
+                                                    uint64_t timestamp, speckv_prefetch_request_t* d_table,
+                                                    uint32_t* d_ids, float* d_conf, void* cuda_stream);
+
+/* SpeculativePrefetcher::handle_misprediction (speculative_prefetcher.cpp:84-97): counts a misprediction when
+ * actual_token is not among the n predicted tokens.  Host logic; *out_was_correct (optional) = 1 if it was. */
+SPECKV_API speckv_status_t speckv_ext_prefetch_handle_misprediction(uint32_t actual_token, const uint32_t* h_predicted,
+                                                                    size_t n, int* out_was_correct);
+/* SpeculativePrefetcher::get_statistics / reset_statistics (speculative_prefetcher.cpp:126-142; PrefetchStatistics,
+ * speculative_prefetcher.h:59-66).  total_prefetches = requests emitted by speckv_ext_prefetch_emit;
+ * avg_prediction_latency_us follows the reference's update rule (:72-79) with the device time of each emit call;
+ * successful_prefetches is never incremented in the reference either, so hit_rate and precision are 0.  Blocking. */
+typedef struct {
+    uint64_t total_prefetches, successful_prefetches, mispredictions;
+    double hit_rate, precision, avg_prediction_latency_us;
+} speckv_prefetch_stats_t;
+SPECKV_API speckv_status_t speckv_ext_prefetch_stats(speckv_prefetch_stats_t* out, int reset);
+/* SpeculativePrefetcher::is_already_prefetched (speculative_prefetcher.cpp:174-185) for n addresses against the
+ * queue of the 16 most recent requests; h_queue (optional, 16 records) / out_queue_len receive the queue itself,
+ * oldest first.  Blocking. */
+SPECKV_API speckv_status_t speckv_ext_prefetch_outstanding(const uint64_t* h_va, size_t n, uint8_t* out_found,
+                                                           speckv_prefetch_request_t* h_queue, uint32_t* out_queue_len,
+                                                           void* cuda_stream);
+
+/* Turns request tables into this rank's decode list, on the device.  d_tables holds n_tables tables of
+ * (1 + table_capacity) records each, as produced by speckv_ext_prefetch_emit (and all-gathered across ranks):
+ * record 0 is a header whose virtual_addr field is the number of valid requests that follow.  A request names
+ * stored block b = predicted_token_id % n_blocks_total; blocks are owned in contiguous ranges,
+ * owner = b / ceil(n_blocks_total / world), local index = b - owner * ceil(n_blocks_total / world).  The requests
+ * owned by `rank` are compacted, in table and record order, into d_block_index (capacity n_tables *
+ * table_capacity) and their number is written to *d_count -- the pair speckv_ext_decompress_routed consumes.
+ * d_request_index (optional) receives table * table_capacity + position of each kept request. */
+SPECKV_API speckv_status_t speckv_ext_route_requests(const speckv_prefetch_request_t* d_tables, uint32_t n_tables,
+                                                     uint32_t table_capacity, uint32_t n_blocks_total,
+                                                     uint32_t world, uint32_t rank, uint32_t* d_block_index,
+                                                     uint32_t* d_request_index, uint32_t* d_count,
+                                                     void* cuda_stream);
+
 /* Adaptive prefetch depth (SpeculativePrefetcher::update_prediction_accuracy / get_adaptive_depth,
  * speculative_prefetcher.cpp:99-124): report whether the last prediction was correct; the depth
  * used by the prefetcher moves between 2 and 8 exactly as in the reference.  Host logic: works
@@ -381,6 +453,24 @@ typedef struct {
     uint64_t kernel_launches;        /* CUDA kernels this library launched */
 } speckv_ext_stats_t;
 SPECKV_API void speckv_ext_get_stats(speckv_ext_stats_t* out);
+/* FPGACacheEngine::get_statistics (cache_engine.cpp:150-158, EngineStatistics cache_engine.h:65-72) with the
+ * reference's field meaning: the latencies are running means over CALLS, updated by the reference's rule
+ * (:76-79, :108-112), measured with CUDA events on the caller's stream (a call = one batch of groups here, one
+ * group in the reference; the per-group figures are given next to them).  avg_compression_ratio is the running
+ * mean over the groups reported through speckv_ext_ratio_stats (the sizes live on the device; the reference
+ * updates it inside compress(), :69-75).  throughput_gbps is measured (uncompressed gigabits per second of
+ * device time in the timed calls) where the reference returns the constant 512 bit x 800 MHz (:291-296).
+ * wait != 0 synchronises with the calls still in flight; otherwise only finished calls are counted.
+ * Calls captured into a CUDA graph are not timed; SPECKV_LATENCY_STATS=0 switches the timing off. */
+typedef struct {
+    uint64_t total_compressions, total_decompressions;   /* groups, like speckv_ext_stats_t */
+    double avg_compression_ratio;
+    double avg_compression_latency_ns, avg_decompression_latency_ns;   /* per call */
+    double throughput_gbps;
+    uint64_t compress_calls_timed, decompress_calls_timed;
+    double compress_ns_per_group, decompress_ns_per_group;
+} speckv_engine_stats_t;
+SPECKV_API void speckv_ext_engine_stats(speckv_engine_stats_t* out, int wait);
 /* EngineStatistics::avg_compression_ratio (cache_engine.cpp:69-75): the mean over groups of
  * original_size / compressed_size with original_size = group_elems * sizeof(float), the reference's
  * own accounting (:49); plus the total payload bytes.  Blocking (returns host values). */
