@@ -4,21 +4,25 @@
     python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
     python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path
 
-One "step" = one pass of the hot path over one batch of synthetic KV: every group of
-the workload is compressed (scale -> wrapped int8 -> delta -> byte-pair RLE) and then
-decompressed again, layer by layer.  `value` = uncompressed fp16 KV bytes that made the
-round trip per second, whole job (all ranks), inputs resident in HBM.  `e2e` = the same
-metric through the host-buffer C ABI (speckv_ext_compress_host / _decompress_host) with
-the H2D / D2H copies inside the timed region.
+One "step" = one pass of the hot path over one batch of synthetic KV: every group of the
+workload is compressed (scale -> wrapped int8 -> delta -> byte-pair RLE) and then
+decompressed again.  `value` = uncompressed fp16 KV bytes that made the round trip per
+second, whole job (all ranks), inputs resident in HBM.  `e2e` = the same metric through the
+host-buffer C ABI (speckv_ext_compress_host / _decompress_host) with the H2D / D2H copies
+inside the timed region, next to the plain-memcpy ceiling of the same bytes.
 
-Workloads (BASELINE.json `configs`):
-  cfg2  Llama-2-7B KV, batch 32 x 4K ctx per GPU: 32 L x 2 x 32 H x 32 x 4 blocks of
-        1024 tok x 128 d = 262144 groups = 64 GiB fp16 per GPU (default; weak scaling)
-  cfg3  Llama-2-70B GQA KV, 80 L x 8 KVH x 8K ctx: 10240 groups = 2.5 GiB, layers
-        sharded 80/N across ranks (strong scaling)
-  cfg4p Llama-3-8B 32K ctx as 4 KiB page groups (2048 elems): 1 Mi groups = 4 GiB
-One process per GPU (torchrun), no data-path collective; at N > 1 the only exchange is
-an NCCL all-gather of the per-group page-table metadata (comp_bytes) per step.
+Headline workload (BASELINE.json configs[2], the shape the north-star target is quoted on):
+  cfg3  Llama-2-70B GQA KV, 80 L x 2 x 8 KVH x 8K ctx: 10240 groups of 1024 tok x 128 d
+        = 2.5 GiB fp16, layers split 80/N contiguously across the ranks (STRONG scaling;
+        at N = 1 the whole tensor on one GPU)
+Sub-records in `aux` (same run, same ranks):
+  cfg2  Llama-2-7B KV, batch 32 x 4K ctx PER GPU: 262144 groups = 64 GiB per GPU (weak scaling)
+  cfg5  batch-256 decode: LSTM prefetch scoring + request exchange + routed decompress
+  tier  cfg4 (Llama-3-8B 32K ctx as 4 KiB pages): translate, offload -> restore through the
+        pinned host pool, PCIe GB/s
+  ratios  per value distribution / scheme: ratio, MSE, codec GB/s and fraction of the HBM peak
+One process per GPU (torchrun), no data-path collective; at N > 1 the only exchanges are NCCL
+all-gathers of metadata (per-group page-table records; PrefetchRequest tables in cfg5).
 """
 from __future__ import annotations
 
@@ -48,7 +52,7 @@ def workload_spec(name: str, world: int, rank: int, scale: float):
                     global_batch=32 * world)
     if name == "cfg3":
         layers, per_layer = 80, 2 * 8 * 8                # K|V x KV heads x (8192/1024)
-        mine = [l for l in range(layers) if l % world == rank] if world > 1 else list(range(layers))
+        mine = range(rank * layers // world, (rank + 1) * layers // world)      # contiguous 80 / N layers per rank
         return dict(label=f"cfg3: Llama-2-70B GQA KV, 80 L x 8 KVH x 8K ctx, layers sharded {layers}/{world}",
                     group_elems=G_BLOCK, n_groups=len(mine) * per_layer, chunk_groups=per_layer * 20, scaling="strong",
                     global_batch=1)
@@ -71,12 +75,17 @@ def hbm_peak():
 
 
 def ncu_traffic(kernel_key: str):
-    """dram bytes per launch from the committed ncu --set full capture, if one matches."""
+    """DRAM bytes per group of 131072 fp16 elements from the committed ncu --set full capture of the kernel
+    (profiles/ncu_traffic.json: {"compress": {"dram_bytes_per_group": .., "source": "<capture, head, date>"}, ..})."""
     try:
         with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
-            return json.load(f).get(kernel_key)
+            r = json.load(f).get(kernel_key)
+        return r if isinstance(r, dict) and "dram_bytes_per_group" in r else None
     except Exception:
         return None
+
+
+SCHEME_IDS = {"fp16": 0, "int8": 1, "int8_delta_rle": 2}       # speckv_comp_scheme_t (host/include/speckv.h:59-63)
 
 
 class ClockSampler(threading.Thread):
@@ -217,33 +226,61 @@ def bind_to_gpu_cpus(local_rank):
     return before
 
 
-def run_cuda(args, rank, world, local_rank):
+class Env:
+    """What every leg of the CUDA arm needs: torch, the process group, the library."""
+
+    def __init__(self, args, rank, world, local_rank):
+        import torch
+        import torch.distributed as dist
+
+        import cxl_speckv_b200 as pkg
+
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py: no CUDA device; the CUDA path has no CPU fallback "
+                             "(use --impl reference for the CPU baseline)")
+        self.args, self.rank, self.world, self.local_rank = args, rank, world, local_rank
+        self.torch, self.dist = torch, dist
+        torch.cuda.set_device(local_rank)
+        self.dev = torch.device("cuda", local_rank)
+        if world > 1:
+            dist.init_process_group("nccl", device_id=self.dev)
+        self.L = pkg.lib()
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def reduce(self, vals, op="max"):
+        """list of floats -> the same list reduced over the ranks"""
+        t = self.torch.tensor(vals, dtype=self.torch.float64, device=self.dev)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX if op == "max" else self.dist.ReduceOp.SUM)
+        return t.tolist()
+
+    def gather_floats(self, v):
+        t = self.torch.tensor([v], dtype=self.torch.float64, device=self.dev)
+        if self.world == 1:
+            return [float(v)]
+        out = self.torch.empty(self.world, dtype=self.torch.float64, device=self.dev)
+        self.dist.all_gather_into_tensor(out, t)
+        return out.tolist()
+
+
+def codec_roundtrip(env, spec, steps, warmup, use_graph, sample_clocks=False, scheme=2):
+    """K timed steps of: compress every group of this rank's shard -> (N > 1: all-gather of the page-table
+    metadata on a side stream, overlapped) -> decompress every group.  Device-resident inputs.
+    -> dict with the whole-job value, the per-phase times (CUDA events on the launching stream) and the roofline."""
     import ctypes as C
 
-    import numpy as np
-    import torch
-    import torch.distributed as dist
-
-    import cxl_speckv_b200 as pkg
+    torch, dist, L, dev, world = env.torch, env.dist, env.L, env.dev, env.world
     from cxl_speckv_b200 import codec
 
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device; the CUDA path has no CPU fallback "
-                         "(use --impl reference for the CPU baseline)")
-    all_cpus = bind_to_gpu_cpus(local_rank)
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    L = pkg.lib()
-
-    spec = workload_spec(args.workload, world, rank, args.scale)
     G, n_groups, cg = spec["group_elems"], spec["n_groups"], spec["chunk_groups"]
-    sb = codec.slot_bytes(G)
+    sb = codec.slot_bytes(G, scheme)
     n_chunks = (n_groups + cg - 1) // cg
-    # ---- resident synthetic KV (N(0,1), seed 1234 + rank), payload slots, one output chunk ------
     gen = torch.Generator(device=dev)
-    gen.manual_seed(1234 + rank)
+    gen.manual_seed(1234 + env.rank)
     x = torch.empty(n_groups * G, dtype=torch.float16, device=dev)
     for c0 in range(0, n_groups, cg):
         c1 = min(n_groups, c0 + cg)
@@ -251,261 +288,235 @@ def run_cuda(args, rank, world, local_rank):
     payload = torch.empty((n_groups, sb), dtype=torch.uint8, device=dev)
     scales = torch.empty(n_groups, dtype=torch.float32, device=dev)
     comp = torch.empty(n_groups, dtype=torch.int32, device=dev)
-    out = torch.empty((min(cg, n_groups), G), dtype=torch.float16, device=dev)
+    out_groups = n_groups if n_groups * G * 2 <= (4 << 30) else min(cg, n_groups)   # whole shard, or one launch chunk
+    out = torch.empty((out_groups, G), dtype=torch.float16, device=dev)
     gathered = torch.empty(world * n_groups, dtype=torch.int32, device=dev) if world > 1 else None
-    stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    main = torch.cuda.Stream(device=dev)
+    side = torch.cuda.Stream(device=dev) if world > 1 else None
 
     def compress_all():
+        st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
         for c0 in range(0, n_groups, cg):
             n = min(cg, n_groups - c0)
-            st = L.speckv_ext_compress(x.data_ptr() + c0 * G * 2, 0, G, n, payload.data_ptr() + c0 * sb, sb,
-                                       scales.data_ptr() + c0 * 4, comp.data_ptr() + c0 * 4, 2, stream)
-            assert st == 0, st
+            rc = L.speckv_ext_compress(x.data_ptr() + c0 * G * 2, 0, G, n, payload.data_ptr() + c0 * sb, sb,
+                                       scales.data_ptr() + c0 * 4, comp.data_ptr() + c0 * 4, scheme, st)
+            assert rc == 0, rc
 
     def decompress_all():
+        st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
         for c0 in range(0, n_groups, cg):
             n = min(cg, n_groups - c0)
-            st = L.speckv_ext_decompress(payload.data_ptr() + c0 * sb, sb, scales.data_ptr() + c0 * 4,
-                                         comp.data_ptr() + c0 * 4, G, n, 0, out.data_ptr(), None, 2, stream)
-            assert st == 0, st
+            o = out.data_ptr() + (c0 * G * 2 if out_groups == n_groups else 0)
+            rc = L.speckv_ext_decompress(payload.data_ptr() + c0 * sb, sb, scales.data_ptr() + c0 * 4,
+                                         comp.data_ptr() + c0 * 4, G, n, 0, o, None, scheme, st)
+            assert rc == 0, rc
+
+    graphs = None
+    with torch.cuda.stream(main):
+        s0 = codec.stats()["kernel_launches"]
+        compress_all()
+        decompress_all()                                    # also sizes the per-stream scratch before any capture
+        launches_per_step = codec.stats()["kernel_launches"] - s0
+        main.synchronize()
+        if use_graph:
+            try:
+                graphs = (torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph())
+                with torch.cuda.graph(graphs[0], stream=main):
+                    compress_all()
+                with torch.cuda.graph(graphs[1], stream=main):
+                    decompress_all()
+            except Exception as e:                          # noqa: BLE001 -- eager launches are the same kernels
+                graphs = None
+                spec = dict(spec, graph_error=str(e)[:200])
+                torch.cuda.synchronize()
 
     def step(ev=None):
         if ev:
-            ev[0].record()
-        compress_all()
+            ev[0].record(main)
+        graphs[0].replay() if graphs else compress_all()
         if ev:
-            ev[1].record()
+            ev[1].record(main)
+        if world > 1:                                       # page-table metadata exchange, overlapped with the decode
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                dist.all_gather_into_tensor(gathered, comp)
+        graphs[1].replay() if graphs else decompress_all()
+        if ev:
+            ev[2].record(main)
         if world > 1:
-            dist.all_gather_into_tensor(gathered, comp)     # page-table metadata exchange
-        if ev:
-            ev[2].record()
-        decompress_all()
-        if ev:
-            ev[3].record()
+            main.wait_stream(side)                          # the next step rewrites comp
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    for _ in range(max(args.warmup, 3)):
-        step()
-    barrier()
-    codec_stats0 = codec.stats()
-    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    t_start.record()
-    for i in range(args.steps):
-        step(evs[i])
-    t_end.record()
-    barrier()
-    clocks = sampler.stop()
-    launches = codec.stats()["kernel_launches"] - codec_stats0["kernel_launches"]
+    sampler = None
+    with torch.cuda.stream(main):
+        n_warm, t_w = 0, time.perf_counter()
+        while n_warm < max(warmup, 3) or (time.perf_counter() - t_w < 0.25 and n_warm < 2000):
+            step()                                          # >= W steps and >= 0.25 s of them: clocks are up before the timed region
+            n_warm += 1
+            if n_warm % 16 == 0:
+                main.synchronize()
+        env.barrier()
+        evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(steps)]
+        if sample_clocks:
+            sampler = ClockSampler(env.local_rank, period=0.002)
+            sampler.start()
+        t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        env.barrier()
+        t_start.record(main)
+        for i in range(steps):
+            step(evs[i])
+        t_end.record(main)
+        env.barrier()
+    clocks = sampler.stop() if sampler else None
     elapsed_ms = t_start.elapsed_time(t_end)
-    t_comp = sum(e[0].elapsed_time(e[1]) for e in evs) / args.steps
-    t_dec = sum(e[2].elapsed_time(e[3]) for e in evs) / args.steps
-    tt = torch.tensor([elapsed_ms, t_comp, t_dec], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    elapsed_ms, t_comp_max, t_dec_max = tt.tolist()
+    t_comp = sum(e[0].elapsed_time(e[1]) for e in evs) / steps
+    t_dec = sum(e[1].elapsed_time(e[2]) for e in evs) / steps
+    elapsed_max, = env.reduce([elapsed_ms])
+    per_rank_ms = env.gather_floats(elapsed_ms / steps)
+    kv_bytes = n_groups * G * 2
+    comp_total = int(comp.to(torch.int64).sum().item())
+    kv_all, comp_all, groups_all = env.reduce([kv_bytes, comp_total, n_groups], "sum")
+    ms_per_step = elapsed_max / steps
+    value = kv_all / (ms_per_step * 1e-3) / 1e9
 
-    kv_bytes = n_groups * G * 2                                   # this rank, per step
-    comp_total = int(comp.to(torch.int64).sum().item())           # payload bytes c, this rank
-    tot = torch.tensor([kv_bytes, comp_total, n_groups], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
-    kv_bytes_all, comp_all, groups_all = tot.tolist()
-    ms_per_step = elapsed_ms / args.steps
-    value = kv_bytes_all / (ms_per_step * 1e-3) / 1e9
+    # correctness of what was timed: the round trip of the first groups equals the library's one-shot path
+    chk = min(n_groups, 8)
+    ref = codec.decompress(codec.compress(x[:chk * G], G, scheme=scheme))
+    assert torch.equal(ref.view(torch.int16), out[:chk].view(torch.int16)) or out_groups != n_groups, "bench output differs"
 
-    # ---- roofline of the dominant kernel (per launch = one chunk of cg groups) -------------------
     peak, peak_src = hbm_peak()
-    alg_comp = 2 * G * n_groups + comp_total + 12 * n_groups       # 2n read + c write + header
-    alg_dec = comp_total + 12 * n_groups + 2 * G * n_groups        # c read + header + 2n write
+    alg_comp = 2 * G * n_groups + comp_total + 12 * n_groups       # 2n read + c write + 12 B header per group
+    alg_dec = comp_total + 12 * n_groups + 2 * G * n_groups        # c + header read, 2n write
     comp_gbs = alg_comp / (t_comp * 1e-3) / 1e9
     dec_gbs = alg_dec / (t_dec * 1e-3) / 1e9
     dom = "compress" if t_comp >= t_dec else "decompress"
-    dom_bytes_per_launch = (alg_comp if dom == "compress" else alg_dec) / n_chunks
-    dom_ms_per_launch = (t_comp if dom == "compress" else t_dec) / n_chunks
-    achieved = comp_gbs if dom == "compress" else dec_gbs
-    roofline = {"bound": "hbm", "kernel": f"kv_{dom}", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "peak_source": peak_src,
-                "traffic": ncu_traffic(f"{args.workload}:{dom}"),
-                "algorithmic_bytes_per_launch": dom_bytes_per_launch, "ms_per_launch": dom_ms_per_launch,
+    tr = ncu_traffic(dom)
+    roofline = {"bound": "hbm", "kernel": f"kv_{dom} ({dom}_fast_kernel)", "achieved": comp_gbs if dom == "compress" else dec_gbs,
+                "peak": peak, "unit": "GB/s", "frac": (comp_gbs if dom == "compress" else dec_gbs) / peak, "peak_source": peak_src,
+                "traffic": (tr["dram_bytes_per_group"] * min(cg, n_groups)) if tr else None,
+                "traffic_source": tr.get("source") if tr else None,
+                "algorithmic_bytes_per_launch": (alg_comp if dom == "compress" else alg_dec) / n_chunks,
+                "ms_per_launch": (t_comp if dom == "compress" else t_dec) / n_chunks, "launches_per_phase": n_chunks,
+                "timing": "CUDA events on the launching stream around each phase of every timed step (this rank)",
                 "compress": {"GB/s": comp_gbs, "frac": comp_gbs / peak, "ms_per_step": t_comp,
                              "kv_GB/s": kv_bytes / (t_comp * 1e-3) / 1e9},
                 "decompress": {"GB/s": dec_gbs, "frac": dec_gbs / peak, "ms_per_step": t_dec,
                                "kv_GB/s": kv_bytes / (t_dec * 1e-3) / 1e9},
-                "frac_of_nominal_8TBs": achieved / 8000.0}
-
-    # ---- e2e: host buffers through the C ABI, copies inside the timed region ----------------------
-    e2e = None
-    if not args.no_e2e:
-        ng = min(n_groups, max(1, int(args.e2e_mib * 2**20) // (G * 2)))
-        nb_in, nb_pay = ng * G * 2, ng * sb
-        h_in = L.speckv_ext_host_alloc(nb_in)
-        h_pay = L.speckv_ext_host_alloc(nb_pay)
-        h_out = L.speckv_ext_host_alloc(nb_in)
-        h_sc = L.speckv_ext_host_alloc(ng * 4)
-        h_cb = L.speckv_ext_host_alloc(ng * 4)
-        assert h_in and h_pay and h_out and h_sc and h_cb, "pinned host allocation failed"
-        x_host = x[:ng * G].cpu().numpy()                      # keep alive across the memmove
-        C.memmove(h_in, x_host.ctypes.data, nb_in)
-        del x_host
-
-        def e2e_step():
-            st = L.speckv_ext_compress_host(h_in, 0, G, ng, h_pay, sb, h_sc, h_cb, 2)
-            assert st == 0, st
-            st = L.speckv_ext_decompress_host(h_pay, sb, h_sc, h_cb, G, ng, 0, h_out, None, 2)
-            assert st == 0, st
-
-        e2e_step()
-        e2e_steps = max(1, min(args.steps, 5))
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(e2e_steps):
-            e2e_step()
-        torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-        te = torch.tensor([dt], dtype=torch.float64, device=dev)
-        tb = torch.tensor([float(nb_in)], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(te, op=dist.ReduceOp.MAX)
-            dist.all_reduce(tb, op=dist.ReduceOp.SUM)
-        e2e = {"value": tb.item() * e2e_steps / te.item() / 1e9, "unit": UNIT,
-               "h2d_bytes_per_step": nb_in + nb_pay + 8 * ng, "d2h_bytes_per_step": nb_pay + 8 * ng + nb_in,
-               "steps": e2e_steps, "api": "speckv_ext_compress_host + speckv_ext_decompress_host (pinned host buffers)",
-               "sample": f"{ng} groups ({nb_in / 2**20:.0f} MiB fp16) per rank per step"}
-        # the host path must reproduce the device path bit for bit
-        y = np.ctypeslib.as_array(C.cast(h_out, C.POINTER(C.c_uint16)), shape=(ng * G,))
-        codec_out = codec.decompress(codec.compress(x[:min(ng, 64) * G], G))
-        assert np.array_equal(y[:min(ng, 64) * G], codec_out.view(torch.int16).cpu().numpy().view(np.uint16).ravel())
-        for p in (h_in, h_pay, h_out, h_sc, h_cb):
-            L.speckv_ext_host_free(p)
-
-    # ---- CPU baseline (rank 0, N = 1 only) ----------------------------------------------------------
-    cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu:
-        os.sched_setaffinity(0, all_cpus)
-        cpu = cpu_roundtrip_rate(G, args.cpu_seconds, os.cpu_count() or 1)
-        cpu.pop("seconds", None)
-
-    if rank == 0:
-        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-                "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
-                "scaling": spec["scaling"], "vs_baseline": None, "dtype": "f32+i8", "data": "synthetic N(0,1) fp16 KV (torch seed 1234+rank)",
-                "config": {"workload": spec["label"], "group_elems": G, "groups_per_rank": n_groups,
-                           "groups_total": int(groups_all), "kv_bytes_per_step_total": int(kv_bytes_all),
-                           "launch_chunk_groups": cg, "global_batch": spec["global_batch"],
-                           "parallelism": f"independent shards x{world}, all-gather of comp_bytes only" if world > 1 else "single GPU",
-                           "cache": "inputs larger than L2 (no flush needed)" if kv_bytes > (1 << 30) else "inputs + outputs exceed L2 per step"},
-                "per_gpu_value": value / world,
-                "compression_ratio": {"vs_fp16": kv_bytes_all / comp_all, "vs_fp32_reference_accounting": 2 * kv_bytes_all / comp_all},
-                "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu}
-        print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+                "roundtrip_frac": (alg_comp + alg_dec) / ((t_comp + t_dec) * 1e-3) / 1e9 / peak,
+                "frac_of_nominal_8TBs": (comp_gbs if dom == "compress" else dec_gbs) / 8000.0}
+    res = {"value": value, "ms_per_step": ms_per_step, "per_gpu_value": value / world, "per_rank_ms_per_step": per_rank_ms,
+           "kv_bytes_per_step_total": int(kv_all), "groups_total": int(groups_all), "groups_per_rank": n_groups,
+           "launch_chunk_groups": min(cg, n_groups), "warmup_steps_run": n_warm, "graph": bool(graphs), "graph_error": spec.get("graph_error"),
+           "gpu_launches": int(launches_per_step) * steps,
+           "compression_ratio": {"vs_fp16": kv_all / comp_all, "vs_fp32_reference_accounting": 2 * kv_all / comp_all},
+           "roofline": roofline, "clocks": clocks}
+    res["_x"] = x                                              # the e2e leg reuses the shard
+    del payload, out, gathered
+    return res
 
 
-# --------------------------------------------------------------------------------------
-# auxiliary reports (not the driver's bench line): BASELINE configs 4 and 5
-# --------------------------------------------------------------------------------------
-def run_cfg4(args, local_rank):
-    """Llama-3-8B 32K-context paged KV: translate every page address, page-table lookup, then
-    offload -> restore through the pinned host pool (PCIe GB/s of stored bytes), verify bytes."""
+def pcie_ceiling(env, h2d_bytes, d2h_bytes, reps=3):
+    """Plain pinned cudaMemcpyAsync in both directions at once (two streams), every rank at the same time:
+    the most the host side of this box gives the e2e leg.  -> seconds for one (h2d_bytes up, d2h_bytes down) pass."""
+    torch, dev = env.torch, env.dev
+    piece = 256 << 20
+    hb_up = torch.empty(min(h2d_bytes, piece), dtype=torch.uint8, pin_memory=True)
+    hb_dn = torch.empty(min(d2h_bytes, piece), dtype=torch.uint8, pin_memory=True)
+    db_up, db_dn = torch.empty_like(hb_up, device=dev), torch.empty_like(hb_dn, device=dev)
+    s_up, s_dn = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+
+    def one_pass():
+        with torch.cuda.stream(s_up):
+            left = h2d_bytes
+            while left > 0:
+                n = min(left, hb_up.numel())
+                db_up[:n].copy_(hb_up[:n], non_blocking=True)
+                left -= n
+        with torch.cuda.stream(s_dn):
+            left = d2h_bytes
+            while left > 0:
+                n = min(left, hb_dn.numel())
+                hb_dn[:n].copy_(db_dn[:n], non_blocking=True)
+                left -= n
+
+    one_pass()
+    env.barrier()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        one_pass()
+    torch.cuda.synchronize()
+    dt = (time.perf_counter() - t0) / reps
+    dt, = env.reduce([dt])
+    return dt
+
+
+def e2e_leg(env, spec, x, steps, scheme=2):
+    """The same round trip through the host-buffer C ABI: pinned host in -> payload in host memory -> host out,
+    every H2D / D2H copy inside the timed region; next to it the plain-memcpy ceiling of the same bytes."""
     import ctypes as C
 
     import numpy as np
-    import torch
 
-    import cxl_speckv_b200 as pkg
+    torch, L, dev = env.torch, env.L, env.dev
     from cxl_speckv_b200 import codec
-    from cxl_speckv_b200.tier import HostTier
 
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    L = pkg.lib()
-    layers = max(1, int(round(32 * args.scale)))
-    G, pages = 2048, layers * 2 * 8 * 32768 * 128 // 2048
-    x = torch.empty(pages * G, dtype=torch.float16, device=dev)
-    gen = torch.Generator(device=dev); gen.manual_seed(1234)
-    x.normal_(generator=gen)
+    G = spec["group_elems"]
+    sb = codec.slot_bytes(G, scheme)
+    ng = min(spec["n_groups"], max(1, int(env.args.e2e_mib * 2**20) // (G * 2)))
+    nb_in, nb_pay = ng * G * 2, ng * sb
+    ptrs = [L.speckv_ext_host_alloc(n) for n in (nb_in, nb_pay, nb_in, ng * 4, ng * 4)]
+    assert all(ptrs), "pinned host allocation failed"
+    h_in, h_pay, h_out, h_sc, h_cb = ptrs
+    x_host = x[:ng * G].cpu().numpy()
+    C.memmove(h_in, x_host.ctypes.data, nb_in)
+    del x_host
 
-    def timed(fn, reps=3):
-        fn(); torch.cuda.synchronize()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        for _ in range(reps):
-            fn()
-        b.record(); torch.cuda.synchronize()
-        return a.elapsed_time(b) / reps
+    def e2e_step():
+        rc = L.speckv_ext_compress_host(h_in, 0, G, ng, h_pay, sb, h_sc, h_cb, scheme)
+        assert rc == 0, rc
+        rc = L.speckv_ext_decompress_host(h_pay, sb, h_sc, h_cb, G, ng, 0, h_out, None, scheme)
+        assert rc == 0, rc
 
-    # address translation of every page + page-table lookup through the exported table
-    assert L.speckv_init(f"cuda:{local_rank}".encode()) == 0
-    h = C.c_uint64(); assert L.speckv_alloc(pages * 4096, None, C.byref(h)) == 0
-    tbl = torch.empty(pages * 3, dtype=torch.int64, device=dev); cnt = C.c_size_t()
-    assert L.speckv_ext_page_table_export(h.value, tbl.data_ptr(), pages, C.byref(cnt), None) == 0
-    va = (torch.arange(pages, dtype=torch.int64, device=dev) << 12) + (h.value << 32) + 0x123
-    pa = torch.empty_like(va); fl = torch.empty(pages, dtype=torch.int32, device=dev)
-    t_tr = timed(lambda: codec.translate(va, out=pa))
-    t_lk = timed(lambda: L.speckv_ext_page_lookup(tbl.data_ptr(), pages, h.value << 32, va.data_ptr(), pa.data_ptr(), fl.data_ptr(), pages, None))
-    assert int(pa[5].item()) == 0x4000000000 + (h.value << 20) + (5 << 12) + 0x123
-    L.speckv_finalize()
-
-    tier = HostTier(int(pages * G * 2 * 1.02) + (64 << 20))
-    ids = np.arange(pages, dtype=np.uint64) << np.uint64(12)
-    tier.offload(x[:65536 * G], G, ids[:65536]); tier.drop(ids[:65536])      # warm-up: staging buffers, pinned mirrors
-    t0 = time.perf_counter(); tier.offload(x, G, ids); torch.cuda.synchronize(); t_off = time.perf_counter() - t0
-    out = torch.empty((pages, G), dtype=torch.float16, device=dev)
-    st_off = tier.stats()
-    tier.restore(ids[:65536], G, torch.float16, out=out[:65536])             # warm-up
-    t0 = time.perf_counter(); tier.restore(ids, G, torch.float16, out=out); torch.cuda.synchronize(); t_res = time.perf_counter() - t0
-    st = tier.stats()
-    want = codec.decompress(codec.compress(x[:4096 * G], G))
-    assert torch.equal(out[:4096].view(torch.int16), want.view(torch.int16))
-    tier.close()
-    del out
-
-    # residency policy over the same pages: one decode step touches every page; then a prefetch-sized promotion
-    from cxl_speckv_b200.tier import TierPolicy
-    pol = TierPolicy(pages, l1_pages=pages // 16)
-    allp = np.arange(pages, dtype=np.uint64)
-    pol.place(allp[:pages // 16], 0); pol.place(allp[pages // 16:], 2)
-    perm = torch.randperm(pages, device=dev, generator=gen)
-    t_touch = timed(lambda: pol.touch(perm))
-    batch = allp[pages // 16:][:4096]
-    torch.cuda.synchronize(); t0 = time.perf_counter(); ok, ev = pol.promote(batch); t_prom = time.perf_counter() - t0
-    assert ok.all() and ev.size == 4096
-    pol.close()
-    print(json.dumps({"report": "cfg4", "workload": f"Llama-3-8B 32K ctx paged KV, {layers} layers, {pages} pages of 4 KiB",
-                      "policy": {"touch_Gpages_per_s": pages / t_touch / 1e6, "touch_ms_all_pages": t_touch,
-                                 "promote_4096_with_eviction_ms": t_prom * 1e3},
-                      "translate_Gaddr_per_s": pages / t_tr / 1e6, "translate_GB/s": pages * 16 / t_tr / 1e6,
-                      "page_lookup_Gaddr_per_s": pages / t_lk / 1e6,
-                      "offload": {"s": t_off, "stored_bytes": st_off["last_offload_stored_bytes"], "pcie_GB/s": st_off["last_offload_stored_bytes"] / t_off / 1e9,
-                                  "kv_GB/s": pages * G * 2 / t_off / 1e9},
-                      "restore": {"s": t_res, "pcie_GB/s": st["last_restore_stored_bytes"] / t_res / 1e9, "kv_GB/s": pages * G * 2 / t_res / 1e9},
-                      "verified": "restored pages == device compress->decompress, bit for bit"}), flush=True)
+    e2e_step()
+    n_steps = max(1, min(steps, 5))
+    env.barrier()
+    t0 = time.perf_counter()
+    for _ in range(n_steps):
+        e2e_step()
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    dt, = env.reduce([dt])
+    tot_in, = env.reduce([float(nb_in)], "sum")
+    cb = np.ctypeslib.as_array(C.cast(h_cb, C.POINTER(C.c_uint32)), shape=(ng,))
+    moved_pay = int(cb.astype(np.int64).sum())               # the host API ships comp_bytes of every slot, not the slot
+    h2d, d2h = nb_in + moved_pay + 8 * ng, moved_pay + 8 * ng + nb_in
+    # the host path must reproduce the device path bit for bit
+    y = np.ctypeslib.as_array(C.cast(h_out, C.POINTER(C.c_uint16)), shape=(ng * G,))
+    k = min(ng, 64)
+    want = codec.decompress(codec.compress(x[:k * G], G, scheme=scheme))
+    assert np.array_equal(y[:k * G], want.view(torch.int16).cpu().numpy().view(np.uint16).ravel()), "e2e output differs"
+    for p in ptrs:
+        L.speckv_ext_host_free(p)
+    t_ceil = pcie_ceiling(env, h2d, d2h)
+    traffic = (h2d + d2h) * env.world
+    return {"value": tot_in * n_steps / dt / 1e9, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+            "steps": n_steps, "api": "speckv_ext_compress_host + speckv_ext_decompress_host (pinned host buffers)",
+            "sample": f"{ng} groups ({nb_in / 2**20:.0f} MiB fp16) per rank per step",
+            "pcie_traffic_GBs": traffic * n_steps / dt / 1e9,
+            "pcie_ceiling_GBs": traffic / t_ceil / 1e9,
+            "pcie_ceiling": "plain pinned cudaMemcpyAsync, the step's H2D and D2H bytes on two streams at once, all ranks concurrently",
+            "frac_of_ceiling": (t_ceil * n_steps) / dt}
 
 
-def run_cfg5(args, rank, world, local_rank):
-    """Batch-256 decode step: LSTM prefetch scoring (k = 4) + decompress of the predicted blocks.
-    N GPUs: the 256 sequences split over the ranks; every rank scores its share, the PrefetchRequest records
-    (32 bytes each) are all-gathered over NCCL -- the only collective -- and every rank
-    decodes the predicted blocks it owns (stored blocks shard round-robin, like layers)."""
+def aux_cfg5(env, use_graph):
+    """Batch-256 decode step (BASELINE config 5): LSTM prefetch scoring (k = 4) with residency filter and
+    PrefetchRequest emission on the device -> N > 1: NCCL all-gather of the request tables (the only collective)
+    -> device-side routing to the owning rank -> decompress of the predicted blocks with a device-side count.
+    No host synchronisation inside a step; the step is one CUDA graph where the capture allows it."""
     import numpy as np
-    import torch
-    import torch.distributed as dist
 
-    from cxl_speckv_b200 import codec, prefetch, sharding
+    torch, dist, dev, world, rank = env.torch, env.dist, env.dev, env.world, env.rank
+    from cxl_speckv_b200 import codec, prefetch
 
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
     rng = np.random.default_rng(1)
     emb = ((rng.random((32000, 64), dtype=np.float32) - 0.5) * 0.1).astype(np.float32)
     wout = ((rng.random((32000, 128), dtype=np.float32) - 0.5) * 0.1).astype(np.float32)
@@ -514,127 +525,303 @@ def run_cfg5(args, rank, world, local_rank):
     all_toks = np.random.default_rng(7).integers(0, 32000, (batch, 16)).astype(np.int32)
     per = (batch + world - 1) // world
     toks = torch.from_numpy(all_toks[rank * per:(rank + 1) * per]).to(dev)
-    G, n_blocks = 131072, 4096                                    # 1 GiB of stored blocks to pick from, in all
-    local_blocks = n_blocks // world                              # block b lives on rank b % world as local block b // world
+    G, n_blocks = G_BLOCK, 4096                                   # 1 GiB of stored blocks in all, contiguous ranges per rank
+    per_blocks = (n_blocks + world - 1) // world
+    local_blocks = max(0, min(per_blocks, n_blocks - rank * per_blocks))
     x = torch.empty(local_blocks * G, device=dev, dtype=torch.float16).normal_()
     c = codec.compress(x, G)
-    out = torch.empty((batch * k, G), dtype=torch.float16, device=dev)   # worst case: every prediction lands here
+    cap = per * k                                                 # requests per table
+    table = torch.zeros((prefetch.table_records(per, k), prefetch.REQUEST_BYTES), dtype=torch.uint8, device=dev)
+    tables = torch.zeros((world,) + tuple(table.shape), dtype=torch.uint8, device=dev) if world > 1 else table
+    block_index = torch.zeros(world * cap, dtype=torch.int32, device=dev)
+    count = torch.zeros(1, dtype=torch.int32, device=dev)
+    out = torch.empty((world * cap, G), dtype=torch.float16, device=dev)   # worst case: every prediction lands here
+    main = torch.cuda.Stream(device=dev)
 
-    def step():
-        ids, conf, va = prefetch.score(toks, k=k, layer_id=0)
-        if world == 1:
-            blocks = (ids.view(-1) % n_blocks).to(torch.int32)
-            codec.decompress_indexed(c, blocks, out=out[:blocks.numel()])
-            return blocks.numel()
-        rec = sharding.pack_prefetch_requests(va, 0, ids, conf)
-        allrec = sharding.gather_records(rec, sharding.PREFETCH_RECORD_BYTES)          # [world, per * k, 32]
-        _, _, tok, _ = sharding.unpack_prefetch_requests(allrec.view(-1, sharding.PREFETCH_RECORD_BYTES))
-        blocks = tok.to(torch.int64) % n_blocks
-        mine = blocks[blocks % world == rank] // world
-        n = int(mine.numel())                                      # host sync: the size of this rank's decode batch
-        if n:
-            codec.decompress_indexed(c, mine.to(torch.int32), out=out[:n])
-        return n
+    def score_part():
+        prefetch.emit(toks, k=k, layer_id=0, timestamp=1, table=table)
 
-    for _ in range(3):
-        step()
+    def decode_part():
+        prefetch.route(tables, world, cap, n_blocks, world, rank, block_index=block_index, count=count)
+        codec.decompress_routed(c, block_index, count, out)
+
+    def exchange():
+        if world > 1:
+            dist.all_gather_into_tensor(tables.view(-1), table.view(-1))
+
+    def eager_step():
+        score_part()
+        exchange()
+        decode_part()
+
+    graph, graph_note = None, None
+    with torch.cuda.stream(main):
+        for _ in range(3):
+            eager_step()
+        main.synchronize()
+        if use_graph:
+            try:
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph, stream=main):
+                    eager_step()
+            except Exception as e:                               # noqa: BLE001
+                graph, graph_note = None, str(e)[:200]
+                torch.cuda.synchronize()
+        step = graph.replay if graph else eager_step
+        for _ in range(3):
+            step()
+        env.barrier()
+        reps = 20
+        a, m, b = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        a.record(main)
+        for _ in range(reps):
+            score_part()
+        m.record(main)
+        for _ in range(reps):
+            step()
+        b.record(main)
+        env.barrier()
+    n_dec = int(count.item())
+    # what was decoded is what the requests name
+    bi = block_index[:n_dec].long()
+    full = codec.decompress(c)
+    assert torch.equal(out[:n_dec].view(torch.int16), full[bi].view(torch.int16)), "cfg5: routed decode differs"
+    t_score, t_step = env.reduce([a.elapsed_time(m) / reps, m.elapsed_time(b) / reps])
+    n_all, = env.reduce([float(n_dec)], "sum")
+    return {"workload": "cfg5: 256 sequences x 16-token history, vocab 32000, k=4 -> 1024 predicted blocks of 1024x128 fp16, "
+                        f"sequences and stored blocks split over {world} GPU(s)",
+            "n_gpus": world, "score_ms": t_score, "step_ms": t_step, "step": "emit (score + residency filter + request records)"
+            " -> all-gather of request tables -> route -> routed decompress", "graph": bool(graph), "graph_error": graph_note,
+            "blocks_decoded_per_step": n_all, "step_seq_per_s": batch / t_step * 1e3,
+            "decoded_kv_GB/s": n_all * G * 2 / (t_step * 1e-3) / 1e9, "reference_cpu_ms_per_sequence": 17.8,
+            "exchange": "none (1 GPU)" if world == 1 else f"NCCL all-gather of {world} tables x {1 + cap} PrefetchRequest records (32 B)"}
+
+
+def aux_tier(env):
+    """BASELINE config 4 data path: Llama-3-8B 32K-context KV as 4 KiB pages, address translation + page-table
+    lookup for every page, offload -> restore through the pinned host pool (PCIe GB/s of stored bytes)."""
+    import ctypes as C
+
+    import numpy as np
+
+    torch, L, dev = env.torch, env.L, env.dev
+    from cxl_speckv_b200 import codec
+    from cxl_speckv_b200.tier import HostTier
+
+    layers = max(1, int(round(32 * env.args.tier_scale)))
+    G, pages = 2048, layers * 2 * 8 * 32768 * 128 // 2048
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(4321 + env.rank)
+    x = torch.empty(pages * G, dtype=torch.float16, device=dev).normal_(generator=gen)
+
+    def timed(fn, reps=3):
+        fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / reps
+
+    assert L.speckv_init(f"cuda:{env.local_rank}".encode()) == 0
+    h = C.c_uint64()
+    assert L.speckv_alloc(pages * 4096, None, C.byref(h)) == 0
+    tbl = torch.empty(pages * 3, dtype=torch.int64, device=dev)
+    cnt = C.c_size_t()
+    assert L.speckv_ext_page_table_export(h.value, tbl.data_ptr(), pages, C.byref(cnt), None) == 0
+    va = (torch.arange(pages, dtype=torch.int64, device=dev) << 12) + (h.value << 32) + 0x123
+    pa = torch.empty_like(va)
+    fl = torch.empty(pages, dtype=torch.int32, device=dev)
+    t_tr = timed(lambda: codec.translate(va, out=pa))
+    t_lk = timed(lambda: L.speckv_ext_page_lookup(tbl.data_ptr(), pages, h.value << 32, va.data_ptr(), pa.data_ptr(), fl.data_ptr(), pages, None))
+    assert int(pa[5].item()) == 0x4000000000 + (h.value << 20) + (5 << 12) + 0x123
+    L.speckv_finalize()
+    del tbl, va, pa, fl
+
+    tier = HostTier(int(pages * G * 2 * 1.02) + (64 << 20))
+    ids = np.arange(pages, dtype=np.uint64) << np.uint64(12)
+    warm = min(pages, 65536)
+    tier.offload(x[:warm * G], G, ids[:warm])
+    tier.drop(ids[:warm])
+    env.barrier()
+    t0 = time.perf_counter()
+    tier.offload(x, G, ids)
     torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    a, b, m = (torch.cuda.Event(enable_timing=True) for _ in range(3))
-    reps = 10
-    a.record()
-    for _ in range(reps):
-        prefetch.score(toks, k=k, layer_id=0)
-    m.record()
-    decoded = 0
-    for _ in range(reps):
-        decoded += step()
-    b.record(); torch.cuda.synchronize()
-    t = torch.tensor([a.elapsed_time(m) / reps, m.elapsed_time(b) / reps, float(decoded) / reps], device=dev, dtype=torch.float64)
-    tot = t.clone()
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)                    # times: max over ranks
-        dist.all_reduce(tot, op=dist.ReduceOp.SUM)                  # decoded blocks: sum over ranks
-    t_score, t_step, n_dec = float(t[0]), float(t[1]), float(tot[2])
-    if rank == 0:
-        print(json.dumps({"report": "cfg5", "n_gpus": world,
-                          "workload": "256 sequences x 16-token history, vocab 32000, k=4 -> 1024 predicted blocks of 1024x128 fp16",
-                          "score_ms": t_score, "score_seq_per_s": batch / t_score * 1e3, "reference_cpu_ms_per_sequence": 17.8,
-                          "step_ms(score+exchange+decompress)": t_step, "blocks_decoded_per_step": n_dec,
-                          "step_seq_per_s": batch / t_step * 1e3,
-                          "decompress_kv_GB/s": n_dec * G * 2 / (max(t_step - t_score, 1e-9) * 1e-3) / 1e9,
-                          "exchange": "none (1 GPU)" if world == 1 else f"all-gather of {batch * k} PrefetchRequest records (32 B) over NCCL"}),
-              flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    t_off = time.perf_counter() - t0
+    st_off = tier.stats()
+    out = torch.empty((pages, G), dtype=torch.float16, device=dev)
+    tier.restore(ids[:warm], G, torch.float16, out=out[:warm])
+    env.barrier()
+    t0 = time.perf_counter()
+    tier.restore(ids, G, torch.float16, out=out)
+    torch.cuda.synchronize()
+    t_res = time.perf_counter() - t0
+    st = tier.stats()
+    k = min(pages, 4096)
+    want = codec.decompress(codec.compress(x[:k * G], G))
+    assert torch.equal(out[:k].view(torch.int16), want.view(torch.int16)), "tier: restored pages differ"
+    tier.close()
+    t_off_max, t_res_max = env.reduce([t_off, t_res])
+    stored, = env.reduce([float(st_off["last_offload_stored_bytes"])], "sum")
+    restored, = env.reduce([float(st["last_restore_stored_bytes"])], "sum")
+    kv_all = pages * G * 2 * env.world
+    return {"workload": f"cfg4: Llama-3-8B 32K ctx paged KV per GPU, {layers} layers, {pages} pages of 4 KiB, offload -> restore through the pinned host pool",
+            "n_gpus": env.world, "translate_Gaddr_per_s": pages / t_tr / 1e6, "translate_GB/s": pages * 16 / t_tr / 1e6,
+            "page_lookup_Gaddr_per_s": pages / t_lk / 1e6,
+            "offload": {"s": t_off_max, "stored_bytes": stored, "pcie_GB/s": stored / t_off_max / 1e9, "kv_GB/s": kv_all / t_off_max / 1e9},
+            "restore": {"s": t_res_max, "stored_bytes": restored, "pcie_GB/s": restored / t_res_max / 1e9, "kv_GB/s": kv_all / t_res_max / 1e9},
+            "pcie_GB/s_per_gpu": {"offload": stored / t_off_max / 1e9 / env.world, "restore": restored / t_res_max / 1e9 / env.world},
+            "verified": "restored pages == device compress -> decompress, bit for bit"}
 
 
-def run_ratios(args, local_rank):
-    """Compression ratio and codec throughput per value distribution:
-    N(0,1) (the headline: incompressible for this format), all-zero, runs of 300, bf16 N(0,1)."""
-    import torch
-
+def aux_ratios(env, n_groups=1024):
+    """Compression ratio, reconstruction error and codec throughput per value distribution
+    and per scheme; rank 0 only."""
+    torch, dev = env.torch, env.dev
     from cxl_speckv_b200 import codec
 
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    G, n_groups = G_BLOCK, 2048                                   # 512 MiB of fp16 per distribution
-    gen = torch.Generator(device=dev); gen.manual_seed(1234)
+    G = G_BLOCK
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(1234)
     base = torch.empty(n_groups * G, dtype=torch.float16, device=dev).normal_(generator=gen)
+    peak, _ = hbm_peak()
     dists = {
-        "normal_fp16": base,
-        "normal_bf16": base.to(torch.bfloat16),
-        "zeros_fp16": torch.zeros_like(base),
-        "runs300_fp16": base[: (n_groups * G + 299) // 300].repeat_interleave(300)[: n_groups * G].contiguous(),
+        "normal_fp16": (base, 2),
+        "normal_bf16": (base.to(torch.bfloat16), 2),
+        "zeros_fp16": (torch.zeros_like(base), 2),
+        "runs300_fp16": (base[: (n_groups * G + 299) // 300].repeat_interleave(300)[: n_groups * G].contiguous(), 2),
+        "smooth_fp16": ((torch.cumsum(base.float().view(n_groups, G) * 0.01, 1)).to(torch.float16).view(-1), 2),
+        "normal_fp16_int8": (base, 1),
+        "normal_fp16_fp16": (base, 0),
     }
-    out = {}
-    for name, x in dists.items():
-        c = codec.compress(x, G)
-        y = codec.decompress(c)
-        torch.cuda.synchronize()
-        ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
-        ev[0].record()
-        for _ in range(5):
-            codec.compress(x, G, out=c)
-        ev[1].record()
-        for _ in range(5):
-            codec.decompress(c, out=y)
-        ev[2].record(); torch.cuda.synchronize()
-        tc, td = ev[0].elapsed_time(ev[1]) / 5, ev[1].elapsed_time(ev[2]) / 5
-        cb = float(c.comp_bytes.to(torch.int64).sum().item())
-        raw = n_groups * G * 2
-        mse = ((y.float() - x.view(n_groups, G).float()) ** 2).mean().item()
-        out[name] = {"ratio_vs_fp16": raw / cb, "ratio_fp32_reference_accounting": 2 * raw / cb,
-                     "compress_kv_GB/s": raw / tc / 1e6, "decompress_kv_GB/s": raw / td / 1e6,
-                     "compress_algorithmic_GB/s": (raw + cb) / tc / 1e6, "decompress_algorithmic_GB/s": (raw + cb) / td / 1e6,
-                     "roundtrip_mse": mse}
-    print(json.dumps({"report": "ratios", "workload": f"{n_groups} groups of 1024x128 per distribution", "distributions": out}), flush=True)
+    for name, sid in SCHEME_IDS.items():
+        if sid > 2:
+            dists[f"normal_fp16_{name}"] = (base, sid)
+            dists[f"smooth_fp16_{name}"] = (dists["smooth_fp16"][0], sid)
+    res = {}
+    for name, (x, scheme) in dists.items():
+        try:
+            c = codec.compress(x, G, scheme=scheme)
+            y = codec.decompress(c)
+            torch.cuda.synchronize()
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+            ev[0].record()
+            for _ in range(5):
+                codec.compress(x, G, scheme=scheme, out=c)
+            ev[1].record()
+            for _ in range(5):
+                codec.decompress(c, out=y)
+            ev[2].record()
+            torch.cuda.synchronize()
+            tc, td = ev[0].elapsed_time(ev[1]) / 5, ev[1].elapsed_time(ev[2]) / 5
+            cb = float(c.comp_bytes.to(torch.int64).sum().item())
+            raw = n_groups * G * 2
+            mse = ((y.float() - x.view(n_groups, G).float()) ** 2).mean().item()
+            res[name] = {"scheme": scheme, "ratio_vs_fp16": raw / cb, "ratio_fp32_reference_accounting": 2 * raw / cb,
+                         "compress_kv_GB/s": raw / tc / 1e6, "decompress_kv_GB/s": raw / td / 1e6,
+                         "compress_algorithmic_GB/s": (raw + cb) / tc / 1e6, "decompress_algorithmic_GB/s": (raw + cb) / td / 1e6,
+                         "compress_frac_of_peak": (raw + cb) / tc / 1e6 / peak, "decompress_frac_of_peak": (raw + cb) / td / 1e6 / peak,
+                         "roundtrip_mse": mse}
+            del c, y
+        except Exception as e:                                   # noqa: BLE001
+            res[name] = {"error": str(e)[:200]}
+    return {"workload": f"{n_groups} groups of 1024x128 per distribution", "distributions": res}
+
+
+def run_cuda(args, rank, world, local_rank):
+    all_cpus = bind_to_gpu_cpus(local_rank)
+    env = Env(args, rank, world, local_rank)
+    torch = env.torch
+    use_graph = not args.no_graph
+    spec = workload_spec(args.workload, world, rank, args.scale)
+    head = codec_roundtrip(env, spec, args.steps, args.warmup, use_graph, sample_clocks=True)
+    x = head.pop("_x")
+    e2e = None
+    if not args.no_e2e:
+        e2e = e2e_leg(env, spec, x, args.steps)
+    del x
+    torch.cuda.empty_cache()
+
+    aux = {}
+    wanted = [a for a in args.aux.split(",") if a and a != "none"]
+
+    def leg(name, fn):
+        env.barrier()
+        t0 = time.perf_counter()
+        try:
+            r = fn()
+        except Exception as e:                                   # noqa: BLE001 -- an auxiliary record must not cost the headline
+            r = {"error": f"{type(e).__name__}: {str(e)[:300]}"}
+        if isinstance(r, dict):
+            r["wall_s"] = round(time.perf_counter() - t0, 2)
+        aux[name] = r
+        torch.cuda.empty_cache()
+
+    if "cfg2" in wanted and args.workload != "cfg2":
+        def cfg2():
+            s2 = workload_spec("cfg2", world, rank, args.aux_scale)
+            r = codec_roundtrip(env, s2, max(1, min(args.steps, 4)), 3, use_graph, sample_clocks=True)
+            r.pop("_x")
+            return dict(r, workload=s2["label"], scaling="weak", unit=UNIT)
+        leg("cfg2", cfg2)
+    if "cfg5" in wanted:
+        leg("cfg5", lambda: aux_cfg5(env, use_graph))
+    if "tier" in wanted:
+        leg("tier", lambda: aux_tier(env))
+    if "ratios" in wanted:
+        if rank == 0:
+            leg("ratios", lambda: aux_ratios(env))
+        env.barrier()
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        os.sched_setaffinity(0, all_cpus)
+        cpu = cpu_roundtrip_rate(spec["group_elems"], args.cpu_seconds, os.cpu_count() or 1)
+        cpu.pop("seconds", None)
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": head["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": max(args.warmup, 3), "warmup_steps_run": head["warmup_steps_run"], "ms_per_step": head["ms_per_step"], "higher_is_better": True,
+                "scaling": spec["scaling"], "vs_baseline": None, "dtype": "f32+i8",
+                "data": "synthetic N(0,1) fp16 KV (torch seed 1234+rank)",
+                "config": {"workload": spec["label"], "group_elems": spec["group_elems"], "groups_per_rank": head["groups_per_rank"],
+                           "groups_total": head["groups_total"], "kv_bytes_per_step_total": head["kv_bytes_per_step_total"],
+                           "launch_chunk_groups": head["launch_chunk_groups"], "global_batch": spec["global_batch"],
+                           "parallelism": (f"layers split {world} ways (contiguous), no data-path collective; NCCL all-gather of the "
+                                           "page-table metadata on a side stream" if world > 1 else "single GPU"),
+                           "cuda_graph": head["graph"],
+                           "cache": "each step streams this rank's shard (input + payload + output > L2) once per direction; no flush needed"},
+                "per_gpu_value": head["per_gpu_value"], "per_rank_ms_per_step": head["per_rank_ms_per_step"],
+                "compression_ratio": head["compression_ratio"], "clocks": head["clocks"], "e2e": e2e,
+                "gpu_launches": head["gpu_launches"], "roofline": head["roofline"], "cpu_baseline": cpu, "aux": aux}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        env.dist.destroy_process_group()
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
-    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg3", "cfg4p", "cfg4", "cfg5", "ratios"])
-    ap.add_argument("--scale", type=float, default=1.0, help="fraction of the workload's layers (debug only; 1.0 = the named config)")
-    ap.add_argument("--e2e-mib", type=float, default=2048.0, help="host-buffer sample per e2e step (MiB of fp16 KV)")
+    ap.add_argument("--workload", default="cfg3", choices=["cfg2", "cfg3", "cfg4p"], help="headline workload")
+    ap.add_argument("--aux", default="cfg2,cfg5,tier,ratios", help="comma list of sub-records to add (or 'none')")
+    ap.add_argument("--scale", type=float, default=1.0, help="fraction of the headline workload's layers (debug only; cfg2 / cfg4p)")
+    ap.add_argument("--aux-scale", type=float, default=1.0, help="fraction of aux.cfg2's layers (debug only)")
+    ap.add_argument("--tier-scale", type=float, default=1.0, help="fraction of aux.tier's layers (debug only)")
+    ap.add_argument("--e2e-mib", type=float, default=2560.0, help="host-buffer sample per rank per e2e step (MiB of fp16 KV)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying CUDA graphs")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if args.workload == "cfg4":
-        run_cfg4(args, local_rank)
-    elif args.workload == "cfg5":
-        run_cfg5(args, rank, world, local_rank)
-    elif args.workload == "ratios":
-        run_ratios(args, local_rank)
-    elif args.impl == "reference":
+    if args.impl == "reference":
         run_reference(args, rank, world)
     else:
         run_cuda(args, rank, world, local_rank)

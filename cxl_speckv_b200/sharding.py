@@ -17,11 +17,12 @@ import torch.distributed as dist
 
 
 def shard_layers(n_layers: int, world: int, rank: int) -> List[int]:
-    """Round-robin layer ownership: layer l lives on rank l % world (what TP/PP serving
-    already does, so compressed blocks never cross NVLink)."""
+    """Contiguous layer ownership (80 / G contiguous layers per GPU): rank r holds layers
+    [r * n // world, (r + 1) * n // world) -- the split pipeline-parallel serving already uses, so compressed
+    blocks never cross NVLink."""
     if not 0 <= rank < world:
         raise ValueError("rank out of range")
-    return [l for l in range(n_layers) if l % world == rank]
+    return list(range(rank * n_layers // world, (rank + 1) * n_layers // world))
 
 
 def shard_groups(n_layers: int, groups_per_layer: int, world: int, rank: int) -> Tuple[List[int], int]:
@@ -30,8 +31,11 @@ def shard_groups(n_layers: int, groups_per_layer: int, world: int, rank: int) ->
     return layers, len(layers) * groups_per_layer
 
 
-def owner_of(layer: int, world: int) -> int:
-    return layer % world
+def owner_of(layer: int, n_layers: int, world: int) -> int:
+    """Rank that holds `layer` under the contiguous split."""
+    if not 0 <= layer < n_layers:
+        raise ValueError("layer out of range")
+    return ((layer + 1) * world - 1) // n_layers
 
 
 def gather_page_metadata(comp_bytes: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
@@ -48,10 +52,10 @@ def gather_page_metadata(comp_bytes: torch.Tensor, out: torch.Tensor | None = No
     return out.view(world, n)
 
 
-def global_block_location(layer: int, block_in_layer: int, groups_per_layer: int, world: int) -> Tuple[int, int]:
-    """(rank, local group index) of a block under round-robin layer sharding."""
-    rank = owner_of(layer, world)
-    local_layer = layer // world
+def global_block_location(layer: int, block_in_layer: int, groups_per_layer: int, n_layers: int, world: int) -> Tuple[int, int]:
+    """(rank, local group index) of a block under the contiguous layer split."""
+    rank = owner_of(layer, n_layers, world)
+    local_layer = layer - rank * n_layers // world
     return rank, local_layer * groups_per_layer + block_in_layer
 
 

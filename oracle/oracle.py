@@ -295,6 +295,14 @@ class Ref:
             L.ref_prefetcher_prefetch.restype = C.c_size_t
             L.ref_prefetcher_prefetch.argtypes = [C.c_void_p, _u32p, C.c_size_t, C.c_uint32, C.c_size_t,
                                                   _u64p, _u32p, _u32p, _f32p]
+            L.ref_prefetcher_mm_allocate.restype = C.c_uint64
+            L.ref_prefetcher_mm_allocate.argtypes = [C.c_void_p, C.c_size_t, C.c_uint32, C.c_int]
+            L.ref_prefetcher_mispredict.argtypes = [C.c_void_p, C.c_uint32, _u32p, C.c_size_t]
+            L.ref_prefetcher_stats.argtypes = [C.c_void_p, _u64p, _f64p, C.c_int]
+            L.ref_prefetcher_is_outstanding.restype = C.c_int
+            L.ref_prefetcher_is_outstanding.argtypes = [C.c_void_p, C.c_uint64]
+            L.ref_prefetcher_queue.restype = C.c_size_t
+            L.ref_prefetcher_queue.argtypes = [C.c_void_p, _u64p, _u32p, C.c_size_t]
             L.ref_kv_address.restype = C.c_uint64
             L.ref_kv_address.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32]
             L.ref_mm_new.restype = C.c_void_p

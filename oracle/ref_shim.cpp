@@ -222,6 +222,31 @@ uint64_t ref_kv_address(void* p, uint32_t req, uint32_t layer, uint32_t pos) {
     return static_cast<RefPrefetcher*>(p)->pf.compute_kv_address(req, layer, pos);
 }
 
+// the prefetcher's own memory manager, populated: allocate :28-82 (residency filter of prefetch(), :51-54)
+uint64_t ref_prefetcher_mm_allocate(void* p, size_t bytes, uint32_t layer, int tier) {
+    return static_cast<RefPrefetcher*>(p)->mm.allocate(bytes, layer, static_cast<cxlspeckv::MemoryTier>(tier));
+}
+// handle_misprediction :84-97, get_statistics :126-135, reset_statistics :137-142, is_already_prefetched :174-185
+void ref_prefetcher_mispredict(void* p, uint32_t actual, const uint32_t* predicted, size_t n) {
+    static_cast<RefPrefetcher*>(p)->pf.handle_misprediction(actual, std::vector<uint32_t>(predicted, predicted + n));
+}
+void ref_prefetcher_stats(void* p, uint64_t* counters3, double* rates3, int reset) {
+    auto& pf = static_cast<RefPrefetcher*>(p)->pf;
+    const auto s = pf.get_statistics();
+    counters3[0] = s.total_prefetches; counters3[1] = s.successful_prefetches; counters3[2] = s.mispredictions;
+    rates3[0] = s.hit_rate; rates3[1] = s.precision; rates3[2] = s.avg_prediction_latency_us;
+    if (reset) pf.reset_statistics();
+}
+int ref_prefetcher_is_outstanding(void* p, uint64_t va) {
+    return static_cast<RefPrefetcher*>(p)->pf.is_already_prefetched(va) ? 1 : 0;
+}
+size_t ref_prefetcher_queue(void* p, uint64_t* va, uint32_t* tok, size_t cap) {   // outstanding_prefetches_, oldest first
+    auto q = static_cast<RefPrefetcher*>(p)->pf.outstanding_prefetches_;
+    size_t n = 0;
+    while (!q.empty() && n < cap) { va[n] = q.front().virtual_addr; tok[n] = q.front().predicted_token_id; ++n; q.pop(); }
+    return n;
+}
+
 // ---- CXLMemoryManager page table (src/cxl_memory/cxl_memory_manager.cpp) ----
 void* ref_mm_new() { return new cxlspeckv::CXLMemoryManager(); }
 void ref_mm_free(void* m) { delete static_cast<cxlspeckv::CXLMemoryManager*>(m); }

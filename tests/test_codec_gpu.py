@@ -680,3 +680,39 @@ def test_memory_manager_address_map_on_device():
         assert int(f2[0]) & 1
     prod.close()
     P.oracle_mm_free(m)
+
+
+@pytest.mark.parametrize("G,n_groups,tdt", [(131072, 128, torch.float16), (131072, 128, torch.bfloat16),
+                                            (2048, 16384, torch.float16), (2048, 8192, torch.bfloat16)])
+def test_full_layer_bit_exact_against_reference_engine(G, n_groups, tdt):
+    """One whole Llama-2-70B layer (config 3: 2 x 8 KV heads x 8 blocks = 128 groups of 1024 x 128) and a config-4
+    layer slice (4 KiB page groups), EVERY group compared with the reference's own FPGACacheEngine (oracle/_ref,
+    else the C restatement): compressed bytes, sizes, scale bits and decoded bits.  A tenth of the groups carry
+    constant stretches (runs past the 255 cap) and zero tails, the rest is N(0,1)."""
+    from oracle.oracle import Ref
+    dcode = F16 if tdt == torch.float16 else BF16
+    gen = torch.Generator(device=DEV)
+    gen.manual_seed(99 + G)
+    x = torch.empty(n_groups * G, dtype=torch.float32, device=DEV).normal_(generator=gen).to(tdt).view(n_groups, G)
+    for g in range(0, n_groups, 10):
+        x[g, G // 3: G // 3 + 777] = 0.125
+        x[g, G - min(G // 4, 600):] = 0
+    x = x.reshape(-1).contiguous()
+    c = codec.compress(x, G)
+    y = codec.decompress(c)
+    torch.cuda.synchronize()
+    xh = x.view(torch.int16).cpu().numpy().view(np.uint16)
+    if Ref.available():
+        rp, rs, rc, ro = Ref.roundtrip_batch(xh, dcode, G, threads=8)
+    else:
+        xf = xh.view(np.float16) if dcode == F16 else xh
+        rp, rs, rc = Port.compress_batch(xf, G, dtype=dcode, threads=8)
+        ro, _ = Port.decompress_batch(rp, rs, rc, G, dcode, threads=8)
+        ro = ro.view(np.uint16).reshape(n_groups, G)
+    comp = c.comp_bytes.cpu().numpy().view(np.uint32)
+    assert np.array_equal(comp, rc)
+    assert np.array_equal(f32_bits(c.scales.cpu().numpy()), f32_bits(rs))
+    gp = c.payload.cpu().numpy()
+    mask = np.arange(gp.shape[1])[None, :] < comp[:, None]
+    assert np.array_equal(np.where(mask, gp, 0), np.where(mask, rp[:, :gp.shape[1]], 0))
+    assert np.array_equal(y.view(torch.int16).cpu().numpy().view(np.uint16), ro.view(np.uint16).reshape(n_groups, G))

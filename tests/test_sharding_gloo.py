@@ -36,7 +36,7 @@ def _worker(rank, world, port, n_layers, gpl, ret):
         ok = table.shape == (world, n_max)
         for layer in range(n_layers):
             for b in (0, gpl - 1):
-                r, idx = sharding.global_block_location(layer, b, gpl, world)
+                r, idx = sharding.global_block_location(layer, b, gpl, n_layers, world)
                 ok &= int(table[r, idx]) == 1_000_000 * r + 1000 * layer + b
         ok &= sorted(sum((sharding.shard_layers(n_layers, world, r) for r in range(world)), [])) == list(range(n_layers))
         ret[rank] = bool(ok)
@@ -55,9 +55,12 @@ def test_layer_sharding_and_metadata_allgather(n_layers, gpl):
 
 
 def test_single_process_paths():
-    assert sharding.shard_layers(80, 8, 3) == list(range(3, 80, 8))
-    assert sharding.owner_of(17, 4) == 1
-    assert sharding.global_block_location(17, 5, 128, 4) == (1, 4 * 128 + 5)
+    assert sharding.shard_layers(80, 8, 3) == list(range(30, 40))
+    assert sharding.owner_of(17, 80, 4) == 0 and sharding.owner_of(20, 80, 4) == 1 and sharding.owner_of(79, 80, 8) == 7
+    assert sharding.global_block_location(27, 5, 128, 80, 4) == (1, 7 * 128 + 5)
+    for n, w in ((80, 8), (5, 2), (7, 3), (3, 4)):
+        for l in range(n):
+            assert l in sharding.shard_layers(n, w, sharding.owner_of(l, n, w))
     t = torch.arange(6, dtype=torch.int32)
     assert torch.equal(sharding.gather_page_metadata(t), t.view(1, 6))
     with pytest.raises(ValueError):
