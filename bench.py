@@ -85,7 +85,8 @@ def ncu_traffic(kernel_key: str):
         return None
 
 
-SCHEME_IDS = {"fp16": 0, "int8": 1, "int8_delta_rle": 2}       # speckv_comp_scheme_t (host/include/speckv.h:59-63)
+# speckv_comp_scheme_t (host/include/speckv.h:59-63) + the extension ids of include/speckv_ext.h (non-wrapping quantiser)
+SCHEME_IDS = {"fp16": 0, "int8": 1, "int8_delta_rle": 2, "int8_clamp_delta_rle": 3, "int8_clamp": 4}
 
 
 class ClockSampler(threading.Thread):

@@ -8,6 +8,7 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 
 SPECKV_OK, SPECKV_ERR_GENERAL, SPECKV_ERR_DRIVER, SPECKV_ERR_NOMEM, SPECKV_ERR_INVAL = 0, -1, -2, -3, -4
 COMP_FP16, COMP_INT8, COMP_INT8_DELTA_RLE = 0, 1, 2
+COMP_INT8_CLAMP_DELTA_RLE, COMP_INT8_CLAMP = 3, 4   # extension ids (speckv_ext.h): the non-wrapping quantiser
 DTYPE_F16, DTYPE_BF16, DTYPE_F32 = 0, 1, 2
 
 _STATUS = {0: "SPECKV_OK", -1: "SPECKV_ERR_GENERAL", -2: "SPECKV_ERR_DRIVER", -3: "SPECKV_ERR_NOMEM",
@@ -23,7 +24,8 @@ class SpeckvError(RuntimeError):
 class Stats(C.Structure):
     _fields_ = [("total_compressions", C.c_uint64), ("total_decompressions", C.c_uint64),
                 ("total_translations", C.c_uint64), ("bytes_in_compress", C.c_uint64),
-                ("bytes_out_decompress", C.c_uint64), ("kernel_launches", C.c_uint64)]
+                ("bytes_out_decompress", C.c_uint64), ("kernel_launches", C.c_uint64),
+                ("host_api_h2d_bytes", C.c_uint64), ("host_api_d2h_bytes", C.c_uint64)]
 
 
 class TierStats(C.Structure):
@@ -179,6 +181,9 @@ def lib() -> C.CDLL:
     L.speckv_ext_prefetch_outstanding.argtypes = [u64p, sz, C.POINTER(C.c_uint8), C.POINTER(PrefetchRequest), u32p, vp]
     L.speckv_ext_prefetch_outstanding.restype = C.c_int
     L.speckv_ext_engine_stats.argtypes = [C.POINTER(EngineStats), C.c_int]; L.speckv_ext_engine_stats.restype = None
+    L.speckv_ext_tier_set_scheme.argtypes = [vp, C.c_int]; L.speckv_ext_tier_set_scheme.restype = C.c_int
+    L.speckv_ext_set_pool_dtype.argtypes = [C.c_uint64, C.c_int]; L.speckv_ext_set_pool_dtype.restype = C.c_int
+    L.speckv_ext_get_compression_scheme.argtypes = [C.POINTER(C.c_int)]; L.speckv_ext_get_compression_scheme.restype = C.c_int
     L.speckv_ext_get_stats.argtypes = [C.POINTER(Stats)]; L.speckv_ext_get_stats.restype = None
     L.speckv_ext_reset_stats.argtypes = []; L.speckv_ext_reset_stats.restype = None
     _LIB = L

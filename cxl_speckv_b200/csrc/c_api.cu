@@ -37,6 +37,8 @@ struct PoolBinding {               // device memory behind a handle + the host t
     speckv_tier_t* tier = nullptr;
     // KV layout of the region, [req][layer][kind][pos][head] x entry_bytes (vllm_speckv_backend.py:95-100)
     uint32_t num_layers = 0, num_tokens = 0, num_heads = 0, entry_bytes = 0;
+    speckv_dtype_t dtype = SPECKV_DTYPE_F16;   // element type of the pool (speckv_ext_set_pool_dtype): what the codec quantises
+    size_t page_elems() const { return kPageSize / (dtype == SPECKV_DTYPE_F32 ? 4 : 2); }
 };
 
 struct Runtime {
@@ -54,8 +56,6 @@ struct Runtime {
 static std::mutex g_mutex;
 static std::unique_ptr<Runtime> g_rt;
 
-constexpr size_t kPageElems = kPageSize / 2;   // one 4 KiB page = one group of 2048 fp16 values
-
 // make pages [p0, p1) of `a` resident in the bound pool: pages whose only copy is the compressed one
 // in the host tier (flag bit2 set, bits 0-1 clear) are restored, then marked L2 (the reference's
 // sync_fetch_page, speckv_allocator.cpp:115-138, with a real transfer behind it)
@@ -65,11 +65,14 @@ static speckv_status_t fetch_pages_locked(Runtime& rt, uint64_t handle, KvAlloca
     (void)handle;
     std::vector<uint64_t> ids;
     uint64_t run_start = p0;
-    auto flush = [&](uint64_t end) -> speckv_status_t {
+    // a run of pages to restore: they are marked resident only once their restore has succeeded (a failed restore
+    // must not leave stale pages looking valid to later speckv_access calls)
+    auto flush = [&]() -> speckv_status_t {
         if (ids.empty()) return SPECKV_OK;
-        speckv_status_t rc = speckv_ext_tier_restore(pb.tier, ids.data(), ids.size(), kPageElems, SPECKV_DTYPE_F16,
+        speckv_status_t rc = speckv_ext_tier_restore(pb.tier, ids.data(), ids.size(), pb.page_elems(), pb.dtype,
                                                      pb.d_base + run_start * kPageSize, st);
-        (void)end;
+        if (rc == SPECKV_OK)
+            for (uint64_t p = run_start; p < run_start + ids.size(); ++p) a.pages[p].flags |= kFlagL2;
         ids.clear();
         return rc;
     };
@@ -80,12 +83,12 @@ static speckv_status_t fetch_pages_locked(Runtime& rt, uint64_t handle, KvAlloca
             if (ids.empty()) run_start = p;
             ids.push_back(pg.virt_page_id);
         } else {
-            speckv_status_t rc = flush(p);
+            speckv_status_t rc = flush();
             if (rc != SPECKV_OK) return rc;
+            pg.flags |= kFlagL2;      // nothing to fetch: the reference's sync_fetch_page marks it L2 as well
         }
-        pg.flags |= kFlagL2;
     }
-    return flush(p1);
+    return flush();
 }
 
 Runtime* runtime_locked() { return g_rt.get(); }
@@ -240,8 +243,12 @@ speckv_status_t speckv_set_compression_scheme(speckv_comp_scheme_t scheme) {
     std::lock_guard<std::mutex> lock(g_mutex);
     if (!g_rt) return SPECKV_ERR_INVAL;
     if (g_rt->cuda_device < 0) return SPECKV_ERR_DRIVER;
-    if ((int)scheme < 0 || (int)scheme > 2) return SPECKV_ERR_DRIVER;  // the device has no such mode
+    if ((int)scheme < 0 || (int)scheme > 4) return SPECKV_ERR_DRIVER;  // the device has no such mode (3, 4: speckv_ext.h)
     g_rt->scheme = (int)scheme;
+    // a real switch: pages offloaded from now on are stored under this scheme (pages already in a tier keep the
+    // scheme they were stored under and restore through it)
+    for (auto& kv : g_rt->pools)
+        if (kv.second.tier) speckv_ext_tier_set_scheme(kv.second.tier, scheme);
     return SPECKV_OK;
 }
 
@@ -303,7 +310,9 @@ speckv_status_t speckv_ext_bind_pool(speckv_handle_t handle, void* d_base, size_
         pb.num_tokens = it->second.num_tokens;
         pb.num_heads = it->second.num_heads;
         pb.entry_bytes = it->second.entry_bytes;
+        pb.dtype = it->second.dtype;
     }
+    if (tier) speckv_ext_tier_set_scheme(tier, (speckv_comp_scheme_t)g_rt->scheme);
     g_rt->pools[handle] = pb;
     for (KvPage& pg : a->pages) pg.flags |= kFlagL1;   // the pool's current contents are the resident copy
     return SPECKV_OK;
@@ -323,6 +332,30 @@ speckv_status_t speckv_ext_set_kv_layout(speckv_handle_t handle, uint32_t num_la
     return SPECKV_OK;
 }
 
+speckv_status_t speckv_ext_set_pool_dtype(speckv_handle_t handle, speckv_dtype_t dtype) {
+    std::lock_guard<std::mutex> lock(g_mutex);
+    if (!g_rt) return SPECKV_ERR_INVAL;
+    auto it = g_rt->pools.find(handle);
+    if (it == g_rt->pools.end()) return SPECKV_ERR_GENERAL;
+    if ((int)dtype < 0 || (int)dtype > 2) return SPECKV_ERR_INVAL;
+    // pages stored under another element type would restore as garbage: refuse while any page lives only in the tier
+    if (dtype != it->second.dtype) {
+        KvAllocation* a = g_rt->table.find(handle);
+        if (a)
+            for (const KvPage& pg : a->pages)
+                if ((pg.flags & kFlagCompressed) && !(pg.flags & (kFlagL1 | kFlagL2))) return SPECKV_ERR_GENERAL;
+    }
+    it->second.dtype = dtype;
+    return SPECKV_OK;
+}
+
+speckv_status_t speckv_ext_get_compression_scheme(int* out_scheme) {
+    std::lock_guard<std::mutex> lock(g_mutex);
+    if (!g_rt || !out_scheme) return SPECKV_ERR_INVAL;
+    *out_scheme = g_rt->scheme;
+    return SPECKV_OK;
+}
+
 speckv_status_t speckv_ext_offload_pages(speckv_handle_t handle, uint64_t first_page, uint64_t n_pages, void* cuda_stream) {
     std::lock_guard<std::mutex> lock(g_mutex);
     if (!g_rt) return SPECKV_ERR_INVAL;
@@ -338,7 +371,7 @@ speckv_status_t speckv_ext_offload_pages(speckv_handle_t handle, uint64_t first_
     uint64_t run_start = first_page;
     auto flush = [&]() -> speckv_status_t {
         if (ids.empty()) return SPECKV_OK;
-        speckv_status_t rc = speckv_ext_tier_offload(pb.tier, pb.d_base + run_start * kPageSize, SPECKV_DTYPE_F16, kPageElems,
+        speckv_status_t rc = speckv_ext_tier_offload(pb.tier, pb.d_base + run_start * kPageSize, pb.dtype, pb.page_elems(),
                                                      ids.size(), ids.data(), cuda_stream);
         if (rc == SPECKV_OK)
             for (uint64_t p = run_start; p < run_start + ids.size(); ++p)

@@ -35,6 +35,12 @@ template <> __device__ __forceinline__ float narrow<float>(float v) { return v; 
 // returns the non-NaN operand, so with m starting at 0 it is the same function.
 __device__ __forceinline__ float absmax_step(float m, float x) { return fmaxf(m, fabsf(x)); }
 __device__ __forceinline__ float scale_from_max(float m) { return (m > 0.0f) ? __fdiv_rn(m, 127.0f) : 1.0f; }
+// The clamped schemes (ids 3 / 4: this library's extension, not reference behaviour) store s = max|x|: then
+// (x / s) * 127 spans [-127, 127], the clamp of cache_engine.cpp:192 never acts and the wrapping cast is the
+// identity on every code -- the quantiser below is the same code path with a different scale.
+__device__ __forceinline__ float scale_for(float m, bool max_scale) {
+    return max_scale ? ((m > 0.0f) ? m : 1.0f) : scale_from_max(m);
+}
 
 // ---- rounding + the wrapping cast ------------------------------------------------
 // std::round (half away from zero) then static_cast<int8_t>:

@@ -3,6 +3,7 @@
 // Thin argument checking + dispatch onto the sm_100a kernels.  No torch types,
 // no C++ types across the boundary.  There is no CPU fallback: without a usable
 // CUDA device every entry point returns SPECKV_ERR_DRIVER.
+#include <algorithm>
 #include <atomic>
 #include <cstdio>
 #include <cstdlib>
@@ -94,6 +95,7 @@ speckv_status_t status_of(cudaError_t e) {
 
 // ---- statistics ---------------------------------------------------------------------
 static std::atomic<uint64_t> g_n_comp{0}, g_n_decomp{0}, g_n_xlate{0}, g_b_comp{0}, g_b_decomp{0};
+static std::atomic<uint64_t> g_b_h2d{0}, g_b_d2h{0};   // bytes the *_host calls moved over PCIe
 std::atomic<uint64_t> g_kernel_launches{0};
 void count_launch(unsigned n) { g_kernel_launches += n; }
 
@@ -235,7 +237,7 @@ private:
 };
 
 static bool valid_common(int dtype, size_t group_elems, size_t n_groups, size_t slot_bytes, int scheme) {
-    if (dtype < 0 || dtype > 2 || scheme < 0 || scheme > 2) return false;
+    if (dtype < 0 || dtype > 2 || scheme < 0 || scheme > 4) return false;
     if (group_elems >= (1ull << 31) || n_groups >= (1ull << 32)) return false;
     if (scheme == 0 && dtype == DT_F32) return false;  // FP16 scheme is a raw 16-bit passthrough
     if (slot_bytes % 16 != 0 || slot_bytes < speckv_ext_slot_bytes(group_elems, (speckv_comp_scheme_t)scheme)) return false;
@@ -249,6 +251,7 @@ struct HostPipe {
     std::mutex mu;
     int device = -1;
     cudaStream_t st[kSlots] = {};
+    cudaEvent_t ev_meta[kSlots] = {};   // "the sizes of this slot's chunk are on the host"
     void* d_elems[kSlots] = {};
     void* d_payload[kSlots] = {};
     float* d_scales[kSlots] = {};
@@ -278,12 +281,16 @@ struct HostPipe {
             release();
             for (int i = 0; i < kSlots; ++i) {
                 if (st[i]) cudaStreamDestroy(st[i]);
+                if (ev_meta[i]) cudaEventDestroy(ev_meta[i]);
                 st[i] = nullptr;
+                ev_meta[i] = nullptr;
             }
             device = dev;
         }
-        for (int i = 0; i < kSlots; ++i)
+        for (int i = 0; i < kSlots; ++i) {
             if (!st[i] && (e = cudaStreamCreateWithFlags(&st[i], cudaStreamNonBlocking)) != cudaSuccess) return e;
+            if (!ev_meta[i] && (e = cudaEventCreateWithFlags(&ev_meta[i], cudaEventDisableTiming)) != cudaSuccess) return e;
+        }
         if (elems_bytes > cap_elems || payload_bytes > cap_payload || groups > cap_groups) {
             release();
             for (int i = 0; i < kSlots; ++i) {
@@ -318,6 +325,25 @@ static size_t chunk_groups(size_t group_bytes, size_t n_groups) {
     if (c < 1) c = 1;
     if (c > n_groups) c = n_groups;
     return c ? c : 1;
+}
+
+// Payload copies of the host-buffer calls.  The slots of a chunk are mostly empty when the data compresses, so the
+// copy follows the sizes: one copy of all slots when they are nearly full (or the groups are many and small: a
+// driver call per group would cost more than the bytes it saves), else one copy per group of just its payload
+// (rounded up to 16 bytes, never past the slot).  Returns the bytes moved.
+static uint64_t copy_payloads(void* dst, const void* src, size_t slot_bytes, const uint32_t* h_comp, size_t ng,
+                              cudaMemcpyKind kind, cudaStream_t st, cudaError_t& e) {
+    uint64_t sum = 0;
+    for (size_t g = 0; g < ng; ++g) sum += std::min<uint64_t>(((uint64_t)h_comp[g] + 15u) & ~15ull, slot_bytes);
+    if (ng > 4096 || sum * 4 >= (uint64_t)ng * slot_bytes * 3) {
+        e = cudaMemcpyAsync(dst, src, ng * slot_bytes, kind, st);
+        return (uint64_t)ng * slot_bytes;
+    }
+    for (size_t g = 0; g < ng && e == cudaSuccess; ++g) {
+        const size_t len = std::min<uint64_t>(((uint64_t)h_comp[g] + 15u) & ~15ull, slot_bytes);
+        if (len) e = cudaMemcpyAsync((char*)dst + g * slot_bytes, (const char*)src + g * slot_bytes, len, kind, st);
+    }
+    return sum;
 }
 
 // sum of payload sizes and sum of the per-group ratios original_size / compressed_size, where
@@ -381,7 +407,7 @@ int speckv_ext_device_count(void) { return device_count(); }
 const char* speckv_ext_version(void) { return "cxl-speckv-b200 0.1 (sm_100a)"; }
 
 size_t speckv_ext_slot_bytes(size_t group_elems, speckv_comp_scheme_t scheme) {
-    size_t b = (scheme == SPECKV_COMP_INT8) ? group_elems : 2 * group_elems;
+    size_t b = ((int)scheme == SPECKV_COMP_INT8 || (int)scheme == SPECKV_COMP_INT8_CLAMP) ? group_elems : 2 * group_elems;
     return (b + 15) / 16 * 16;
 }
 
@@ -520,11 +546,24 @@ speckv_status_t speckv_ext_compress_host(const void* h_in, speckv_dtype_t dtype,
     cudaError_t e = g_pipe.ensure(cg * gbytes + 16, cg * slot_bytes, cg);
     if (e != cudaSuccess) return status_of(e);
     size_t chunk = 0;
+    uint64_t moved_up = 0, moved_down = 0;
+    // the payload copy of a chunk is issued one chunk later, once its sizes have reached the host: the copy then
+    // moves the payload bytes, not the worst-case slots
+    size_t prev_g0 = 0, prev_ng = 0;
+    int prev_k = -1;
+    auto finish = [&](size_t g0, size_t ng, int k) {
+        cudaError_t e2 = cudaEventSynchronize(g_pipe.ev_meta[k]);
+        if (e2 == cudaSuccess)
+            moved_down += copy_payloads((char*)h_payload + g0 * slot_bytes, g_pipe.d_payload[k], slot_bytes, h_comp_bytes + g0, ng,
+                                        cudaMemcpyDeviceToHost, g_pipe.st[k], e2);
+        return e2;
+    };
     for (size_t g0 = 0; g0 < n_groups; g0 += cg, ++chunk) {
         const size_t ng = (n_groups - g0 < cg) ? n_groups - g0 : cg;
         const int k = (int)(chunk % HostPipe::kSlots);
         cudaStream_t st = g_pipe.st[k];
         if ((e = cudaMemcpyAsync(g_pipe.d_elems[k], (const char*)h_in + g0 * gbytes, ng * gbytes, cudaMemcpyHostToDevice, st)) != cudaSuccess) break;
+        moved_up += ng * gbytes;
         CodecArgs a;
         a.in = g_pipe.d_elems[k];
         a.payload = g_pipe.d_payload[k];
@@ -537,10 +576,16 @@ speckv_status_t speckv_ext_compress_host(const void* h_in, speckv_dtype_t dtype,
         a.scheme = scheme;
         a.sm_count = current_sm_count();
         if ((e = launch_compress(a, st)) != cudaSuccess) break;
-        if ((e = cudaMemcpyAsync((char*)h_payload + g0 * slot_bytes, g_pipe.d_payload[k], ng * slot_bytes, cudaMemcpyDeviceToHost, st)) != cudaSuccess) break;
-        if ((e = cudaMemcpyAsync(h_scales + g0, g_pipe.d_scales[k], ng * sizeof(float), cudaMemcpyDeviceToHost, st)) != cudaSuccess) break;
         if ((e = cudaMemcpyAsync(h_comp_bytes + g0, g_pipe.d_comp[k], ng * sizeof(uint32_t), cudaMemcpyDeviceToHost, st)) != cudaSuccess) break;
+        if ((e = cudaEventRecord(g_pipe.ev_meta[k], st)) != cudaSuccess) break;
+        if ((e = cudaMemcpyAsync(h_scales + g0, g_pipe.d_scales[k], ng * sizeof(float), cudaMemcpyDeviceToHost, st)) != cudaSuccess) break;
+        moved_down += ng * 8;
+        if (prev_k >= 0 && (e = finish(prev_g0, prev_ng, prev_k)) != cudaSuccess) break;
+        prev_g0 = g0;
+        prev_ng = ng;
+        prev_k = k;
     }
+    if (e == cudaSuccess && prev_k >= 0) e = finish(prev_g0, prev_ng, prev_k);
     for (int k = 0; k < HostPipe::kSlots; ++k) {
         cudaError_t e2 = cudaStreamSynchronize(g_pipe.st[k]);
         if (e == cudaSuccess) e = e2;
@@ -548,6 +593,8 @@ speckv_status_t speckv_ext_compress_host(const void* h_in, speckv_dtype_t dtype,
     if (e == cudaSuccess) {
         g_n_comp += n_groups;
         g_b_comp += (uint64_t)n_groups * gbytes;
+        g_b_h2d += moved_up;
+        g_b_d2h += moved_down;
     }
     return status_of(e);
 }
@@ -565,12 +612,17 @@ speckv_status_t speckv_ext_decompress_host(const void* h_payload, size_t slot_by
     std::lock_guard<std::mutex> lk(g_pipe.mu);
     cudaError_t e = g_pipe.ensure(cg * gbytes + 16, cg * slot_bytes, cg);
     if (e != cudaSuccess) return status_of(e);
+    uint64_t moved_up = 0, moved_down = 0;
     size_t chunk = 0;
     for (size_t g0 = 0; g0 < n_groups; g0 += cg, ++chunk) {
         const size_t ng = (n_groups - g0 < cg) ? n_groups - g0 : cg;
         const int k = (int)(chunk % HostPipe::kSlots);
         cudaStream_t st = g_pipe.st[k];
-        if ((e = cudaMemcpyAsync(g_pipe.d_payload[k], (const char*)h_payload + g0 * slot_bytes, ng * slot_bytes, cudaMemcpyHostToDevice, st)) != cudaSuccess) break;
+        moved_up += copy_payloads(g_pipe.d_payload[k], (const char*)h_payload + g0 * slot_bytes, slot_bytes, h_comp_bytes + g0, ng,
+                                  cudaMemcpyHostToDevice, st, e);
+        if (e != cudaSuccess) break;
+        moved_up += ng * 8;
+        moved_down += ng * gbytes + (h_out_elems ? ng * 4 : 0);
         if ((e = cudaMemcpyAsync(g_pipe.d_scales[k], h_scales + g0, ng * sizeof(float), cudaMemcpyHostToDevice, st)) != cudaSuccess) break;
         if ((e = cudaMemcpyAsync(g_pipe.d_comp[k], h_comp_bytes + g0, ng * sizeof(uint32_t), cudaMemcpyHostToDevice, st)) != cudaSuccess) break;
         CodecArgs a;
@@ -596,6 +648,8 @@ speckv_status_t speckv_ext_decompress_host(const void* h_payload, size_t slot_by
     if (e == cudaSuccess) {
         g_n_decomp += n_groups;
         g_b_decomp += (uint64_t)n_groups * gbytes;
+        g_b_h2d += moved_up;
+        g_b_d2h += moved_down;
     }
     return status_of(e);
 }
@@ -631,6 +685,8 @@ void speckv_ext_get_stats(speckv_ext_stats_t* out) {
     out->bytes_in_compress = g_b_comp.load();
     out->bytes_out_decompress = g_b_decomp.load();
     out->kernel_launches = g_kernel_launches.load();
+    out->host_api_h2d_bytes = g_b_h2d.load();
+    out->host_api_d2h_bytes = g_b_d2h.load();
 }
 
 void speckv_ext_engine_stats(speckv_engine_stats_t* out, int wait) {
@@ -669,6 +725,8 @@ void speckv_ext_reset_stats(void) {
     g_n_xlate = 0;
     g_b_comp = 0;
     g_b_decomp = 0;
+    g_b_h2d = 0;
+    g_b_d2h = 0;
     g_kernel_launches = 0;
 }
 

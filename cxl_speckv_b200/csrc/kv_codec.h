@@ -26,9 +26,15 @@ struct CodecArgs {
     uint32_t group_elems = 0;
     uint32_t n_groups = 0;
     int dtype = 0;                   // DT_F16 / DT_BF16 / DT_F32
-    int scheme = 2;                  // speckv_comp_scheme_t
+    int scheme = 2;                  // speckv_comp_scheme_t, or one of the extension ids 3 / 4 (speckv_ext.h)
     int sm_count = 148;
 };
+
+// scheme ids: 0 raw 16-bit passthrough, 1 codes only, 2 codes + delta + RLE (the reference's three), and the clamped
+// variants of 2 and 1 that store s = max|x| (3, 4)
+inline bool scheme_is_rle(int s) { return s == 2 || s == 3; }
+inline bool scheme_is_codes(int s) { return s == 1 || s == 4; }
+inline bool scheme_max_scale(int s) { return s == 3 || s == 4; }
 
 // any geometry, any alignment (kv_codec_generic.cu)
 // `only_flagged` (optional, device): process group g only if only_flagged[g] != 0

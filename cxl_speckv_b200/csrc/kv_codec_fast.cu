@@ -560,7 +560,7 @@ template <typename T, int R>
 __global__ void __launch_bounds__(kThreadsF, kCtasPerSm)
 compress_fast_kernel(const T* __restrict__ in, uint32_t n_groups, uint8_t* __restrict__ payload, size_t slot_bytes,
                      float* __restrict__ scales, uint32_t* __restrict__ comp_bytes,
-                     uint32_t* __restrict__ needs_generic, const uint32_t* __restrict__ elem_index) {
+                     uint32_t* __restrict__ needs_generic, const uint32_t* __restrict__ elem_index, uint32_t max_scale) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     FastSmem& sm = *reinterpret_cast<FastSmem*>(smem_raw);
     constexpr int C = R > kW ? R / kW : 1;        // CTAs per group (cluster size)
@@ -617,7 +617,7 @@ compress_fast_kernel(const T* __restrict__ in, uint32_t n_groups, uint8_t* __res
     uint32_t t0, t1, gmax_bits;
     group_reduce<R>(sm.xa, warp, lane, ridx, t0, t1, gmax_bits);
     const float gmax = __uint_as_float(gmax_bits);
-    const float s = scale_from_max(gmax);
+    const float s = scale_for(gmax, max_scale != 0u);   // max / 127 (the reference), or max for the clamped scheme
     const bool fast = fast_quant_ok<T>(gmax);
     // a group whose max-abs is 0 (zeros, possibly NaNs: cache_engine.cpp:176-179 skips them and the cast maps
     // them to code 0) has the closed-form payload [0][255] x floor(G/255) + [0][G%255]: no second read
@@ -1120,6 +1120,168 @@ decompress_fast_kernel(const uint8_t* __restrict__ payload, size_t slot_bytes, c
     flush_region(sbase, gout, (int)e0, (int)ecur, lane);   // (an early partial flush, as in compress, measured slower here)
 }
 
+// ===================================================================================
+// codes-only schemes (INT8 and its clamped variant): quantize_to_int8 / dequantize_from_int8 alone
+// (cache_engine.cpp:186-196, :275-284).  Compress is the kernel above without its second half: one bulk-TMA load per
+// region, region max, one exchange for the group max, eight codes per lane and iteration written in place, one
+// bulk-TMA store of the region's 2 KiB.  Decompress has no dependency between regions at all: no cluster, no exchange.
+// Algorithmic traffic: 2n + n bytes per group either way.
+// ===================================================================================
+template <typename T, int R>
+__global__ void __launch_bounds__(kThreadsF, kCtasPerSm)
+compress_codes_fast_kernel(const T* __restrict__ in, uint32_t n_groups, uint8_t* __restrict__ payload, size_t slot_bytes,
+                           float* __restrict__ scales, uint32_t* __restrict__ comp_bytes,
+                           uint32_t* __restrict__ needs_generic, const uint32_t* __restrict__ elem_index, uint32_t max_scale) {
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    FastSmem& sm = *reinterpret_cast<FastSmem*>(smem_raw);
+    constexpr int C = R > kW ? R / kW : 1;
+    constexpr int GPC = R >= kW ? 1 : kW / R;
+    constexpr uint32_t G = (uint32_t)R * kRegion;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint32_t g;
+    int ridx;
+    if (R >= kW) {
+        const unsigned crank = C > 1 ? cg::this_cluster().block_rank() : 0u;
+        g = blockIdx.x / C;
+        ridx = (int)crank * kW + warp;
+    } else {
+        g = blockIdx.x * GPC + warp / R;
+        ridx = warp % R;
+    }
+    const bool active = g < n_groups;
+    const T* rin = in + (size_t)((elem_index && active) ? elem_index[g] : g) * G + (size_t)ridx * kRegion;
+    uint8_t* reg = sm.tile[warp] + kPadBytes;
+    const uint32_t reg_s = smem_u32(reg);
+    const uint32_t mb = smem_u32(&sm.mbar[warp]);
+    if (lane == 0) {
+        mbar_init(mb, 1);
+        if (active) {
+            mbar_expect_tx(mb, kRegionBytes);
+            tma_load_1d(reg_s, rin, kRegionBytes, mb);
+        }
+    }
+    __syncwarp();
+    exchange_init<R>(sm, 1, 0);
+    float m = 0.0f;
+    if (active) {
+        mbar_wait(mb, 0);
+        const uint32_t z = 0u;
+        typename Pack2<T>::type pm = *reinterpret_cast<const typename Pack2<T>::type*>(&z);
+#pragma unroll
+        for (int k = 0; k < kIters; ++k) pm = absmax8<T>(pm, lds128(reg + k * 512 + lane * 16));
+        m = __uint_as_float(__reduce_max_sync(kFull, __float_as_uint(pack_max_to_float(pm))));
+    }
+    if (C > 1) cluster_wait();
+    group_publish<R>(sm, sm.xa, 0, warp, lane, ridx, __float_as_uint(m));
+    group_sync<R>(sm, 0);
+    uint32_t t0, t1, gmax_bits;
+    group_reduce<R>(sm.xa, warp, lane, ridx, t0, t1, gmax_bits);
+    if (!active) return;
+    const float gmax = __uint_as_float(gmax_bits);
+    const float s = scale_for(gmax, max_scale != 0u);
+    const bool zero_group = gmax_bits == 0u;                 // zeros / NaNs only: every code is 0 (scale 1)
+    const bool fast = fast_quant_ok<T>(gmax) || zero_group;
+    if (ridx == 0 && lane == 0) {
+        needs_generic[g] = fast ? 0u : 1u;
+        if (!fast) comp_bytes[g] = gmax_bits;                // the generic second pass skips its own max pass
+    }
+    if (!fast) return;
+    float r, rl;
+    recip_hi_lo(s, r, rl);
+    uint32_t half_k = HalfConst<T>::k;
+    asm volatile("" : "+r"(half_k));
+#pragma unroll
+    for (int k = 0; k < kIters; ++k) {
+        const uint4 raw = lds128(reg + k * 512 + lane * 16);
+        __syncwarp();   // the codes of this iteration land on bytes that iterations <= k read
+        float x[8];
+        unpack8<T>(raw, x);
+        uint32_t q[8];
+        const uint32_t rw[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) quantize_fast_pair_i<T>(rw[j], x[2 * j], x[2 * j + 1], r, rl, half_k, q[2 * j], q[2 * j + 1]);
+        const uint32_t c0 = __byte_perm(__byte_perm(q[0], q[1], 0x0040), __byte_perm(q[2], q[3], 0x0040), 0x5410);
+        const uint32_t c1 = __byte_perm(__byte_perm(q[4], q[5], 0x0040), __byte_perm(q[6], q[7], 0x0040), 0x5410);
+        *reinterpret_cast<uint2*>(reg + k * 256 + lane * 8) = make_uint2(c0, c1);
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncwarp();
+    if (lane == 0) {
+        uint8_t* gout = payload + (size_t)g * slot_bytes + (size_t)ridx * kRegion;
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gout), "r"(reg_s), "r"((uint32_t)kRegion)
+                     : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        if (ridx == 0) {
+            scales[g] = s;
+            comp_bytes[g] = G;
+        }
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    }
+}
+
+// one warp per region of 2048 codes; `regions` = R of the group geometry (any value: regions are independent)
+template <typename T>
+__global__ void __launch_bounds__(kThreadsF, kCtasPerSm)
+decompress_codes_fast_kernel(const uint8_t* __restrict__ payload, size_t slot_bytes, const float* __restrict__ scales,
+                             const uint32_t* __restrict__ comp_bytes, uint32_t n_groups, uint32_t regions, T* __restrict__ out,
+                             uint32_t* __restrict__ out_elems, uint32_t* __restrict__ needs_generic,
+                             const uint32_t* __restrict__ src_index, const uint64_t* __restrict__ slot_offsets,
+                             const uint32_t* __restrict__ elem_index, const uint32_t* __restrict__ n_groups_dev) {
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    FastSmem& sm = *reinterpret_cast<FastSmem*>(smem_raw);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint64_t rid = (uint64_t)blockIdx.x * kW + warp;
+    const uint32_t g = (uint32_t)(rid / regions), ridx = (uint32_t)(rid % regions);
+    const uint32_t G = regions * (uint32_t)kRegion;
+    const bool in_grid = g < n_groups;
+    const bool active = in_grid && (!n_groups_dev || g < *n_groups_dev);
+    if (!in_grid) return;
+    uint32_t gi = g;
+    float s = 1.0f;
+    bool cplx = false;
+    if (active) {
+        if (src_index) gi = src_index[g];
+        s = scales[gi];
+        // short or oversized payloads and non-finite scales: the generic kernel's clamping / special values
+        cplx = comp_bytes[gi] != G || (size_t)G > slot_bytes || scale_is_special(s);
+    }
+    if (ridx == 0 && lane == 0) {
+        needs_generic[g] = (active && cplx) ? 1u : 0u;
+        if (out_elems && active && !cplx) out_elems[g] = G;
+    }
+    if (!active || cplx) return;
+    uint8_t* reg = sm.tile[warp] + kPadBytes;
+    const uint32_t reg_s = smem_u32(reg);
+    const uint32_t mb = smem_u32(&sm.mbar[warp]);
+    const uint8_t* rp = payload + (slot_offsets ? (size_t)slot_offsets[gi] : (size_t)gi * slot_bytes) + (size_t)ridx * kRegion;
+    if (lane == 0) {
+        mbar_init(mb, 1);
+        mbar_expect_tx(mb, (uint32_t)kRegion);
+        tma_load_1d(reg_s + (uint32_t)kRegion, rp, (uint32_t)kRegion, mb);   // codes in the upper half: expansion runs in place
+    }
+    __syncwarp();
+    mbar_wait(mb, 0);
+#pragma unroll
+    for (int k = 0; k < kIters; ++k) {
+        const uint2 c = *reinterpret_cast<const uint2*>(reg + kRegion + k * 256 + lane * 8);
+        __syncwarp();   // iteration 7 writes over the codes it reads
+        float y[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) y[j] = dequantize(((j < 4 ? c.x : c.y) >> (8 * (j & 3))) & 0xffu, s);
+        *reinterpret_cast<uint4*>(reg + k * 512 + lane * 16) =
+            make_uint4(pack2_out<T>(y[0], y[1]), pack2_out<T>(y[2], y[3]), pack2_out<T>(y[4], y[5]), pack2_out<T>(y[6], y[7]));
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncwarp();
+    if (lane == 0) {
+        T* gout = out + (size_t)(elem_index ? elem_index[g] : g) * G + (size_t)ridx * kRegion;
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gout), "r"(reg_s), "r"((uint32_t)kRegionBytes)
+                     : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    }
+}
+
 // ---- launch -------------------------------------------------------------------------
 template <typename K>
 cudaError_t launch_clustered(K kernel, int R, uint32_t n_groups, cudaStream_t st, void** args) {
@@ -1163,7 +1325,16 @@ cudaError_t compress_fast_t(int R, const CodecArgs& a, uint32_t* flags, cudaStre
     float* sc = a.scales;
     uint32_t* cb = a.comp_bytes;
     const uint32_t* ei = a.elem_index;
-    void* args[] = {&in, &n, &pay, &sb, &sc, &cb, &flags, &ei};
+    uint32_t ms = scheme_max_scale(a.scheme) ? 1u : 0u;
+    void* args[] = {&in, &n, &pay, &sb, &sc, &cb, &flags, &ei, &ms};
+    if (scheme_is_codes(a.scheme)) {
+        switch (R) {
+#define SPECKV_CASE(RR) case RR: return launch_clustered(compress_codes_fast_kernel<T, RR>, RR, n, st, args);
+            SPECKV_CASE(1) SPECKV_CASE(2) SPECKV_CASE(4) SPECKV_CASE(8) SPECKV_CASE(16) SPECKV_CASE(32) SPECKV_CASE(64) SPECKV_CASE(128)
+#undef SPECKV_CASE
+            default: return cudaErrorInvalidValue;
+        }
+    }
     switch (R) {
 #define SPECKV_CASE(RR) case RR: return launch_clustered(compress_fast_kernel<T, RR>, RR, n, st, args);
         SPECKV_CASE(1) SPECKV_CASE(2) SPECKV_CASE(4) SPECKV_CASE(8) SPECKV_CASE(16) SPECKV_CASE(32) SPECKV_CASE(64) SPECKV_CASE(128)
@@ -1185,6 +1356,16 @@ cudaError_t decompress_fast_t(int R, const CodecArgs& a, uint32_t* flags, cudaSt
     const uint64_t* so = a.slot_offsets;
     const uint32_t* ei = a.elem_index;
     const uint32_t* nd = a.n_groups_dev;
+    if (scheme_is_codes(a.scheme)) {
+        const size_t smem = sizeof(FastSmem);
+        cudaError_t e = cudaFuncSetAttribute(decompress_codes_fast_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        const uint64_t regions = (uint64_t)n * (uint32_t)R;
+        decompress_codes_fast_kernel<T><<<(unsigned)((regions + kW - 1) / kW), kThreadsF, smem, st>>>(
+            pay, sb, sc, cb, n, (uint32_t)R, out, oe, flags, si, so, ei, nd);
+        count_launch();
+        return cudaGetLastError();
+    }
     void* args[] = {&pay, &sb, &sc, &cb, &n, &out, &oe, &flags, &si, &so, &ei, &nd};
     switch (R) {
 #define SPECKV_CASE(RR) case RR: return launch_clustered(decompress_fast_kernel<T, RR>, RR, n, st, args);
@@ -1198,14 +1379,15 @@ cudaError_t decompress_fast_t(int R, const CodecArgs& a, uint32_t* flags, cudaSt
 
 // regions per group if the tuned kernels cover this geometry, else 0
 int fast_regions(const CodecArgs& a, bool decompress) {
-    if (a.scheme != 2 || (a.dtype != DT_F16 && a.dtype != DT_BF16)) return 0;
+    if (!(scheme_is_rle(a.scheme) || scheme_is_codes(a.scheme)) || (a.dtype != DT_F16 && a.dtype != DT_BF16)) return 0;
     if (a.group_elems == 0 || a.group_elems % kRegion) return 0;
     const uint32_t R = a.group_elems / kRegion;
     if (R > 128 || (R & (R - 1))) return 0;
     if (R > (uint32_t)kW * 8) return 0;   // portable cluster size limit (8 CTAs)
     const void* elems = decompress ? a.out : a.in;
     if ((reinterpret_cast<uintptr_t>(elems) | reinterpret_cast<uintptr_t>(a.payload)) & 15) return 0;
-    if (a.slot_bytes < (size_t)R * kRegionBytes) return 0;
+    if (a.slot_bytes < (size_t)R * (scheme_is_codes(a.scheme) ? kRegion : kRegionBytes)) return 0;
+    if ((uint64_t)a.n_groups * R >= (1ull << 31) * (uint64_t)kW) return 0;   // grid of the codes-only decode
     return (int)R;
 }
 

@@ -182,7 +182,8 @@ __global__ void __launch_bounds__(kThreads)
 compress_rle_generic_kernel(const T* __restrict__ in, uint32_t G, uint32_t n_groups,
                             uint8_t* __restrict__ payload, size_t slot_bytes,
                             float* __restrict__ scales, uint32_t* __restrict__ comp_bytes,
-                            const uint32_t* __restrict__ only_flagged, const uint32_t* __restrict__ elem_index) {
+                            const uint32_t* __restrict__ only_flagged, const uint32_t* __restrict__ elem_index,
+                            bool max_scale) {
     __shared__ __align__(16) uint16_t stage[kTile + 16];
     __shared__ int wbuf[kWarps];
     __shared__ float fbuf[kWarps];
@@ -200,7 +201,7 @@ compress_rle_generic_kernel(const T* __restrict__ in, uint32_t G, uint32_t n_gro
         // second pass behind the tuned kernel: that kernel already took the group max and left its bits in
         // comp_bytes[g] (overwritten with the size below), so the input is read once here, not twice
         const float m = only_flagged ? __uint_as_float(comp_bytes[g]) : group_absmax<T>(gin, G, vec_ok, fbuf);
-        const float s = scale_from_max(m);
+        const float s = scale_for(m, max_scale);
         const bool fast = fast_quant_ok<T>(m);
         float r = 0.0f, rl = 0.0f;
         if (fast) recip_hi_lo(s, r, rl);
@@ -434,15 +435,19 @@ __global__ void __launch_bounds__(kThreads)
 compress_int8_generic_kernel(const T* __restrict__ in, uint32_t G, uint32_t n_groups,
                              uint8_t* __restrict__ payload, size_t slot_bytes,
                              float* __restrict__ scales, uint32_t* __restrict__ comp_bytes,
-                             const uint32_t* __restrict__ elem_index) {
+                             const uint32_t* __restrict__ only_flagged, const uint32_t* __restrict__ elem_index,
+                             bool max_scale) {
     __shared__ float fbuf[kWarps];
+    __shared__ uint32_t smask[kWarps];
     const int tid = threadIdx.x;
-    for (uint32_t g = blockIdx.x; g < n_groups; g += gridDim.x) {
+    GroupIter it(only_flagged, n_groups, smask);
+    for (uint32_t g; it.next(g);) {
         const T* gin = in + (size_t)(elem_index ? elem_index[g] : g) * G;
         uint8_t* gout = payload + (size_t)g * slot_bytes;
         const bool vec_ok = (reinterpret_cast<uintptr_t>(gin) & 15) == 0;
-        const float m = group_absmax<T>(gin, G, vec_ok, fbuf);
-        const float s = scale_from_max(m);
+        // behind the tuned kernel the group max is already known (left in comp_bytes[g])
+        const float m = only_flagged ? __uint_as_float(comp_bytes[g]) : group_absmax<T>(gin, G, vec_ok, fbuf);
+        const float s = scale_for(m, max_scale);
         const bool fast = fast_quant_ok<T>(m);
         float r = 0.0f, rl = 0.0f;
         if (fast) recip_hi_lo(s, r, rl);
@@ -474,13 +479,16 @@ __global__ void __launch_bounds__(kThreads)
 decompress_int8_generic_kernel(const uint8_t* __restrict__ payload, size_t slot_bytes,
                                const float* __restrict__ scales, const uint32_t* __restrict__ comp_bytes,
                                uint32_t G, uint32_t n_groups, T* __restrict__ out,
-                               uint32_t* __restrict__ out_elems, const uint32_t* __restrict__ src_index,
+                               uint32_t* __restrict__ out_elems, const uint32_t* __restrict__ only_flagged,
+                               const uint32_t* __restrict__ src_index, const uint64_t* __restrict__ slot_offsets,
                                const uint32_t* __restrict__ elem_index, const uint32_t* __restrict__ n_groups_dev) {
+    __shared__ uint32_t smask[kWarps];
     const int tid = threadIdx.x;
     if (n_groups_dev) n_groups = min(n_groups, *n_groups_dev);
-    for (uint32_t g = blockIdx.x; g < n_groups; g += gridDim.x) {
+    GroupIter it(only_flagged, n_groups, smask);
+    for (uint32_t g; it.next(g);) {
         const uint32_t gi = src_index ? src_index[g] : g;
-        const uint8_t* gp = payload + (size_t)gi * slot_bytes;
+        const uint8_t* gp = payload + (slot_offsets ? (size_t)slot_offsets[gi] : (size_t)gi * slot_bytes);
         const uint32_t n = min(min(comp_bytes[gi], G), (uint32_t)slot_bytes);
         const float s = scales[gi];
         T* gout = out + (size_t)(elem_index ? elem_index[g] : g) * G;
@@ -492,13 +500,28 @@ decompress_int8_generic_kernel(const uint8_t* __restrict__ payload, size_t slot_
 }
 
 // scheme FP16: raw 16-bit passthrough of fp16 / bf16 groups
+// raw copy of whole groups into their slots (and the metadata), 16 bytes per thread and step when both sides allow
 __global__ void __launch_bounds__(kThreads)
-passthrough_meta_kernel(uint32_t n_groups, uint32_t bytes, float* __restrict__ scales,
-                        uint32_t* __restrict__ comp_bytes) {
-    const uint32_t g = blockIdx.x * kThreads + threadIdx.x;
-    if (g < n_groups) {
+passthrough_in_kernel(const uint16_t* __restrict__ in, uint32_t G, uint32_t n_groups, uint8_t* __restrict__ payload,
+                      size_t slot_bytes, float* __restrict__ scales, uint32_t* __restrict__ comp_bytes) {
+    const bool vec_ok = ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(payload) | slot_bytes) & 15) == 0 && G % 8 == 0;
+    const uint64_t vec_per_group = G / 8;
+    if (vec_ok) {
+        const uint64_t total = (uint64_t)n_groups * vec_per_group;
+        for (uint64_t v = (uint64_t)blockIdx.x * kThreads + threadIdx.x; v < total; v += (uint64_t)gridDim.x * kThreads) {
+            const uint64_t g = v / vec_per_group, k = v - g * vec_per_group;
+            reinterpret_cast<uint4*>(payload + g * slot_bytes)[k] = ldg_stream(reinterpret_cast<const uint4*>(in) + v);
+        }
+    } else {
+        const uint64_t total = (uint64_t)n_groups * G;
+        for (uint64_t e = (uint64_t)blockIdx.x * kThreads + threadIdx.x; e < total; e += (uint64_t)gridDim.x * kThreads) {
+            const uint64_t g = e / G, k = e - g * G;
+            reinterpret_cast<uint16_t*>(payload + g * slot_bytes)[k] = in[e];
+        }
+    }
+    for (uint32_t g = blockIdx.x * kThreads + threadIdx.x; g < n_groups; g += gridDim.x * kThreads) {
         scales[g] = 1.0f;
-        comp_bytes[g] = bytes;
+        comp_bytes[g] = G * 2u;
     }
 }
 
@@ -506,11 +529,12 @@ __global__ void __launch_bounds__(kThreads)
 passthrough_out_kernel(const uint8_t* __restrict__ payload, size_t slot_bytes,
                        const uint32_t* __restrict__ comp_bytes, uint32_t G, uint32_t n_groups,
                        uint16_t* __restrict__ out, uint32_t* __restrict__ out_elems,
-                       const uint32_t* __restrict__ src_index, const uint32_t* __restrict__ n_groups_dev) {
+                       const uint32_t* __restrict__ src_index, const uint64_t* __restrict__ slot_offsets,
+                       const uint32_t* __restrict__ n_groups_dev) {
     if (n_groups_dev) n_groups = min(n_groups, *n_groups_dev);
     for (uint32_t g = blockIdx.x; g < n_groups; g += gridDim.x) {
         const uint32_t gi = src_index ? src_index[g] : g;
-        const uint16_t* gp = reinterpret_cast<const uint16_t*>(payload + (size_t)gi * slot_bytes);
+        const uint16_t* gp = reinterpret_cast<const uint16_t*>(payload + (slot_offsets ? (size_t)slot_offsets[gi] : (size_t)gi * slot_bytes));
         const uint32_t n = min(min(comp_bytes[gi] >> 1, G), (uint32_t)(slot_bytes >> 1));
         for (uint32_t i = threadIdx.x; i < n; i += kThreads) out[(size_t)g * G + i] = gp[i];
         if (threadIdx.x == 0 && out_elems) out_elems[g] = n;
@@ -529,12 +553,14 @@ static cudaError_t launch_compress_t(const CodecArgs& a, cudaStream_t st, const 
     const T* in = static_cast<const T*>(a.in);
     uint8_t* pay = static_cast<uint8_t*>(a.payload);
     const int grid = grid_for(a.n_groups, a.sm_count, 8);
-    if (a.scheme == 2) {
+    if (scheme_is_rle(a.scheme)) {
         compress_rle_generic_kernel<T><<<grid, kThreads, 0, st>>>(in, a.group_elems, a.n_groups, pay, a.slot_bytes,
-                                                                  a.scales, a.comp_bytes, only_flagged, a.elem_index);
+                                                                  a.scales, a.comp_bytes, only_flagged, a.elem_index,
+                                                                  scheme_max_scale(a.scheme));
     } else {
         compress_int8_generic_kernel<T><<<grid, kThreads, 0, st>>>(in, a.group_elems, a.n_groups, pay, a.slot_bytes,
-                                                                   a.scales, a.comp_bytes, a.elem_index);
+                                                                   a.scales, a.comp_bytes, only_flagged, a.elem_index,
+                                                                   scheme_max_scale(a.scheme));
     }
     count_launch();
     return cudaGetLastError();
@@ -545,14 +571,14 @@ static cudaError_t launch_decompress_t(const CodecArgs& a, cudaStream_t st, cons
     T* out = static_cast<T*>(a.out);
     const uint8_t* pay = static_cast<const uint8_t*>(a.payload);
     const int grid = grid_for(a.n_groups, a.sm_count, 8);
-    if (a.scheme == 2) {
+    if (scheme_is_rle(a.scheme)) {
         decompress_rle_generic_kernel<T><<<grid, kThreads, 0, st>>>(pay, a.slot_bytes, a.scales, a.comp_bytes,
                                                                     a.group_elems, a.n_groups, out, a.out_elems, only_flagged, a.src_index,
                                                                     a.slot_offsets, a.elem_index, a.n_groups_dev);
     } else {
         decompress_int8_generic_kernel<T><<<grid, kThreads, 0, st>>>(pay, a.slot_bytes, a.scales, a.comp_bytes,
-                                                                     a.group_elems, a.n_groups, out, a.out_elems,
-                                                                     a.src_index, a.elem_index, a.n_groups_dev);
+                                                                     a.group_elems, a.n_groups, out, a.out_elems, only_flagged,
+                                                                     a.src_index, a.slot_offsets, a.elem_index, a.n_groups_dev);
     }
     count_launch();
     return cudaGetLastError();
@@ -562,12 +588,9 @@ cudaError_t launch_compress_generic(const CodecArgs& a, cudaStream_t st, const u
     if (a.n_groups == 0) return cudaSuccess;
     if (a.scheme == 0) {
         if (a.elem_index) return cudaErrorInvalidValue;   // the raw passthrough has no gather form
-        const uint32_t bytes = a.group_elems * 2u;
-        cudaError_t e = cudaMemcpy2DAsync(a.payload, a.slot_bytes, a.in, bytes, bytes, a.n_groups,
-                                          cudaMemcpyDeviceToDevice, st);
-        if (e != cudaSuccess) return e;
-        passthrough_meta_kernel<<<(a.n_groups + kThreads - 1) / kThreads, kThreads, 0, st>>>(a.n_groups, bytes, a.scales,
-                                                                                            a.comp_bytes);
+        passthrough_in_kernel<<<a.sm_count * 8, kThreads, 0, st>>>(static_cast<const uint16_t*>(a.in), a.group_elems, a.n_groups,
+                                                                   static_cast<uint8_t*>(a.payload), a.slot_bytes, a.scales,
+                                                                   a.comp_bytes);
         count_launch();
         return cudaGetLastError();
     }
@@ -584,7 +607,7 @@ cudaError_t launch_decompress_generic(const CodecArgs& a, cudaStream_t st, const
         if (a.elem_index) return cudaErrorInvalidValue;
         passthrough_out_kernel<<<grid_for(a.n_groups, a.sm_count, 8), kThreads, 0, st>>>(
             static_cast<const uint8_t*>(a.payload), a.slot_bytes, a.comp_bytes, a.group_elems, a.n_groups,
-            static_cast<uint16_t*>(a.out), a.out_elems, a.src_index, a.n_groups_dev);
+            static_cast<uint16_t*>(a.out), a.out_elems, a.src_index, a.slot_offsets, a.n_groups_dev);
         count_launch();
         return cudaGetLastError();
     }

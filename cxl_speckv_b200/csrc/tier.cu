@@ -86,7 +86,8 @@ struct BlockRec {
     uint32_t comp_bytes;   // bytes held in the pool (payload bytes, or the raw size for raw blocks)
     float scale;
     uint32_t group_elems;  // 0 for raw (uncompressed) blocks
-    int dtype;
+    int dtype;             // speckv_dtype_t | scheme << 8 (the scheme the block was stored under); -1 = empty map entry
+    int scheme() const { return (dtype >> 8) & 0xff; }
 };
 
 struct Extent {
@@ -207,6 +208,7 @@ struct Tier {
     uint64_t* h_offsets[kBuf] = {};
     uint64_t* h_total[kBuf] = {};
     size_t cap_groups = 0, cap_slot_bytes = 0;           // per buffer
+    int scheme = SPECKV_COMP_INT8_DELTA_RLE;             // what new offloads are stored under (speckv_ext_tier_set_scheme)
     speckv_tier_stats_t stats = {};
 
     size_t alloc_pool(size_t len) {   // first fit in the free list, else bump; returns SIZE_MAX when full
@@ -342,7 +344,9 @@ static speckv_status_t tier_offload_impl(speckv_tier_t* tier, const void* d_in, 
     if (n_groups == 0) return SPECKV_OK;
     Tier& t = tier->t;
     std::lock_guard<std::mutex> lk(t.mu);
-    const size_t slot = speckv_ext_slot_bytes(group_elems, SPECKV_COMP_INT8_DELTA_RLE);
+    const int scheme = t.scheme;
+    if (scheme == SPECKV_COMP_FP16 && (d_block_table || dtype == SPECKV_DTYPE_F32)) return SPECKV_ERR_INVAL;   // raw passthrough: no gather form
+    const size_t slot = speckv_ext_slot_bytes(group_elems, (speckv_comp_scheme_t)scheme);
     const size_t esz = dtype == SPECKV_DTYPE_F32 ? 4 : 2;
     const size_t cg = tier_chunk_groups(slot, n_groups);
     cudaError_t e = t.ensure_staging(cg, slot);
@@ -373,7 +377,7 @@ static speckv_status_t tier_offload_impl(speckv_tier_t* tier, const void* d_in, 
             r.comp_bytes = t.h_comp[b][i];
             r.scale = t.h_scales[b][i];
             r.group_elems = (uint32_t)group_elems;
-            r.dtype = dtype;
+            r.dtype = (int)dtype | (scheme << 8);
             if (t.blocks.exchange(h_block_ids[g0 + i], r, &old)) {
                 t.stats.used_bytes -= ((uint64_t)old.comp_bytes + 15u) & ~15ull;
                 // an id listed twice in this chunk: its first copy is part of the transfer in flight, so its
@@ -405,7 +409,7 @@ static speckv_status_t tier_offload_impl(speckv_tier_t* tier, const void* d_in, 
         a.group_elems = (uint32_t)group_elems;
         a.n_groups = (uint32_t)ng;
         a.dtype = dtype;
-        a.scheme = SPECKV_COMP_INT8_DELTA_RLE;
+        a.scheme = scheme;
         a.sm_count = current_sm_count();
         if ((e = launch_compress(a, st)) != cudaSuccess) { rc = status_of(e); break; }
         pack_offsets_kernel<<<1, 1024, 0, st>>>(t.d_comp[b], (uint32_t)ng, t.d_offsets[b], t.d_total[b]);
@@ -460,7 +464,7 @@ static speckv_status_t tier_restore_impl(speckv_tier_t* tier, const uint64_t* h_
     if (n_groups == 0) return SPECKV_OK;
     Tier& t = tier->t;
     std::lock_guard<std::mutex> lk(t.mu);
-    const size_t slot = speckv_ext_slot_bytes(group_elems, SPECKV_COMP_INT8_DELTA_RLE);
+    const size_t slot = speckv_ext_slot_bytes(group_elems, SPECKV_COMP_INT8_DELTA_RLE);   // the largest slot of any scheme
     const size_t esz = dtype == SPECKV_DTYPE_F32 ? 4 : 2;
     const size_t cg = tier_chunk_groups(slot, n_groups);
     cudaError_t e = t.ensure_staging(cg, slot);
@@ -469,9 +473,10 @@ static speckv_status_t tier_restore_impl(speckv_tier_t* tier, const uint64_t* h_
     const auto t0 = std::chrono::steady_clock::now();
     uint64_t moved = 0;
     size_t chunk = 0;
-    for (size_t g0 = 0; g0 < n_groups; g0 += cg, ++chunk) {
-        const size_t ng = std::min(cg, n_groups - g0);
+    for (size_t g0 = 0, ng = 0; g0 < n_groups; g0 += ng, ++chunk) {
+        ng = std::min(cg, n_groups - g0);
         const int b = (int)(chunk % Tier::kBuf);
+        int scheme = -1;   // of the chunk: blocks stored under another scheme start the next chunk
         // the pinned metadata mirrors and the staging of buffer b are reusable once its previous
         // H2D copies and decompress have completed
         if ((e = cudaStreamSynchronize(t.copy_st[b])) != cudaSuccess) return status_of(e);
@@ -485,6 +490,11 @@ static speckv_status_t tier_restore_impl(speckv_tier_t* tier, const uint64_t* h_
             const BlockRec* rec = t.blocks.find(h_block_ids[g0 + i]);
             if (!rec || rec->group_elems != group_elems) return SPECKV_ERR_GENERAL;   // unknown, raw, or other geometry
             const BlockRec& r = *rec;
+            if (scheme < 0) scheme = r.scheme();
+            else if (r.scheme() != scheme) {
+                ng = i;
+                break;
+            }
             const uint64_t len = ((uint64_t)r.comp_bytes + 15u) & ~15ull;
             t.h_offsets[b][i] = dst;
             t.h_comp[b][i] = r.comp_bytes;
@@ -517,8 +527,9 @@ static speckv_status_t tier_restore_impl(speckv_tier_t* tier, const uint64_t* h_
         a.group_elems = (uint32_t)group_elems;
         a.n_groups = (uint32_t)ng;
         a.dtype = dtype;
-        a.scheme = SPECKV_COMP_INT8_DELTA_RLE;
+        a.scheme = scheme;
         a.sm_count = current_sm_count();
+        if (scheme == SPECKV_COMP_FP16 && (d_block_table || dtype == SPECKV_DTYPE_F32)) return SPECKV_ERR_INVAL;
         if ((e = launch_decompress(a, st)) != cudaSuccess) return status_of(e);
         cudaEventRecord(t.ev_kernel[b], st);
     }
@@ -622,6 +633,13 @@ speckv_status_t speckv_ext_submit_dma_batch(speckv_tier_t* tier, const speckv_dm
 }
 
 uint32_t speckv_ext_poll_complete(void) { return g_dma_done.exchange(0); }   // handle_poll_done, :194-213
+
+speckv_status_t speckv_ext_tier_set_scheme(speckv_tier_t* tier, speckv_comp_scheme_t scheme) {
+    if (!tier || (int)scheme < 0 || (int)scheme > 4) return SPECKV_ERR_INVAL;
+    std::lock_guard<std::mutex> lk(tier->t.mu);
+    tier->t.scheme = (int)scheme;
+    return SPECKV_OK;
+}
 
 void speckv_ext_tier_get_stats(speckv_tier_t* tier, speckv_tier_stats_t* out) {
     if (!tier || !out) return;

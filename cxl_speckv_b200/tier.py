@@ -29,6 +29,10 @@ class HostTier:
         except Exception:
             pass
 
+    def set_scheme(self, scheme: int) -> None:
+        """Scheme new offloads are stored under (0 .. 4); stored blocks keep theirs."""
+        check(lib().speckv_ext_tier_set_scheme(self._h, int(scheme)), "speckv_ext_tier_set_scheme")
+
     def offload(self, x: torch.Tensor, group_elems: int, block_ids: np.ndarray) -> None:
         x = x.contiguous()
         ids = np.ascontiguousarray(block_ids, dtype=np.uint64)

@@ -28,6 +28,19 @@ class CxlSpeckvKVAllocator:
         self._num_tokens = 0
         self._head_dim = 0
         self._bytes_per_element = 0
+        self._pool = None      # CUDA tensor backing the region (bind_pool)
+        self._tier = None      # keeps the HostTier alive as long as the binding refers to it
+        self._policy = None    # TierPolicy (attach_policy)
+        lib = self._speckv.lib
+        if hasattr(lib, "speckv_ext_bind_pool"):   # additive entry points of the B200 library, declared once
+            lib.speckv_ext_bind_pool.argtypes = [ctypes.c_uint64, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]
+            lib.speckv_ext_set_kv_layout.argtypes = [ctypes.c_uint64] + [ctypes.c_uint32] * 4
+            lib.speckv_ext_set_pool_dtype.argtypes = [ctypes.c_uint64, ctypes.c_int]
+            lib.speckv_ext_offload_pages.argtypes = [ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_void_p]
+            lib.speckv_ext_fetch_pages.argtypes = [ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_void_p]
+            for f in ("speckv_ext_bind_pool", "speckv_ext_set_kv_layout", "speckv_ext_set_pool_dtype",
+                      "speckv_ext_offload_pages", "speckv_ext_fetch_pages"):
+                getattr(lib, f).restype = ctypes.c_int
 
     def allocate(self, num_tokens: int, num_layers: int, num_heads: int, head_dim: int, bytes_per_element: int):
         """Allocate the KV region of one request: tokens x layers x heads x head_dim x bytes x 2 (K+V)."""
@@ -63,10 +76,8 @@ class CxlSpeckvKVAllocator:
         get_kv_ptr() returns addresses inside `pool`; with a HostTier, pages can be demoted with
         offload_pages() and come back on access / prefetch_step()."""
         lib = self._speckv.lib
-        lib.speckv_ext_bind_pool.argtypes = [ctypes.c_uint64, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]
-        lib.speckv_ext_bind_pool.restype = ctypes.c_int
-        lib.speckv_ext_set_kv_layout.argtypes = [ctypes.c_uint64] + [ctypes.c_uint32] * 4
-        lib.speckv_ext_set_kv_layout.restype = ctypes.c_int
+        if self._handle is None:
+            raise RuntimeError("bind_pool: call allocate() first")
         ret = lib.speckv_ext_bind_pool(self._handle, pool.data_ptr(), pool.numel() * pool.element_size(),
                                        tier._h if tier is not None else None)
         if ret != 0:
@@ -75,20 +86,29 @@ class CxlSpeckvKVAllocator:
                                            self._head_dim * self._bytes_per_element)
         if ret != 0:
             raise RuntimeError(f"speckv_ext_set_kv_layout failed: {ret}")
+        # the codec quantises the pool's own element type (fp16 / bf16 / fp32 pages)
+        import torch
+        code = {torch.float16: 0, torch.bfloat16: 1, torch.float32: 2}.get(pool.dtype)
+        if code is None:
+            raise TypeError(f"bind_pool: unsupported pool dtype {pool.dtype}")
+        ret = lib.speckv_ext_set_pool_dtype(self._handle, code)
+        if ret != 0:
+            raise RuntimeError(f"speckv_ext_set_pool_dtype failed: {ret}")
         self._pool = pool
+        self._tier = tier
 
     def offload_pages(self, first_page: int, n_pages: int):
         lib = self._speckv.lib
-        lib.speckv_ext_offload_pages.argtypes = [ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_void_p]
-        lib.speckv_ext_offload_pages.restype = ctypes.c_int
+        if self._pool is None:
+            raise RuntimeError("offload_pages: no pool bound (bind_pool)")
         ret = lib.speckv_ext_offload_pages(self._handle, first_page, n_pages, None)
         if ret != 0:
             raise RuntimeError(f"speckv_ext_offload_pages failed: {ret}")
 
     def fetch_pages(self, first_page: int, n_pages: int):
         lib = self._speckv.lib
-        lib.speckv_ext_fetch_pages.argtypes = [ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_void_p]
-        lib.speckv_ext_fetch_pages.restype = ctypes.c_int
+        if self._pool is None:
+            raise RuntimeError("fetch_pages: no pool bound (bind_pool)")
         ret = lib.speckv_ext_fetch_pages(self._handle, first_page, n_pages, None)
         if ret != 0:
             raise RuntimeError(f"speckv_ext_fetch_pages failed: {ret}")
@@ -120,6 +140,8 @@ class CxlSpeckvKVAllocator:
         data accordingly -- promoted pages are restored into the pool, the pages the policy evicted
         to make room are compressed out to the host tier.  Returns (ok, evicted)."""
         pol = self._policy
+        if pol is None:
+            raise RuntimeError("residency_step: no policy attached (attach_policy)")
         if touched is not None:
             pol.touch(touched)
         if promote is None or len(promote) == 0:

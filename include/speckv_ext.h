@@ -40,6 +40,18 @@ typedef enum {
     SPECKV_DTYPE_F32  = 2,   /* what the reference engine consumes (std::vector<float>) */
 } speckv_dtype_t;
 
+/* Extension scheme ids, accepted wherever a speckv_comp_scheme_t is (cast the value).  NOT reference behaviour:
+ * SURVEY.md section 8f-4 asks for a non-wrapping quantiser as an explicit new id.  The reference multiplies by 127
+ * twice -- s = max|x| / 127 (cache_engine.cpp:183) and (x / s) * 127 (:190-191) -- so its codes wrap modulo 256, the
+ * clamp at :192 is dead and the reconstruction error of schemes 1 and 2 is of the order of the data itself.  The
+ * clamped schemes keep every operation of :186-196 and :275-284, apply the clamp before the narrowing cast as :192
+ * intended and store s = max|x|, so quantiser and dequantiser are inverse to each other (NaN codes as 0).  Same
+ * container, same decoder: a payload written under 3 / 4 decodes under 2 / 1 and vice versa. */
+enum {
+    SPECKV_COMP_INT8_CLAMP_DELTA_RLE = 3,   /* clamped codes + delta + byte-pair RLE, slot 2 * n */
+    SPECKV_COMP_INT8_CLAMP           = 4,   /* clamped codes only, slot n */
+};
+
 /* ---- library / device ----------------------------------------------------- */
 /* Number of usable CUDA devices (0 when none: every other call then fails with
  * SPECKV_ERR_DRIVER). */
@@ -120,7 +132,11 @@ SPECKV_API speckv_status_t speckv_ext_decompress_scatter(const void* d_payload, 
  * buffers on internal streams (H2D, kernel, D2H overlapped) and the call
  * returns when the results are in host memory.  Pinned host memory
  * (speckv_ext_host_alloc) gives full PCIe rate.  This is the call the
- * end-to-end benchmark times. */
+ * end-to-end benchmark times.  Payloads cross PCIe at their size: when the slots of a
+ * chunk are less than three quarters full (and the chunk has at most 4096 groups) every
+ * group's payload travels alone, rounded up to 16 bytes; otherwise the chunk's slots go
+ * in one copy.  Bytes of a slot beyond comp_bytes are left untouched in h_payload.
+ * speckv_ext_get_stats reports the bytes actually moved. */
 SPECKV_API speckv_status_t speckv_ext_compress_host(const void* h_in, speckv_dtype_t dtype,
                                          size_t group_elems, size_t n_groups,
                                          void* h_payload, size_t slot_bytes,
@@ -248,6 +264,11 @@ SPECKV_API speckv_status_t speckv_ext_tier_restore(speckv_tier_t* tier, const ui
                                                    size_t group_elems, speckv_dtype_t dtype, void* d_out,
                                                    void* cuda_stream);
 /* Release pool space of blocks (unknown ids are ignored, like speckv_free). */
+/* The scheme new offloads are stored under (default INT8_DELTA_RLE; 0 .. 4, the raw passthrough 0 only for the
+ * non-paged fp16 / bf16 form).  Every stored block remembers its scheme: restores decode each block the way it was
+ * stored, whatever the tier's current setting.  speckv_set_compression_scheme (host/include/speckv.h:59-66) applies
+ * to the tiers of all bound pools through this call. */
+SPECKV_API speckv_status_t speckv_ext_tier_set_scheme(speckv_tier_t* tier, speckv_comp_scheme_t scheme);
 SPECKV_API speckv_status_t speckv_ext_tier_drop(speckv_tier_t* tier, const uint64_t* h_block_ids, size_t n);
 SPECKV_API void speckv_ext_tier_get_stats(speckv_tier_t* tier, speckv_tier_stats_t* out);
 
@@ -290,8 +311,15 @@ SPECKV_API speckv_status_t speckv_ext_bind_pool(speckv_handle_t handle, void* d_
  * depth_k) into the pages of positions cur_pos+1 .. cur_pos+depth_k and make them resident. */
 SPECKV_API speckv_status_t speckv_ext_set_kv_layout(speckv_handle_t handle, uint32_t num_layers, uint32_t num_tokens,
                                                     uint32_t num_heads, uint32_t entry_bytes);
+/* Element type of the bound pool (default fp16): what the codec quantises when pages of this handle are offloaded
+ * and what restores write back -- one 4 KiB page is one group of 2048 fp16 / bf16 or 1024 fp32 elements.  Refused
+ * (SPECKV_ERR_GENERAL) while pages stored under another type live only in the tier. */
+SPECKV_API speckv_status_t speckv_ext_set_pool_dtype(speckv_handle_t handle, speckv_dtype_t dtype);
+/* The scheme set by speckv_set_compression_scheme / speckv_ext_set_param(2, ..) (default 2). */
+SPECKV_API speckv_status_t speckv_ext_get_compression_scheme(int* out_scheme);
 /* Demote pages to the host tier (compress + move; flags: L1/L2 cleared, compressed set) /
- * promote them back (restore; flags: L2 set).  Pages are fp16 groups of 2048 elements. */
+ * promote them back (restore; flags: L2 set; a page is marked resident only after its restore succeeded).
+ * Pages are groups of the pool's element type, stored under the current compression scheme. */
 SPECKV_API speckv_status_t speckv_ext_offload_pages(speckv_handle_t handle, uint64_t first_page, uint64_t n_pages,
                                                     void* cuda_stream);
 SPECKV_API speckv_status_t speckv_ext_fetch_pages(speckv_handle_t handle, uint64_t first_page, uint64_t n_pages,
@@ -451,6 +479,8 @@ typedef struct {
     uint64_t bytes_in_compress;      /* uncompressed bytes consumed */
     uint64_t bytes_out_decompress;   /* uncompressed bytes produced (capacity) */
     uint64_t kernel_launches;        /* CUDA kernels this library launched */
+    uint64_t host_api_h2d_bytes;     /* bytes speckv_ext_compress_host / _decompress_host copied host -> device */
+    uint64_t host_api_d2h_bytes;     /* ... and device -> host (payloads travel at their size, not at the slot size) */
 } speckv_ext_stats_t;
 SPECKV_API void speckv_ext_get_stats(speckv_ext_stats_t* out);
 /* FPGACacheEngine::get_statistics (cache_engine.cpp:150-158, EngineStatistics cache_engine.h:65-72) with the

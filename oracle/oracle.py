@@ -81,6 +81,12 @@ class Port:
             L.oracle_decompress_batch.restype = C.c_int
             L.oracle_decompress_batch.argtypes = [_u8p, C.c_size_t, _f32p, _u32p, C.c_size_t,
                                                   C.c_size_t, C.c_int, C.c_void_p, _u32p, C.c_int]
+            L.oracle_compress_batch_scheme.restype = C.c_int
+            L.oracle_compress_batch_scheme.argtypes = [C.c_void_p, C.c_int, C.c_size_t, C.c_size_t, _u8p, C.c_size_t,
+                                                       _f32p, _u32p, C.c_int, C.c_int]
+            L.oracle_decompress_batch_scheme.restype = C.c_int
+            L.oracle_decompress_batch_scheme.argtypes = [_u8p, C.c_size_t, _f32p, _u32p, C.c_size_t, C.c_size_t, C.c_int,
+                                                         C.c_void_p, _u32p, C.c_int, C.c_int]
             L.oracle_translate.restype = C.c_uint64
             L.oracle_translate.argtypes = [C.c_uint64]
             L.oracle_atu_new.restype = C.c_void_p
@@ -158,7 +164,8 @@ class Port:
     # -- batched, fp16/bf16/fp32 boundary ------------------------------------------------
     @classmethod
     def compress_batch(cls, x: np.ndarray, group_elems: int, dtype: Optional[int] = None,
-                       slot_bytes: Optional[int] = None, threads: int = 1):
+                       slot_bytes: Optional[int] = None, threads: int = 1, scheme: int = 2):
+        """scheme: 1 INT8 codes, 2 the reference pipeline, 3 / 4 the clamped (non-reference) schemes"""
         code = np_dtype_code(x, dtype)
         x = np.ascontiguousarray(x).ravel()
         n_groups = x.size // group_elems if group_elems else 0
@@ -167,13 +174,13 @@ class Port:
         payload = np.zeros(max(n_groups * slot_bytes, 1), dtype=np.uint8)
         scales = np.zeros(max(n_groups, 1), dtype=np.float32)
         comp = np.zeros(max(n_groups, 1), dtype=np.uint32)
-        cls.lib().oracle_compress_batch(x.ctypes.data, code, group_elems, n_groups, _ptr(payload, _u8p),
-                                        slot_bytes, _ptr(scales, _f32p), _ptr(comp, _u32p), threads)
+        cls.lib().oracle_compress_batch_scheme(x.ctypes.data, code, group_elems, n_groups, _ptr(payload, _u8p),
+                                               slot_bytes, _ptr(scales, _f32p), _ptr(comp, _u32p), scheme, threads)
         return payload[: n_groups * slot_bytes].reshape(n_groups, slot_bytes), scales[:n_groups], comp[:n_groups]
 
     @classmethod
     def decompress_batch(cls, payload: np.ndarray, scales: np.ndarray, comp: np.ndarray,
-                         group_elems: int, dtype: int, threads: int = 1):
+                         group_elems: int, dtype: int, threads: int = 1, scheme: int = 2):
         payload = np.ascontiguousarray(payload, dtype=np.uint8)
         n_groups = scales.size
         slot_bytes = payload.size // n_groups if n_groups else 0
@@ -182,9 +189,9 @@ class Port:
         out_elems = np.zeros(max(n_groups, 1), dtype=np.uint32)
         scales = np.ascontiguousarray(scales, dtype=np.float32)
         comp = np.ascontiguousarray(comp, dtype=np.uint32)
-        cls.lib().oracle_decompress_batch(_ptr(payload, _u8p), slot_bytes, _ptr(scales, _f32p),
-                                          _ptr(comp, _u32p), group_elems, n_groups, dtype,
-                                          out.ctypes.data, _ptr(out_elems, _u32p), threads)
+        cls.lib().oracle_decompress_batch_scheme(_ptr(payload, _u8p), slot_bytes, _ptr(scales, _f32p),
+                                                 _ptr(comp, _u32p), group_elems, n_groups, dtype,
+                                                 out.ctypes.data, _ptr(out_elems, _u32p), scheme, threads)
         return out[: n_groups * group_elems].reshape(n_groups, group_elems), out_elems[:n_groups]
 
     # -- addresses ---------------------------------------------------------------------

@@ -175,11 +175,71 @@ size_t oracle_decompress(const uint8_t* rle, size_t bytes, float scale, float* o
 }
 
 /* ------------------------------------------------------------------------ */
+/* the other compression schemes                                             */
+/* ------------------------------------------------------------------------ */
+/* Scheme 1 (SPECKV_COMP_INT8, host/include/speckv.h:61) is the reference's quantiser on its own: the codes of
+ * quantize_to_int8 (:186-196), one byte per element, decoded by dequantize_from_int8 (:275-284).
+ *
+ * Schemes 3 and 4 are NOT reference behaviour (SURVEY.md section 8f-4 asks for them as explicit new ids): the
+ * reference multiplies by 127 twice -- s = max / 127 (:183) and (x / s) * 127 (:190-191) -- so its codes wrap modulo
+ * 256 and the clamp at :192 is dead.  The clamped schemes keep every operation of :186-196 and :275-284, apply the
+ * clamp BEFORE the narrowing cast as :192 intended, and store s = max|x| so that (x / s) * 127 spans [-127, 127]:
+ * quantiser and dequantiser become inverse to each other.  NaN codes as 0.  Scheme 3 = clamped codes + delta + RLE,
+ * scheme 4 = clamped codes only. */
+float oracle_scale_max(const float* x, size_t n) {
+    float max_val = 0.0f;
+    for (size_t i = 0; i < n; ++i) {
+        float a = fabsf(x[i]);
+        if (a > max_val) max_val = a;
+    }
+    return (max_val > 0.0f) ? max_val : 1.0f;
+}
+
+void oracle_quantize_clamped(const float* x, size_t n, float scale, int8_t* q) {
+    for (size_t i = 0; i < n; ++i) {
+        float r = roundf((x[i] / scale) * 127.0f);
+        int v = (r != r) ? 0 : (r > 127.0f ? 127 : (r < -128.0f ? -128 : (int)r));
+        q[i] = (int8_t)v;
+    }
+}
+
+size_t oracle_compress_scheme(const float* x, size_t n, int scheme, float* scale, uint8_t* out) {
+    if (scheme == ORACLE_SCHEME_RLE) return oracle_compress(x, n, scale, out);
+    const int clamped = scheme == ORACLE_SCHEME_CLAMP_RLE || scheme == ORACLE_SCHEME_CLAMP_INT8;
+    float s = clamped ? oracle_scale_max(x, n) : oracle_scale(x, n);
+    *scale = s;
+    if (n == 0) return 0;
+    int8_t* q = (int8_t*)malloc(n);
+    if (clamped) oracle_quantize_clamped(x, n, s, q);
+    else oracle_quantize(x, n, s, q);
+    size_t bytes;
+    if (scheme == ORACLE_SCHEME_CLAMP_RLE) {
+        int8_t* d = (int8_t*)malloc(n);
+        oracle_delta_encode(q, n, d);
+        bytes = oracle_rle_encode(d, n, out);
+        free(d);
+    } else {
+        memcpy(out, q, n);
+        bytes = n;
+    }
+    free(q);
+    return bytes;
+}
+
+size_t oracle_decompress_scheme(const uint8_t* payload, size_t bytes, float scale, int scheme, float* out, size_t cap) {
+    if (scheme == ORACLE_SCHEME_RLE || scheme == ORACLE_SCHEME_CLAMP_RLE) return oracle_decompress(payload, bytes, scale, out, cap);
+    size_t n = bytes < cap ? bytes : cap;
+    oracle_dequantize((const int8_t*)payload, n, scale, out);
+    return n;
+}
+
+/* ------------------------------------------------------------------------ */
 /* batched forms (independent groups; optional pthread fan-out)              */
 /* ------------------------------------------------------------------------ */
 
 typedef struct {
     int is_compress;
+    int scheme;            /* ORACLE_SCHEME_* */
     const void* in;
     int dtype;
     size_t group_elems, g0, g1;
@@ -212,14 +272,14 @@ static void* batch_worker(void* arg) {
                 x = tmp;
             }
             float s;
-            size_t bytes = oracle_compress(x, n, &s, buf);
+            size_t bytes = oracle_compress_scheme(x, n, j->scheme, &s, buf);
             size_t w = bytes < j->slot_bytes ? bytes : j->slot_bytes;
             memcpy(j->payload + g * j->slot_bytes, buf, w);
             j->scales[g] = s;
             j->comp_bytes[g] = (uint32_t)bytes;
         } else {
-            size_t got = oracle_decompress(j->cpayload + g * j->slot_bytes, j->ccomp_bytes[g],
-                                           j->cscales[g], tmp, n);
+            size_t got = oracle_decompress_scheme(j->cpayload + g * j->slot_bytes, j->ccomp_bytes[g],
+                                                  j->cscales[g], j->scheme, tmp, n);
             if (j->dtype == ORACLE_F32) {
                 memcpy((float*)j->out + g * n, tmp, got * sizeof(float));
             } else {
@@ -257,10 +317,18 @@ static int run_batch(batch_job_t* proto, size_t n_groups, int threads) {
 int oracle_compress_batch(const void* in, int dtype, size_t group_elems, size_t n_groups,
                           uint8_t* payload, size_t slot_bytes, float* scales,
                           uint32_t* comp_bytes, int threads) {
+    return oracle_compress_batch_scheme(in, dtype, group_elems, n_groups, payload, slot_bytes, scales, comp_bytes,
+                                        ORACLE_SCHEME_RLE, threads);
+}
+
+int oracle_compress_batch_scheme(const void* in, int dtype, size_t group_elems, size_t n_groups,
+                                 uint8_t* payload, size_t slot_bytes, float* scales,
+                                 uint32_t* comp_bytes, int scheme, int threads) {
     (void)elem_size;
     batch_job_t j;
     memset(&j, 0, sizeof(j));
     j.is_compress = 1;
+    j.scheme = scheme;
     j.in = in;
     j.dtype = dtype;
     j.group_elems = group_elems;
@@ -274,9 +342,17 @@ int oracle_compress_batch(const void* in, int dtype, size_t group_elems, size_t 
 int oracle_decompress_batch(const uint8_t* payload, size_t slot_bytes, const float* scales,
                             const uint32_t* comp_bytes, size_t group_elems, size_t n_groups,
                             int dtype, void* out, uint32_t* out_elems, int threads) {
+    return oracle_decompress_batch_scheme(payload, slot_bytes, scales, comp_bytes, group_elems, n_groups, dtype, out,
+                                          out_elems, ORACLE_SCHEME_RLE, threads);
+}
+
+int oracle_decompress_batch_scheme(const uint8_t* payload, size_t slot_bytes, const float* scales,
+                                   const uint32_t* comp_bytes, size_t group_elems, size_t n_groups,
+                                   int dtype, void* out, uint32_t* out_elems, int scheme, int threads) {
     batch_job_t j;
     memset(&j, 0, sizeof(j));
     j.is_compress = 0;
+    j.scheme = scheme;
     j.dtype = dtype;
     j.group_elems = group_elems;
     j.cpayload = payload;

@@ -44,13 +44,18 @@ static inline int round_kernel(float t) {
     return (t < 0.0f) ? -k : k;
 }
 
-static long check_type(int bf, int step, long* total, long* lowdomain_bad) {
+/* scale_is_max != 0: the clamped schemes (ids 3 / 4, NOT reference behaviour) store s = max|x| instead of max|x| / 127,
+ * so that (x / s) * 127 spans the int8 range and the clamp of cache_engine.cpp:192 never acts; the kernels run the
+ * same two-operation division there, so the same identity is owed for that divisor set. */
+static inline int clamp_i8(float r) { if (r != r) return 0; if (r > 127.0f) return 127; if (r < -128.0f) return -128; return (int)r; }
+
+static long check_type(int bf, int step, int scale_is_max, long* total, long* lowdomain_bad) {
     long bad = 0, tot = 0, low = 0;
 #pragma omp parallel for schedule(dynamic, 64) reduction(+ : bad, tot, low)
     for (uint32_t mh = 1; mh < 0x7f80; mh += step) {
         if (!bf && mh >= 0x7c00) continue;
         float m = bf ? b2f(mh) : h2f(mh);
-        float sc = m / 127.0f;
+        float sc = scale_is_max ? m : m / 127.0f;
         float r = 1.0f / sc;
         float rl = fmaf(-sc, r, 1.0f) * r;
         int fastok = bf ? (m >= 0x1p-60f && m < 0x1p120f) : 1;
@@ -58,7 +63,7 @@ static long check_type(int bf, int step, long* total, long* lowdomain_bad) {
             float x = bf ? b2f(xh) : h2f(xh);
             for (int sgn = 0; sgn < 2; ++sgn) {
                 float xs = sgn ? -x : x;
-                int qt = cvt(roundf((xs / sc) * 127.0f)) & 0xff;
+                int qt = (scale_is_max ? clamp_i8(roundf((xs / sc) * 127.0f)) : cvt(roundf((xs / sc) * 127.0f))) & 0xff;
                 float y = fmaf(xs, r, xs * rl);                 /* the kernels' form */
                 int qk = round_kernel(y * 127.0f) & 0xff;
                 if ((round_kernel_sx(y * 127.0f, xs) & 0xff) != qk && fastok) bad++;   /* packed-sign variant */
@@ -79,11 +84,17 @@ static long check_type(int bf, int step, long* total, long* lowdomain_bad) {
 int main(int argc, char** argv) {
     int step = (argc > 1 && !strcmp(argv[1], "quick")) ? 16 : 1;
     long tot, low, fail = 0;
-    long bad = check_type(0, step, &tot, &low);
+    long bad = check_type(0, step, 0, &tot, &low);
     printf("fp16: pairs=%ld mismatches=%ld\n", tot, bad);
     fail += bad;
-    bad = check_type(1, step, &tot, &low);
+    bad = check_type(1, step, 0, &tot, &low);
     printf("bf16: pairs=%ld mismatches(2^-60<=max<2^120)=%ld  [other max -> exact path; fast form would miss %ld]\n", tot, bad, low);
+    fail += bad;
+    bad = check_type(0, step, 1, &tot, &low);
+    printf("fp16, s = max (clamped schemes): pairs=%ld mismatches=%ld\n", tot, bad);
+    fail += bad;
+    bad = check_type(1, step, 1, &tot, &low);
+    printf("bf16, s = max (clamped schemes): pairs=%ld mismatches(2^-60<=max<2^120)=%ld  [fast form would miss %ld outside]\n", tot, bad, low);
     fail += bad;
     /* dequantiser identity over all 256 codes */
     float r127 = 1.0f / 127.0f;

@@ -221,3 +221,45 @@ def test_policy_port_eviction_semantics():
     assert r["tiers"] == [2, 0, 2, 0, 2, 2, 1]
     assert r["lru"] == [1, 3]
     assert r["stats"]["migrations_l1_to_l3"] == 2 and r["stats"]["migrations_l3_to_l1"] == 4
+
+
+# ---- the extension schemes (NOT reference behaviour; see oracle/speckv_oracle.c) ------------------------------
+def test_clamped_scheme_restatement_known_answers():
+    """Schemes 3 / 4: s = max|x|, q = clamp(round_half_away((x / s) * 127)), y = (q / 127) * s -- pinned against a
+    hand-computed vector and an independent numpy formulation; scheme 1 = the reference's codes alone."""
+    from oracle.oracle import Port
+    x = np.array([0, 1, -1, 0.5, 0.25, 0.25, 0.25, 2, -2, 1e-3], dtype=np.float32)
+    p, s, c = Port.compress_batch(x, x.size, threads=1, scheme=4)
+    assert s[0] == np.float32(2.0) and c[0] == x.size
+    assert p[0, :x.size].view(np.int8).tolist() == [0, 64, -64, 32, 16, 16, 16, 127, -127, 0]
+    p3, s3, c3 = Port.compress_batch(x, x.size, threads=1, scheme=3)
+    # deltas 0 64 -128 96 -16 0 0 111 2 127 -> pairs (value, count)
+    want = [(0, 1), (64, 1), (-128, 1), (96, 1), (-16, 1), (0, 2), (111, 1), (2, 1), (127, 1)]
+    assert c3[0] == 2 * len(want)
+    got = p3[0, :c3[0]].reshape(-1, 2)
+    assert [(int(np.int8(v)), int(n)) for v, n in got] == want
+    y, n = Port.decompress_batch(p3, s3, c3, x.size, 2, threads=1, scheme=3)
+    assert n[0] == x.size
+    q = np.array([0, 64, -64, 32, 16, 16, 16, 127, -127, 0], dtype=np.float32)
+    assert np.array_equal(y[0], (q / np.float32(127.0)) * np.float32(2.0))
+    # independent numpy formulation on random fp16 groups (incl. zero group and NaN)
+    rng = np.random.default_rng(12)
+    G = 4096
+    xs = rng.standard_normal(6 * G).astype(np.float16).reshape(6, G)
+    xs[1] = 0
+    xs[2, 9] = np.nan
+    pc, sc, cc = Port.compress_batch(xs.reshape(-1), G, threads=2, scheme=4)
+    for g in range(6):
+        xf = xs[g].astype(np.float32)
+        m = np.nanmax(np.abs(xf)) if np.isfinite(np.nanmax(np.abs(xf))) else np.inf
+        sg = np.float32(m) if m > 0 else np.float32(1.0)
+        t = (xf / sg) * np.float32(127.0)
+        r = np.sign(t) * np.floor(np.abs(t) + np.float32(0.5))
+        r = np.where(np.isnan(r), 0, np.clip(r, -128, 127)).astype(np.int8)
+        assert sc[g] == sg and np.array_equal(pc[g, :G].view(np.int8), r), g
+    # scheme 1 == the reference's quantiser alone: the codes whose deltas scheme 2 encodes
+    p1, s1, c1 = Port.compress_batch(xs.reshape(-1), G, threads=2, scheme=1)
+    p2, s2, c2 = Port.compress_batch(xs.reshape(-1), G, threads=2, scheme=2)
+    y1, _ = Port.decompress_batch(p1, s1, c1, G, 0, threads=2, scheme=1)
+    y2, _ = Port.decompress_batch(p2, s2, c2, G, 0, threads=2, scheme=2)
+    assert np.array_equal(s1.view(np.uint32), s2.view(np.uint32)) and np.array_equal(y1.view(np.uint16), y2.view(np.uint16))
