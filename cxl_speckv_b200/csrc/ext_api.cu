@@ -107,6 +107,7 @@ static size_t elem_bytes(int dtype) { return dtype == DT_F32 ? 4 : 2; }
 // stream is being captured -- run the call once before capturing it.
 struct ScratchEntry {
     int device;
+    int tag;
     cudaStream_t stream;
     void* ptr;
     size_t cap;
@@ -114,7 +115,7 @@ struct ScratchEntry {
 static std::mutex g_scratch_mu;
 static std::vector<ScratchEntry> g_scratch;
 
-cudaError_t scratch_persistent(void** p, size_t bytes, cudaStream_t st) {
+cudaError_t scratch_persistent(void** p, size_t bytes, cudaStream_t st, int tag) {
     if (device_count() <= 0) return cudaErrorNoDevice;
     int d = 0;
     cudaError_t e = cudaGetDevice(&d);
@@ -122,7 +123,7 @@ cudaError_t scratch_persistent(void** p, size_t bytes, cudaStream_t st) {
     std::lock_guard<std::mutex> lk(g_scratch_mu);
     ScratchEntry* hit = nullptr;
     for (ScratchEntry& s : g_scratch)
-        if (s.device == d && s.stream == st) hit = &s;
+        if (s.device == d && s.stream == st && s.tag == tag) hit = &s;
     if (hit && hit->cap >= bytes) {
         *p = hit->ptr;
         return cudaSuccess;
@@ -131,6 +132,10 @@ cudaError_t scratch_persistent(void** p, size_t bytes, cudaStream_t st) {
     while (cap < bytes) cap *= 2;
     void* np = nullptr;
     if ((e = cudaMalloc(&np, cap)) != cudaSuccess) return e;
+    if ((e = cudaMemset(np, 0, cap)) != cudaSuccess) {   // counters kept in such buffers start at zero
+        cudaFree(np);
+        return e;
+    }
     if (hit) {
         cudaFree(hit->ptr);   // synchronises: earlier launches on the stream that use the old buffer have finished
         hit->ptr = np;
@@ -140,7 +145,7 @@ cudaError_t scratch_persistent(void** p, size_t bytes, cudaStream_t st) {
             cudaFree(g_scratch.front().ptr);
             g_scratch.erase(g_scratch.begin());
         }
-        g_scratch.push_back(ScratchEntry{d, st, np, cap});
+        g_scratch.push_back(ScratchEntry{d, tag, st, np, cap});
     }
     *p = np;
     return cudaSuccess;

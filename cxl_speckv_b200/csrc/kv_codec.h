@@ -36,17 +36,31 @@ inline bool scheme_is_rle(int s) { return s == 2 || s == 3; }
 inline bool scheme_is_codes(int s) { return s == 1 || s == 4; }
 inline bool scheme_max_scale(int s) { return s == 3 || s == 4; }
 
+// What the tuned decompress kernel leaves for the second pass (one buffer per stream, kept across calls):
+//   flags[g]   0 = done, 1 = the generic kernel decodes group g, 2 = the run-expansion path does
+//   list / counters[0]: the groups flagged 2, appended in any order; counters[1]: CTAs of the second pass that have
+//              finished (the last one clears both, so the next call starts from zero without a memset)
+//   prefix[g * (R + 1) + r] = (elements, code) before pairs-region r of group g; entry R = (decoded length, -)
+struct DecodeScratch {
+    uint32_t* flags = nullptr;
+    uint32_t* list = nullptr;
+    uint32_t* counters = nullptr;
+    uint2* prefix = nullptr;
+    uint32_t regions = 0;   // R of the call
+};
+
 // any geometry, any alignment (kv_codec_generic.cu)
-// `only_flagged` (optional, device): process group g only if only_flagged[g] != 0
+// `only_flagged` (optional, device): process group g only if only_flagged[g] == 1
 cudaError_t launch_compress_generic(const CodecArgs& a, cudaStream_t st, const uint32_t* only_flagged = nullptr);
-cudaError_t launch_decompress_generic(const CodecArgs& a, cudaStream_t st, const uint32_t* only_flagged = nullptr);
+cudaError_t launch_decompress_generic(const CodecArgs& a, cudaStream_t st, const uint32_t* only_flagged = nullptr,
+                                      const DecodeScratch* runs = nullptr);
 
 // tuned fp16/bf16 kernels for groups of R * 2048 elements (kv_codec_fast.cu).  fast_regions()
 // returns R when they cover the call, else 0; they set flags[g] = 1 for every group they leave
 // to the generic kernel.
 int fast_regions(const CodecArgs& a, bool decompress);
 cudaError_t launch_compress_fast(int R, const CodecArgs& a, uint32_t* flags, cudaStream_t st);
-cudaError_t launch_decompress_fast(int R, const CodecArgs& a, uint32_t* flags, cudaStream_t st);
+cudaError_t launch_decompress_fast(int R, const CodecArgs& a, const DecodeScratch& scratch, cudaStream_t st);
 
 // dispatch: tuned kernels for the common geometries, generic otherwise (kv_codec_dispatch.cu)
 cudaError_t launch_compress(const CodecArgs& a, cudaStream_t st);

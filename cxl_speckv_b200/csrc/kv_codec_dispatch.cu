@@ -19,28 +19,40 @@ static bool force_generic() {
     return v;
 }
 
-template <typename Fast, typename Generic>
-static cudaError_t two_pass(const CodecArgs& a, cudaStream_t st, bool decompress, Fast fast, Generic generic) {
-    const int R = force_generic() ? 0 : fast_regions(a, decompress);
-    if (R == 0) return generic(a, st, nullptr);
+cudaError_t launch_compress(const CodecArgs& a, cudaStream_t st) {
+    const int R = force_generic() ? 0 : fast_regions(a, false);
+    if (R == 0) return launch_compress_generic(a, st, nullptr);
     // the per-group flag words live in a buffer that belongs to the stream and stays allocated: no allocation on
     // the call path, and the two launches can be captured into a CUDA graph
     uint32_t* flags = nullptr;
     cudaError_t e = scratch_persistent(reinterpret_cast<void**>(&flags), (size_t)a.n_groups * sizeof(uint32_t), st);
     if (e != cudaSuccess) return e;
-    e = fast(R, a, flags, st);
-    if (e == cudaSuccess) e = generic(a, st, flags);
+    e = launch_compress_fast(R, a, flags, st);
+    if (e == cudaSuccess) e = launch_compress_generic(a, st, flags);
     return e;
 }
 
-cudaError_t launch_compress(const CodecArgs& a, cudaStream_t st) {
-    return two_pass(a, st, false, launch_compress_fast,
-                    [](const CodecArgs& x, cudaStream_t s, const uint32_t* f) { return launch_compress_generic(x, s, f); });
-}
-
 cudaError_t launch_decompress(const CodecArgs& a, cudaStream_t st) {
-    return two_pass(a, st, true, launch_decompress_fast,
-                    [](const CodecArgs& x, cudaStream_t s, const uint32_t* f) { return launch_decompress_generic(x, s, f); });
+    const int R = force_generic() ? 0 : fast_regions(a, true);
+    if (R == 0) return launch_decompress_generic(a, st, nullptr, nullptr);
+    // [counters 64 B][flags n][list n][prefix n * (R + 1)]: its own buffer (tag 1) -- the counters must stay zero
+    // between calls, so nothing else may scribble here
+    const size_t n = a.n_groups;
+    const size_t off_flags = 64, off_list = off_flags + ((n * 4 + 15) & ~(size_t)15), off_prefix = off_list + ((n * 4 + 15) & ~(size_t)15);
+    const bool rle = scheme_is_rle(a.scheme);
+    const size_t bytes = off_prefix + (rle ? n * (size_t)(R + 1) * sizeof(uint2) : 0);
+    uint8_t* base = nullptr;
+    cudaError_t e = scratch_persistent(reinterpret_cast<void**>(&base), bytes, st, 1);
+    if (e != cudaSuccess) return e;
+    DecodeScratch sc;
+    sc.counters = reinterpret_cast<uint32_t*>(base);
+    sc.flags = reinterpret_cast<uint32_t*>(base + off_flags);
+    sc.list = reinterpret_cast<uint32_t*>(base + off_list);
+    sc.prefix = reinterpret_cast<uint2*>(base + off_prefix);
+    sc.regions = (uint32_t)R;
+    e = launch_decompress_fast(R, a, sc, st);
+    if (e == cudaSuccess) e = launch_decompress_generic(a, st, sc.flags, rle ? &sc : nullptr);
+    return e;
 }
 
 }  // namespace speckv

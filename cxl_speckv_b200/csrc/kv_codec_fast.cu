@@ -617,8 +617,13 @@ compress_fast_kernel(const T* __restrict__ in, uint32_t n_groups, uint8_t* __res
     uint32_t t0, t1, gmax_bits;
     group_reduce<R>(sm.xa, warp, lane, ridx, t0, t1, gmax_bits);
     const float gmax = __uint_as_float(gmax_bits);
-    const float s = scale_for(gmax, max_scale != 0u);   // max / 127 (the reference), or max for the clamped scheme
     const bool fast = fast_quant_ok<T>(gmax);
+    // max / 127 (the reference), or max for the clamped scheme.  For the groups this kernel encodes itself (fast) the
+    // IEEE division by 127 is the two-operation form RN(m * r127 + RN(m * d127)) of codec_math.cuh: exact for every
+    // fp16 value and every bf16 value >= 2^-118 (oracle/verify_fastdiv.c, "scale"), a dozen instructions shorter
+    const float s = max_scale != 0u ? (gmax > 0.0f ? gmax : 1.0f)
+                                    : (fast ? __fmaf_rn(gmax, __uint_as_float(0x3c010204u), __fmul_rn(gmax, __uint_as_float(0x2e010204u)))
+                                            : scale_from_max(gmax));
     // a group whose max-abs is 0 (zeros, possibly NaNs: cache_engine.cpp:176-179 skips them and the cast maps
     // them to code 0) has the closed-form payload [0][255] x floor(G/255) + [0][G%255]: no second read
     const bool zero_group = active && gmax_bits == 0u;
@@ -631,7 +636,7 @@ compress_fast_kernel(const T* __restrict__ in, uint32_t n_groups, uint8_t* __res
     uint32_t heads = 0;
     bool cplx = !fast && !zero_group;
     bool longr = false;       // a chunk (or the halo) without any run boundary: the group takes the long-run path
-    uint32_t carry_q = 0, carry_d1 = 0, halo_nz0 = 0u, halo_nz1 = 0x80000000u;
+    uint32_t carry_d1 = 0, halo_tail = 1u;   // halo_tail: distance from the region's first position back to the last head before it
     if (active && fast) {
         if (ridx > 0) {
             // halo: the 16 elements before the region give the last code, the last delta and the
@@ -641,11 +646,9 @@ compress_fast_kernel(const T* __restrict__ in, uint32_t n_groups, uint8_t* __res
             const uint32_t qp = __shfl_up_sync(kFull, qh, 1);
             const uint32_t dh = (qh - qp) & 0xffu;
             const uint32_t dp = __shfl_up_sync(kFull, dh, 1);
-            const unsigned chg = __ballot_sync(kFull, lane >= 8 && lane < 16 && dh != dp) >> 8;   // 8 bits
-            halo_nz0 = ((chg & 1u) << 7) | ((chg & 2u) << 14) | ((chg & 4u) << 21) | ((chg & 8u) << 28);
-            halo_nz1 = ((chg & 16u) << 3) | ((chg & 32u) << 10) | ((chg & 64u) << 17) | ((chg & 128u) << 24);
-            carry_q = __shfl_sync(kFull, qh, 15);
-            carry_d1 = __shfl_sync(kFull, dh, 15) << 24;
+            const unsigned chg = __ballot_sync(kFull, lane >= 8 && lane < 16 && dh != dp) >> 8;   // bit i: position i - 8 starts a run
+            halo_tail = chg ? (uint32_t)__clz((int)chg) - 23u : 9u;
+            carry_d1 = __shfl_sync(kFull, (qh & 0xffu) | (dh << 24), 15);   // code in byte 0, delta in byte 3
             if (chg == 0) longr = true;   // a run of 9+ equal deltas reaches the region edge
         }
         const int src_lane = (lane + 31) & 31;
@@ -662,20 +665,18 @@ compress_fast_kernel(const T* __restrict__ in, uint32_t n_groups, uint8_t* __res
 #pragma unroll
             for (int j = 0; j < 4; ++j)
                 quantize_fast_pair_i<T>(rw[j], x[2 * j], x[2 * j + 1], r, rl, half_k, q[2 * j], q[2 * j + 1]);
-            // previous element's code: lane - 1, or (lane 0) lane 31 of the previous iteration
-            const uint32_t rq = __shfl_sync(kFull, q[7], src_lane);
-            const uint32_t pq = lane == 0 ? carry_q : rq;
-            carry_q = rq;
+            // what the position in front of the chunk hands over -- its code (byte 0) and its delta (byte 3) -- comes in
+            // ONE shuffle: from lane - 1, or (lane 0) from lane 31 of the previous iteration
             uint32_t d[8];
-            d[0] = q[0] - pq;
 #pragma unroll
             for (int j = 1; j < 8; ++j) d[j] = q[j] - q[j - 1];
+            const uint32_t rx = __shfl_sync(kFull, __byte_perm(q[7], d[7], 0x4000), src_lane);
+            const uint32_t px = lane == 0 ? carry_d1 : rx;
+            carry_d1 = rx;
+            d[0] = q[0] - px;
             const uint32_t d0 = __byte_perm(__byte_perm(d[0], d[1], 0x0040), __byte_perm(d[2], d[3], 0x0040), 0x5410);
             const uint32_t d1 = __byte_perm(__byte_perm(d[4], d[5], 0x0040), __byte_perm(d[6], d[7], 0x0040), 0x5410);
-            const uint32_t rd = __shfl_sync(kFull, d1, src_lane);
-            const uint32_t pd1 = lane == 0 ? carry_d1 : rd;
-            carry_d1 = rd;
-            const uint32_t dsh0 = __byte_perm(pd1, d0, 0x6543);
+            const uint32_t dsh0 = __byte_perm(px, d0, 0x6543);
             const uint32_t dsh1 = __byte_perm(d0, d1, 0x6543);
             const uint32_t x0 = d0 ^ dsh0, x1 = d1 ^ dsh1;
             uint32_t nz0 = (((x0 & 0x7f7f7f7fu) + 0x7f7f7f7fu) | x0) & 0x80808080u;
@@ -737,7 +738,7 @@ compress_fast_kernel(const T* __restrict__ in, uint32_t n_groups, uint8_t* __res
     const uint32_t sbase = reg_s - 16u - 2u * (uint32_t)(p0 & ~7);   // pair i is staged at sbase + 2*i
     // tail = distance from the end of a lane chunk back to its last head; the next chunk's first
     // pair closes a run of that length (+ its own offset)
-    uint32_t carry_tail = halo_nz1 ? ((uint32_t)__clz((int)halo_nz1) >> 3) + 1u : ((uint32_t)__clz((int)halo_nz0) >> 3) + 5u;
+    uint32_t carry_tail = halo_tail;
     const int src_lane = (lane + 31) & 31;
 #ifndef SPECKV_UNROLL_2B
 #define SPECKV_UNROLL_2B 8
@@ -827,7 +828,8 @@ decompress_fast_kernel(const uint8_t* __restrict__ payload, size_t slot_bytes, c
                        const uint32_t* __restrict__ comp_bytes, uint32_t n_groups, T* __restrict__ out,
                        uint32_t* __restrict__ out_elems, uint32_t* __restrict__ needs_generic,
                        const uint32_t* __restrict__ src_index, const uint64_t* __restrict__ slot_offsets,
-                       const uint32_t* __restrict__ elem_index, const uint32_t* __restrict__ n_groups_dev) {
+                       const uint32_t* __restrict__ elem_index, const uint32_t* __restrict__ n_groups_dev,
+                       uint32_t* __restrict__ runs_list, uint32_t* __restrict__ runs_counters, uint2* __restrict__ runs_prefix) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     FastSmem& sm = *reinterpret_cast<FastSmem*>(smem_raw);
     constexpr int C = R > kW ? R / kW : 1;
@@ -1026,6 +1028,7 @@ decompress_fast_kernel(const uint8_t* __restrict__ payload, size_t slot_bytes, c
     // ---- A. region totals: elements produced (sum of counts) and code advance (sum of value*count) ----
     uint32_t csum = 0, ssum = 0, nnz = 0;
     bool fill = false;   // region decoded as a constant fill (all pair values zero) instead of through the staging area
+    bool runs = false;   // region expands beyond what in-place staging holds: the group goes to the run-expansion path
     if (np > 0) {
         mbar_wait(mb, 0);
 #pragma unroll
@@ -1071,27 +1074,45 @@ decompress_fast_kernel(const uint8_t* __restrict__ payload, size_t slot_bytes, c
                 vor |= (w.x | w.y | w.z | w.w) & 0x00ff00ffu;
             }
             fill = __reduce_or_sync(kFull, vor) == 0u;
-            if (!fill) cplx = true;
+            if (!fill) runs = true;
         }
+        // a pair with count 0 (never written by the encoder) emits nothing: such payloads keep to the generic kernel,
+        // whose tables allow several pairs at one output position
+        if (nnz != np) cplx = true;
     }
     if (C > 1) cluster_wait();   // all CTAs of the cluster are running: their shared memory may be written
     group_publish<R>(sm, sm.xa, 0, warp, lane, ridx, min(csum, G + 1u));   // saturated: sums stay < 2^32, "> G" still shows
     // xb: code advance (8 bits; the sum over <= 128 regions stays below bit 16) | "needs the generic kernel" counted
-    // in bits 16..23 | "short dequantiser differs" counted in bits 24..31
-    group_publish<R>(sm, sm.xb, 0, warp, lane, ridx, ssum | (cplx ? (1u << 16) : 0u) | (deq_differs ? (1u << 24) : 0u));
+    // in bits 16..23 | "short dequantiser differs" counted in bits 24..30 | bit 31 "needs the run-expansion path" (read
+    // from the MAXIMUM over the regions' words; in the sum it only disturbs bit 31, which nobody reads)
+    group_publish<R>(sm, sm.xb, 0, warp, lane, ridx,
+                     ssum | (cplx ? (1u << 16) : 0u) | (deq_differs ? (1u << 24) : 0u) | (runs ? (1u << 31) : 0u));
     group_sync<R>(sm, 0);
-    uint32_t e_before, e_total, q_before, xb_total, t0;
+    uint32_t e_before, e_total, q_before, xb_total, xb_max, t0;
     group_reduce<R>(sm.xa, warp, lane, ridx, e_before, e_total, t0);
-    group_reduce<R>(sm.xb, warp, lane, ridx, q_before, xb_total, t0);
+    group_reduce<R>(sm.xb, warp, lane, ridx, q_before, xb_total, xb_max);
     if (!active) {
         if (in_grid && ridx == 0 && lane == 0) needs_generic[g] = 0u;
         return;
     }
     const bool any_cplx = ((xb_total >> 16) & 0xffu) != 0 || e_total > G;   // output longer than the group: generic kernel clips
-    const bool short_deq = (xb_total >> 24) == 0;
+    const bool any_runs = !any_cplx && (xb_max >> 31) != 0u;
+    const bool short_deq = ((xb_total >> 24) & 0x7fu) == 0;
     if (ridx == 0 && lane == 0) {
-        needs_generic[g] = any_cplx ? 1u : 0u;
+        needs_generic[g] = any_cplx ? 1u : (any_runs ? 2u : 0u);
         if (out_elems && !any_cplx) out_elems[g] = e_total;
+    }
+    if (any_runs) {
+        // hand the group over with what phase A found: where every pairs-region starts in the output and with which
+        // code; the second pass expands output region by output region (kv_codec_generic.cu, decode_runs_region)
+        if (lane == 0) {
+            runs_prefix[(size_t)g * (R + 1) + ridx] = make_uint2(e_before, q_before & 0xffu);
+            if (ridx == 0) {
+                runs_prefix[(size_t)g * (R + 1) + R] = make_uint2(e_total, 0u);
+                runs_list[atomicAdd(runs_counters, 1u)] = g;
+            }
+        }
+        return;
     }
     if (any_cplx || np == 0) return;
 
@@ -1344,7 +1365,11 @@ cudaError_t compress_fast_t(int R, const CodecArgs& a, uint32_t* flags, cudaStre
 }
 
 template <typename T>
-cudaError_t decompress_fast_t(int R, const CodecArgs& a, uint32_t* flags, cudaStream_t st) {
+cudaError_t decompress_fast_t(int R, const CodecArgs& a, const DecodeScratch& scr, cudaStream_t st) {
+    uint32_t* flags = scr.flags;
+    uint32_t* rl = scr.list;
+    uint32_t* rc = scr.counters;
+    uint2* rp = scr.prefix;
     const uint8_t* pay = static_cast<const uint8_t*>(a.payload);
     size_t sb = a.slot_bytes;
     const float* sc = a.scales;
@@ -1366,7 +1391,7 @@ cudaError_t decompress_fast_t(int R, const CodecArgs& a, uint32_t* flags, cudaSt
         count_launch();
         return cudaGetLastError();
     }
-    void* args[] = {&pay, &sb, &sc, &cb, &n, &out, &oe, &flags, &si, &so, &ei, &nd};
+    void* args[] = {&pay, &sb, &sc, &cb, &n, &out, &oe, &flags, &si, &so, &ei, &nd, &rl, &rc, &rp};
     switch (R) {
 #define SPECKV_CASE(RR) case RR: return launch_clustered(decompress_fast_kernel<T, RR>, RR, n, st, args);
         SPECKV_CASE(1) SPECKV_CASE(2) SPECKV_CASE(4) SPECKV_CASE(8) SPECKV_CASE(16) SPECKV_CASE(32) SPECKV_CASE(64) SPECKV_CASE(128)
@@ -1395,9 +1420,9 @@ cudaError_t launch_compress_fast(int R, const CodecArgs& a, uint32_t* flags, cud
     return a.dtype == DT_F16 ? compress_fast_t<__half>(R, a, flags, st) : compress_fast_t<__nv_bfloat16>(R, a, flags, st);
 }
 
-cudaError_t launch_decompress_fast(int R, const CodecArgs& a, uint32_t* flags, cudaStream_t st) {
-    return a.dtype == DT_F16 ? decompress_fast_t<__half>(R, a, flags, st)
-                             : decompress_fast_t<__nv_bfloat16>(R, a, flags, st);
+cudaError_t launch_decompress_fast(int R, const CodecArgs& a, const DecodeScratch& scratch, cudaStream_t st) {
+    return a.dtype == DT_F16 ? decompress_fast_t<__half>(R, a, scratch, st)
+                             : decompress_fast_t<__nv_bfloat16>(R, a, scratch, st);
 }
 
 }  // namespace speckv

@@ -12,6 +12,8 @@
 //                run_length_encode                     cache_engine.cpp:40-82,172-239
 //   decompress = run_length_decode + delta_decode + dequantize_from_int8
 //                                                      cache_engine.cpp:84-116,241-284
+#include <algorithm>
+
 #include "codec_math.cuh"
 #include "kv_codec.h"
 #include "device_ctx.h"
@@ -64,7 +66,7 @@ struct GroupIter {
                 if ((uint64_t)blockIdx.x + (uint64_t)t0 * gridDim.x >= n) return false;
                 __syncthreads();    // everybody is done with the previous chunk's words
                 const uint64_t i = (uint64_t)blockIdx.x + (uint64_t)(t0 + threadIdx.x) * gridDim.x;
-                const unsigned b = __ballot_sync(0xffffffffu, i < n && flags[i] != 0u);
+                const unsigned b = __ballot_sync(0xffffffffu, i < n && flags[i] == 1u);   // 2 = the run-expansion path's
                 if ((threadIdx.x & 31) == 0) smask[threadIdx.x >> 5] = b;
                 __syncthreads();
                 t0 += kThreads;
@@ -315,6 +317,201 @@ compress_rle_generic_kernel(const T* __restrict__ in, uint32_t G, uint32_t n_gro
 }
 
 // ---------------------------------------------------------------------------------
+// decompress, run expansion: the groups the tuned kernel flagged 2 (payloads whose runs outgrow its in-place
+// staging: constant stretches, zero tails, smooth data -- the regime where the codec actually compresses)
+// ---------------------------------------------------------------------------------
+// Output-stationary, one warp per OUTPUT region of 2048 elements, warps of the whole grid striding over
+// (flagged group, region) items, so a single flagged group still spreads over many warps.  The tuned kernel left,
+// per pairs-region, the number of elements and the code before it (DecodeScratch::prefix): a warp finds the
+// pairs-region its outputs start in, scans pairs from there (256 per step, counts and code advance by dp4a + one
+// warp scan), and records what its 2048 outputs need: one bit per output where a pair starts, the pairs' values in
+// table order, the code in front of the region.  Expansion then is the tuned kernel's arithmetic -- 8 deltas per
+// lane, running byte sums by dp4a, one warp scan, dequantise, one 16-byte store per lane -- after a gather: the
+// lane's 8 deltas are table bytes picked by a byte permute whose selector comes from a 256-entry table indexed by
+// the lane's 8 head bits.  Cost per element does not depend on the run lengths.  Counts are >= 1 here (payloads
+// with empty pairs keep to the generic kernel) and the decoded length is <= G.
+template <typename T> __device__ __forceinline__ uint32_t pack2_bits(float a, float b) { return 0u; }
+template <> __device__ __forceinline__ uint32_t pack2_bits<__half>(float a, float b) {
+    __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+}
+template <> __device__ __forceinline__ uint32_t pack2_bits<__nv_bfloat16>(float a, float b) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+}
+
+constexpr int kRunsTable = 2048 + 256 + 16;       // values of the pairs that can touch one output region (+ first partial step)
+struct RunsSmem {
+    uint32_t lut[256];                            // head bits of 8 outputs -> the two byte-permute selectors
+    uint32_t bitmap[kWarps][64];                  // bit i: output i of the region starts a pair
+    uint32_t wprefix[kWarps][64];                 // pairs started before bitmap word w
+    uint32_t table[kWarps][kRunsTable / 4];       // pair values, one byte each
+};
+
+template <typename T>
+__device__ __forceinline__ void decode_runs_region(RunsSmem& rs, int wid, int lane, const uint8_t* __restrict__ gp,
+                                                   uint32_t npairs, float s, const uint2* __restrict__ pre, uint32_t R,
+                                                   uint32_t o, T* __restrict__ gout) {
+    constexpr unsigned kAll = 0xffffffffu;
+    const uint32_t O0 = o * 2048u;
+    const uint32_t e_total = pre[R].x;
+    if (O0 >= e_total) return;
+    const uint32_t n_out = min(2048u, e_total - O0), Oend = O0 + n_out;
+    uint32_t* bm = rs.bitmap[wid];
+    uint32_t* wp = rs.wprefix[wid];
+    uint32_t* tb = rs.table[wid];
+    bm[lane] = 0u;
+    bm[lane + 32] = 0u;
+    // pairs-region the outputs start in = the number of regions that END at or before O0 (empty ones included);
+    // every lane holds up to four of the (elements, code) prefixes, the one of that region comes by shuffle
+    uint2 mine[4];
+    uint32_t cnt = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const uint32_t r = (uint32_t)lane + 32u * i;
+        mine[i] = r < R ? pre[r + 1] : make_uint2(0xffffffffu, 0u);
+        cnt += (r < R && mine[i].x <= O0) ? 1u : 0u;
+    }
+    const uint32_t r0 = __reduce_add_sync(kAll, cnt);
+    uint32_t ecur = 0, qcur = 0;                  // before pairs-region 0: nothing, code 0
+    if (r0 > 0) {
+        const uint32_t src = (r0 - 1u) & 31u, slot = (r0 - 1u) >> 5;
+        uint32_t ex = 0, qx = 0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const uint32_t a = __shfl_sync(kAll, mine[i].x, src), b = __shfl_sync(kAll, mine[i].y, src);
+            if (slot == (uint32_t)i) {
+                ex = a;
+                qx = b;
+            }
+        }
+        ecur = ex;
+        qcur = qx & 0xffu;
+    }
+    __syncwarp();
+    // ---- scan: head bits, value table, code in front of the region ----
+    uint32_t tbase = 0xffffffffu;                 // first pair of the first step that touches the region
+    uint32_t found = 0;                           // this lane saw the pair that covers O0: (table index << 8) | code at O0 - 1
+    bool have = false;
+    for (uint32_t pk = r0 * 2048u; pk < npairs && ecur < Oend; pk += 256u) {
+        const uint32_t pb = pk + 8u * lane;
+        const int nv = pb < npairs ? (int)min(8u, npairs - pb) : 0;
+        uint4 w = make_uint4(0u, 0u, 0u, 0u);
+        if (nv > 0) w = ldg_stream(reinterpret_cast<const uint4*>(gp + (size_t)pb * 2));   // slots are 16-byte aligned and so is pb * 2
+        if (nv < 8) {
+            uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                if (2 * i >= nv) ww[i] = 0u;
+                else if (2 * i + 1 >= nv) ww[i] &= 0x0000ffffu;
+            }
+            w = make_uint4(ww[0], ww[1], ww[2], ww[3]);
+        }
+        const uint32_t va = __byte_perm(w.x, w.y, 0x6420), ca = __byte_perm(w.x, w.y, 0x7531);
+        const uint32_t vb = __byte_perm(w.z, w.w, 0x6420), cb = __byte_perm(w.z, w.w, 0x7531);
+        const uint32_t cl = __dp4a(cb, 0x01010101u, __dp4a(ca, 0x01010101u, 0u));
+        const uint32_t sl = __dp4a(vb, cb, __dp4a(va, ca, 0u)) & 0xffu;
+        const uint32_t own = cl | (sl << 24);
+        uint32_t inc = own;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t t = __shfl_up_sync(kAll, inc, d);
+            if (lane >= d) inc += t;
+        }
+        const uint32_t tot = __shfl_sync(kAll, inc, 31);
+        const uint32_t step_end = ecur + (tot & 0xffffffu);
+        if (step_end > O0) {
+            if (tbase == 0xffffffffu) tbase = pk;
+            const uint32_t ti = pk - tbase + 8u * lane;
+            if (ti + 8u <= (uint32_t)kRunsTable) *reinterpret_cast<uint2*>(reinterpret_cast<uint8_t*>(tb) + ti) = make_uint2(va, vb);
+            uint32_t p = ecur + ((inc - own) & 0xffffffu);
+            uint32_t q = qcur + ((inc - own) >> 24);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const uint32_t v = (j < 4 ? va >> (8 * j) : vb >> (8 * (j - 4))) & 0xffu;
+                const uint32_t c = (j < 4 ? ca >> (8 * j) : cb >> (8 * (j - 4))) & 0xffu;
+                if (c != 0u && p < Oend && p + c > O0) {
+                    const uint32_t pos = max(p, O0) - O0;
+                    atomicOr(&bm[pos >> 5], 1u << (pos & 31u));
+                    if (p <= O0) {
+                        have = true;
+                        found = ((ti + (uint32_t)j) << 8) | ((q + v * (O0 - p)) & 0xffu);
+                    }
+                }
+                p += c;
+                q += v * c;
+            }
+        }
+        ecur = step_end;
+        qcur = (qcur + (tot >> 24)) & 0xffu;
+    }
+    const unsigned who = __ballot_sync(kAll, have);
+    found = __shfl_sync(kAll, found, who ? __ffs((int)who) - 1 : 0);
+    const uint32_t first_ti = found >> 8;
+    uint32_t qrun = found & 0xffu;                // code of output O0 - 1
+    __syncwarp();
+    // heads before every bitmap word (one scan for the whole region; the steps below then need none for the ranks)
+    {
+        const uint32_t w0 = bm[2 * lane], w1 = bm[2 * lane + 1];
+        const uint32_t n0 = (uint32_t)__popc(w0), n1 = (uint32_t)__popc(w1);
+        uint32_t inc = n0 + n1;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t t = __shfl_up_sync(kAll, inc, d);
+            if (lane >= d) inc += t;
+        }
+        wp[2 * lane] = inc - n0 - n1;
+        wp[2 * lane + 1] = inc - n1;
+    }
+    __syncwarp();
+    // ---- expansion: 256 outputs per step, 8 per lane ----
+    for (uint32_t k0 = 0; k0 < n_out; k0 += 256u) {
+        const uint32_t wi0 = (k0 >> 5) + (lane >> 2), bsh = 8u * (lane & 3u);
+        const uint32_t word = bm[wi0];
+        const uint32_t hb = (word >> bsh) & 0xffu;
+        const uint32_t before = wp[wi0] + (uint32_t)__popc(word & ((1u << bsh) - 1u));   // heads before the lane's chunk
+        // table index of the pair the lane's first byte comes from: the pair running into the chunk, or -- when the
+        // chunk's first output starts a pair -- that pair (the selectors count from there)
+        const uint32_t a = first_ti + before - 1u + (hb & 1u);
+        const uint32_t wi = a >> 2, sh = (a & 3u) * 8u;
+        const uint32_t x0 = tb[wi], x1 = tb[wi + 1], x2 = tb[wi + 2];
+        const uint32_t t0 = __funnelshift_r(x0, x1, sh), t1 = __funnelshift_r(x1, x2, sh);
+        const uint32_t sel = rs.lut[hb];
+        const uint32_t d0 = __byte_perm(t0, t1, sel & 0xffffu), d1 = __byte_perm(t0, t1, sel >> 16);
+        const uint32_t sl = __dp4a(d1, 0x01010101u, __dp4a(d0, 0x01010101u, 0u));
+        uint32_t inc = sl;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t t = __shfl_up_sync(kAll, inc, d);
+            if (lane >= d) inc += t;
+        }
+        const uint32_t qb = qrun + inc - sl;
+        const uint32_t q4 = __dp4a(d0, 0x01010101u, qb);
+        const uint32_t q8 = __dp4a(d1, 0x01010101u, q4);
+        float y[8];
+        y[0] = dequantize(__dp4a(d0, 0x00000001u, qb), s);
+        y[1] = dequantize(__dp4a(d0, 0x00000101u, qb), s);
+        y[2] = dequantize(__dp4a(d0, 0x00010101u, qb), s);
+        y[3] = dequantize(q4, s);
+        y[4] = dequantize(__dp4a(d1, 0x00000001u, q4), s);
+        y[5] = dequantize(__dp4a(d1, 0x00000101u, q4), s);
+        y[6] = dequantize(__dp4a(d1, 0x00010101u, q4), s);
+        y[7] = dequantize(q8, s);
+        const uint32_t e = k0 + 8u * lane;
+        if (sizeof(T) == 2 && e + 8u <= n_out) {
+            *reinterpret_cast<uint4*>(gout + O0 + e) = make_uint4(pack2_bits<T>(y[0], y[1]), pack2_bits<T>(y[2], y[3]),
+                                                                  pack2_bits<T>(y[4], y[5]), pack2_bits<T>(y[6], y[7]));
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                if (e + j < n_out) gout[O0 + e + j] = narrow<T>(y[j]);
+        }
+        qrun = (qrun + __shfl_sync(kAll, inc, 31)) & 0xffu;
+    }
+    __syncwarp();
+}
+
+// ---------------------------------------------------------------------------------
 // decompress, scheme INT8_DELTA_RLE
 // ---------------------------------------------------------------------------------
 template <typename T>
@@ -324,8 +521,46 @@ decompress_rle_generic_kernel(const uint8_t* __restrict__ payload, size_t slot_b
                               uint32_t G, uint32_t n_groups, T* __restrict__ out,
                               uint32_t* __restrict__ out_elems, const uint32_t* __restrict__ only_flagged,
                               const uint32_t* __restrict__ src_index, const uint64_t* __restrict__ slot_offsets,
-                              const uint32_t* __restrict__ elem_index, const uint32_t* __restrict__ n_groups_dev) {
+                              const uint32_t* __restrict__ elem_index, const uint32_t* __restrict__ n_groups_dev,
+                              const uint32_t* __restrict__ runs_list, uint32_t* __restrict__ runs_counters,
+                              const uint2* __restrict__ runs_prefix, uint32_t runs_R) {
     if (n_groups_dev) n_groups = min(n_groups, *n_groups_dev);   // request count held on the device
+    // ---- first the groups flagged for run expansion: warps of the whole grid stride over (group, output region) ----
+    if (runs_counters) {
+        __shared__ RunsSmem rs;
+        const uint32_t n_runs = *reinterpret_cast<const volatile uint32_t*>(runs_counters);
+        if (n_runs) {
+            {   // selectors: output j of a chunk takes table byte popc(heads up to and including j) - (head at 0)
+                const uint32_t hb = threadIdx.x;
+                uint32_t sel = 0;
+                for (int j = 0; j < 8; ++j) {
+                    const uint32_t idx = (uint32_t)__popc(hb & ((2u << j) - 1u)) - (hb & 1u);
+                    sel |= (idx & 7u) << (4 * j);
+                }
+                rs.lut[hb] = sel;
+            }
+            __syncthreads();
+            const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+            const uint64_t n_items = (uint64_t)n_runs * runs_R;
+            for (uint64_t it = (uint64_t)blockIdx.x * kWarps + wid; it < n_items; it += (uint64_t)gridDim.x * kWarps) {
+                const uint32_t g = runs_list[it / runs_R], o = (uint32_t)(it % runs_R);
+                const uint32_t gi = src_index ? src_index[g] : g;
+                const uint8_t* gp = payload + (slot_offsets ? (size_t)slot_offsets[gi] : (size_t)gi * slot_bytes);
+                const uint32_t npairs = min(comp_bytes[gi] >> 1, runs_R * 2048u);
+                decode_runs_region<T>(rs, wid, lane, gp, npairs, scales[gi], runs_prefix + (size_t)g * (runs_R + 1), runs_R, o,
+                                      out + (size_t)(elem_index ? elem_index[g] : g) * G);
+            }
+        }
+        // the last CTA to get here clears the list for the next call (every CTA has read the count by then)
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence();
+            if (atomicAdd(runs_counters + 1, 1u) == gridDim.x - 1) {
+                runs_counters[0] = 0u;
+                runs_counters[1] = 0u;
+            }
+        }
+    }
     // Output-stationary expansion: a chunk of 2048 pairs is scanned once (start position and
     // starting code of every pair go to shared memory); then every thread produces 16 consecutive
     // output elements at a time -- binary search for the pair covering its first element, then a
@@ -567,14 +802,21 @@ static cudaError_t launch_compress_t(const CodecArgs& a, cudaStream_t st, const 
 }
 
 template <typename T>
-static cudaError_t launch_decompress_t(const CodecArgs& a, cudaStream_t st, const uint32_t* only_flagged) {
+static cudaError_t launch_decompress_t(const CodecArgs& a, cudaStream_t st, const uint32_t* only_flagged, const DecodeScratch* runs) {
     T* out = static_cast<T*>(a.out);
     const uint8_t* pay = static_cast<const uint8_t*>(a.payload);
-    const int grid = grid_for(a.n_groups, a.sm_count, 8);
+    int grid = grid_for(a.n_groups, a.sm_count, 8);
+    if (runs) {   // a few flagged groups still spread over the device: one warp per output region, up to 2 CTAs per SM
+        const long long want = ((long long)a.n_groups * runs->regions + kWarps - 1) / kWarps;
+        const long long cap = (long long)a.sm_count * 2;
+        grid = (int)std::max<long long>(grid, std::min(want, cap));
+    }
     if (scheme_is_rle(a.scheme)) {
         decompress_rle_generic_kernel<T><<<grid, kThreads, 0, st>>>(pay, a.slot_bytes, a.scales, a.comp_bytes,
                                                                     a.group_elems, a.n_groups, out, a.out_elems, only_flagged, a.src_index,
-                                                                    a.slot_offsets, a.elem_index, a.n_groups_dev);
+                                                                    a.slot_offsets, a.elem_index, a.n_groups_dev,
+                                                                    runs ? runs->list : nullptr, runs ? runs->counters : nullptr,
+                                                                    runs ? runs->prefix : nullptr, runs ? runs->regions : 0u);
     } else {
         decompress_int8_generic_kernel<T><<<grid, kThreads, 0, st>>>(pay, a.slot_bytes, a.scales, a.comp_bytes,
                                                                      a.group_elems, a.n_groups, out, a.out_elems, only_flagged,
@@ -601,7 +843,7 @@ cudaError_t launch_compress_generic(const CodecArgs& a, cudaStream_t st, const u
     }
 }
 
-cudaError_t launch_decompress_generic(const CodecArgs& a, cudaStream_t st, const uint32_t* only_flagged) {
+cudaError_t launch_decompress_generic(const CodecArgs& a, cudaStream_t st, const uint32_t* only_flagged, const DecodeScratch* runs) {
     if (a.n_groups == 0) return cudaSuccess;
     if (a.scheme == 0) {
         if (a.elem_index) return cudaErrorInvalidValue;
@@ -612,9 +854,9 @@ cudaError_t launch_decompress_generic(const CodecArgs& a, cudaStream_t st, const
         return cudaGetLastError();
     }
     switch (a.dtype) {
-        case DT_F16: return launch_decompress_t<__half>(a, st, only_flagged);
-        case DT_BF16: return launch_decompress_t<__nv_bfloat16>(a, st, only_flagged);
-        default: return launch_decompress_t<float>(a, st, only_flagged);
+        case DT_F16: return launch_decompress_t<__half>(a, st, only_flagged, runs);
+        case DT_BF16: return launch_decompress_t<__nv_bfloat16>(a, st, only_flagged, runs);
+        default: return launch_decompress_t<float>(a, st, only_flagged, runs);
     }
 }
 

@@ -115,6 +115,20 @@ int main(int argc, char** argv) {
     }
     printf("dequant: r127 bits=0x%08x (%.18g) d127 bits=0x%08x mismatches=%d\n", rb, r127, db, dbad);
     fail += dbad + (rb != 0x3c010204u) + (db != 0x2e010204u);
+    /* scale: m / 127 by the same two operations, for every fp16 value and every bf16 value (the tuned compress kernel
+     * uses it for the groups it encodes itself, i.e. bf16 max >= 2^-60; the identity only fails below 2^-118) */
+    {
+        long sbad = 0, slow = 0;
+        for (int bf = 0; bf < 2; ++bf)
+            for (uint32_t mh = 1; mh < 0x7f80; ++mh) {
+                if (!bf && mh >= 0x7c00) continue;
+                float m = bf ? b2f(mh) : h2f(mh);
+                float want = m / 127.0f, got = fmaf(m, r127, m * d127);
+                if (memcmp(&want, &got, 4)) { if (bf && m < 0x1p-60f) slow++; else sbad++; }
+            }
+        printf("scale: mismatches=%ld  [bf16 max < 2^-60 -> exact path; two-operation form would miss %ld]\n", sbad, slow);
+        fail += sbad;
+    }
     /* rounding identity: kernel rounding == roundf on a dense sweep incl. ties and 0.49999997 */
     long rbad = 0;
     for (int i = -3300000; i <= 3300000; ++i) {
