@@ -807,6 +807,28 @@ def run_cuda(args, rank, world, local_rank):
             r.pop("_x")
             return dict(r, workload=s2["label"], scaling="weak", unit=UNIT)
         leg("cfg2", cfg2)
+    if "schemes" in wanted:
+        def schemes():
+            # the same shard under the other schemes: 1 = the reference's codes only, 3 / 4 = the non-wrapping quantiser
+            # (extension ids; NOT reference behaviour) with and without delta + RLE
+            out = {}
+            for name in ("int8", "int8_clamp_delta_rle", "int8_clamp"):
+                r = codec_roundtrip(env, spec, max(1, min(args.steps, 5)), 3, use_graph, scheme=SCHEME_IDS[name])
+                xs = r.pop("_x")
+                rec = {"scheme_id": SCHEME_IDS[name], "value": r["value"], "unit": UNIT, "ms_per_step": r["ms_per_step"],
+                       "compression_ratio_vs_fp16": r["compression_ratio"]["vs_fp16"],
+                       "compress_frac_of_peak": r["roofline"]["compress"]["frac"], "decompress_frac_of_peak": r["roofline"]["decompress"]["frac"],
+                       "compress_kv_GB/s": r["roofline"]["compress"]["kv_GB/s"], "decompress_kv_GB/s": r["roofline"]["decompress"]["kv_GB/s"]}
+                if name == "int8_clamp" and not args.no_e2e:
+                    e = e2e_leg(env, spec, xs, args.steps, scheme=SCHEME_IDS[name])
+                    rec["e2e"] = {k: e[k] for k in ("value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step", "pcie_traffic_GBs", "frac_of_ceiling")}
+                del xs
+                out[name] = rec
+                env.torch.cuda.empty_cache()
+            return {"workload": spec["label"], "schemes": out,
+                    "note": "int8 = the reference's quantiser alone (wrapping codes, MSE ~ the data); the clamp schemes are this "
+                            "library's extension ids 3 / 4 (s = max|x|, non-wrapping; aux.ratios gives their MSE)"}
+        leg("schemes", schemes)
     if "cfg5" in wanted:
         leg("cfg5", lambda: aux_cfg5(env, use_graph))
     if "tier" in wanted:
@@ -849,7 +871,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--workload", default="cfg3", choices=["cfg2", "cfg3", "cfg4p"], help="headline workload")
-    ap.add_argument("--aux", default="cfg2,cfg5,tier,ratios", help="comma list of sub-records to add (or 'none')")
+    ap.add_argument("--aux", default="cfg2,schemes,cfg5,tier,ratios", help="comma list of sub-records to add (or 'none')")
     ap.add_argument("--scale", type=float, default=1.0, help="fraction of the headline workload's layers (debug only; cfg2 / cfg4p)")
     ap.add_argument("--aux-scale", type=float, default=1.0, help="fraction of aux.cfg2's layers (debug only)")
     ap.add_argument("--tier-scale", type=float, default=1.0, help="fraction of aux.tier's layers (debug only)")

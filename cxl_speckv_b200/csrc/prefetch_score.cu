@@ -91,18 +91,26 @@ hidden_warp_kernel(const uint32_t* __restrict__ tokens, uint32_t batch, uint32_t
         my[idx] = tok < vocab ? __ldg(emb + (size_t)tok * emb_dim + j) : 0.0f;   // out-of-vocabulary ids embed to zeros, :149-160
     }
     __syncwarp();
-    if (lane != 0) return;
-    float h = 0.0f, c = 0.0f;
-    for (uint32_t t = 0; t < hist_len; ++t) {
-        float g = 0.0f;
-        for (uint32_t j = 0; j < nj; ++j) g = __fadd_rn(g, __fmul_rn(my[t * nj + j], 0.1f));
-        const float tg = (float)tanh((double)g);
-        for (uint32_t l = 0; l < layers; ++l) {
-            c = __fadd_rn(__fmul_rn(0.5f, c), __fmul_rn(0.5f, tg));
-            h = __fmul_rn(0.5f, (float)tanh((double)c));
+    // The candidate g_t and tanh(g_t) depend on token t alone: lane t computes them (the reference's sequential sum
+    // over j stays sequential inside the lane), 32 tokens at a time.  What is left of the recurrence is the cell
+    // update, c = 0.5 c + 0.5 tanh(g_t) once per layer, in token order; the hidden value is only read after the last
+    // step (every intermediate h = 0.5 tanh(c) of :145 is overwritten before anything uses it).
+    float c = 0.0f;
+    for (uint32_t t0 = 0; t0 < hist_len; t0 += 32) {
+        const uint32_t t = t0 + lane;
+        float tg = 0.0f;
+        if (t < hist_len) {
+            float g = 0.0f;
+            for (uint32_t j = 0; j < nj; ++j) g = __fadd_rn(g, __fmul_rn(my[t * nj + j], 0.1f));
+            tg = (float)tanh((double)g);
+        }
+        const uint32_t nt = min(32u, hist_len - t0);
+        for (uint32_t i = 0; i < nt; ++i) {
+            const float tgi = __shfl_sync(0xffffffffu, tg, (int)i);
+            for (uint32_t l = 0; l < layers; ++l) c = __fadd_rn(__fmul_rn(0.5f, c), __fmul_rn(0.5f, tgi));
         }
     }
-    h_out[b] = h;
+    if (lane == 0) h_out[b] = (hist_len && layers) ? __fmul_rn(0.5f, (float)tanh((double)c)) : 0.0f;
 }
 // very long windows / wide embeddings (the staging above would not fit): one thread per sequence
 __global__ void hidden_kernel(const uint32_t* __restrict__ tokens, uint32_t batch, uint32_t hist_len,
@@ -358,10 +366,12 @@ score_merge_kernel(const MergeArgs a) {
         const float* base = a.partials + (size_t)seq * a.n_partials * PW;
         for (uint32_t p = lane; p < a.n_partials; p += 32) mm = fmaxf(mm, base[(size_t)p * PW]);
         for (int o = 16; o > 0; o >>= 1) mm = fmaxf(mm, __shfl_xor_sync(0xffffffffu, mm, o));
-        double ss = 0.0;
+        // (the partial sums are fp32 sums of fp32 exponentials already; the tolerance on a confidence is 1e-7 absolute
+        // on values of a few 1e-5, so fp32 is ample here -- fp64 exp cost this kernel most of its time)
+        float ss = 0.0f;
         for (uint32_t p = lane; p < a.n_partials; p += 32) {
             const float* q = base + (size_t)p * PW;
-            ss += (double)q[1] * exp((double)q[0] - (double)mm);
+            ss += q[1] * expf(q[0] - mm);
 #pragma unroll
             for (int k = 0; k < K; ++k) list_insert<K>(lv, li, q[2 + k], __float_as_uint(q[2 + K + k]));
         }
@@ -395,11 +405,11 @@ score_merge_kernel(const MergeArgs a) {
             }
         }
         // lanes 0 .. k-1 hold prediction i = lane
-        const float denom = (float)ss;
+        const float denom = ss;
         bool keep = false;
         speckv_prefetch_request_t rq;
         if (lane < a.k) {
-            const float e = (float)exp((double)__fsub_rn(win_v, mm));
+            const float e = expf(__fsub_rn(win_v, mm));
             const float cf = __fdiv_rn(e, denom);                                   // logits[i] /= sum_exp, :183-185
             const uint32_t rid = a.req_ids ? a.req_ids[seq] : a.req_id;
             const uint64_t va = ((uint64_t)rid << 32) | ((uint64_t)a.layer_id << 16) | (uint64_t)(lane + 1);
