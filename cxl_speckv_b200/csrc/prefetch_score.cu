@@ -32,8 +32,12 @@
 //                         surviving PrefetchRequest records in sequence order behind a header that holds their count.
 // tanh and the k reported exp values are evaluated in fp64 and rounded once to fp32 (glibc's float versions are
 // within 1 ulp of that); parity is "same top-k ids, confidences within 1e-7", not bitwise.
+#include <algorithm>
 #include <cfloat>
+#include <cmath>
+#include <cstdlib>
 #include <mutex>
+#include <vector>
 
 #include "../../include/speckv_ext.h"
 #include "codec_math.cuh"
@@ -47,6 +51,9 @@ namespace {
 struct Predictor {
     float* d_emb = nullptr;
     float* d_wout = nullptr;
+    float* d_rowsum = nullptr;   // sum_j W[v][j] (fp64 sum rounded once), the rank-one form of the logits
+    uint32_t* d_cand = nullptr;  // the 16 first rows by (rowsum descending, id) and by (rowsum ascending, id)
+    float row_abs_max = 0.0f;    // max_v sum_j |W[v][j]| (rounded up): scales the error bound of the rank-one form
     uint32_t vocab = 0, emb_dim = 0, hidden = 0, layers = 0, hist_len = 0;
     int device = -1;
     // device-side prefetcher state (SpeculativePrefetcher's queue and counters, speculative_prefetcher.h:83-94)
@@ -326,6 +333,198 @@ score_partial_kernel(const float* __restrict__ wout, uint32_t vocab, uint32_t hi
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------
+// Rank-one scoring.  Every hidden unit carries the same value h (lstm_predictor.cpp:143-145), so the reference's
+// logit_v = fl(sum_j fl(h * W[v][j])) is, up to rounding, h * rowsum[v].  The standard bound for a recursive fp32 sum of
+// n products gives |logit_v - h * rowsum[v]| <= gamma_n * |h| * sum_j |W[v][j]|; with the rounding of rowsum and of the
+// product that is err = (n + 3) u / (1 - n u) * |h| * max_v sum_j |W[v][j]|, u = 2^-24 (+ a denormal allowance).
+// The ORDER of the approximate logits does not depend on the sequence at all: it is the order of rowsum (h > 0) or its
+// reverse (h < 0), so the 16 best rows of either order are found once, when the weights are loaded.  One CTA per sequence:
+//   1. candidates = the first KC rows of the order for sign(h).  If the weakest candidate's approximate logit is more
+//      than 2 err below the k-th best, every row outside the list is provably below the true k-th best: the true top-k
+//      are among the candidates;
+//   2. the candidates are re-scored with the reference's exact sequential sum and ranked by that (value, then lower id);
+//   3. the softmax denominator is summed over the approximate logits (relative error <= 2 err ~ 1e-5, far inside the
+//      1e-7 absolute tolerance on confidences of a few 1e-5);
+//   4. otherwise (near-ties wider than the list, h = 0, non-finite weights) the CTA walks the vocabulary with exact
+//      logits, online softmax and per-thread best-KC lists.
+// ids are therefore the exact method's ids.  Output: one partial per sequence in score_partial_kernel's format,
+// consumed by score_merge_kernel with n_partials = 1.
+constexpr int kCandMax = 16;
+
+// KC rounds of warp arg-max over the heads of the lanes' sorted lists; lane r ends up with the r-th best
+template <int KC>
+__device__ __forceinline__ void warp_select(float (&lv)[KC], uint32_t (&li)[KC], uint32_t lane, float& win_v, uint32_t& win_i) {
+    win_v = -FLT_MAX;
+    win_i = 0xffffffffu;
+    for (int r = 0; r < KC; ++r) {
+        float best = lv[0];
+        uint32_t idx = li[0];
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+            const uint32_t oi = __shfl_xor_sync(0xffffffffu, idx, o);
+            if (better(ob, oi, best, idx)) {
+                best = ob;
+                idx = oi;
+            }
+        }
+        if (li[0] == idx && idx != 0xffffffffu) {
+#pragma unroll
+            for (int i = 0; i + 1 < KC; ++i) {
+                lv[i] = lv[i + 1];
+                li[i] = li[i + 1];
+            }
+            lv[KC - 1] = -FLT_MAX;
+            li[KC - 1] = 0xffffffffu;
+        }
+        if (lane == (uint32_t)r) {
+            win_v = best;
+            win_i = idx;
+        }
+    }
+}
+
+template <int KC>
+__global__ void __launch_bounds__(kScoreThreads)
+score_rank1_kernel(const float* __restrict__ wout, const float* __restrict__ rowsum, const uint32_t* __restrict__ cand,
+                   uint32_t vocab, uint32_t hidden, const float* __restrict__ hvec, uint32_t batch, uint32_t k,
+                   float row_abs_max, uint32_t force_exact, float* __restrict__ partials) {
+    constexpr int PW = 2 + 2 * KC;
+    __shared__ float s_m[kScoreWarps], s_s[kScoreWarps];
+    __shared__ float s_v[kScoreWarps][KC];
+    __shared__ uint32_t s_i[kScoreWarps][KC];
+    constexpr int kRowChunk = 256;
+    __shared__ float s_rows[KC][kRowChunk + 1];   // (+1: the lanes read different rows at the same column)
+    const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t seq = blockIdx.x;
+    if (seq >= batch) return;
+    const float h = hvec[seq];
+    const float u = 5.9604644775390625e-08f;   // 2^-24
+    const float err = fabsf(h) * row_abs_max * ((float)(hidden + 3) * u / (1.0f - (float)hidden * u)) * 1.0001f +
+                      (float)(hidden + 3) * 1.5e-45f;
+    float* o = partials + (size_t)seq * PW;
+    const uint32_t nc = min((uint32_t)KC, vocab);
+    const uint32_t* cl = cand + (h < 0.0f ? kCandMax : 0);
+
+    // the whole CTA takes the same decision (same inputs)
+    bool exact = force_exact != 0u;
+    float M = 0.0f;
+    if (!exact) {
+        M = __fmul_rn(h, __ldg(rowsum + cl[0]));
+        const float a_k = __fmul_rn(h, __ldg(rowsum + cl[k - 1]));
+        const float a_last = __fmul_rn(h, __ldg(rowsum + cl[nc - 1]));
+        exact = !(vocab <= (uint32_t)KC || a_last < a_k - 2.0f * err);   // also taken for NaN bounds
+    }
+
+    float S = 0.0f, xv = -FLT_MAX;
+    uint32_t ci = 0xffffffffu;
+    if (!exact) {
+        // ---- softmax denominator over the approximate logits: independent terms, four accumulators per thread ----
+        float acc4[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+        for (uint32_t v0 = tid; v0 < vocab; v0 += 4 * kScoreThreads) {
+#pragma unroll
+            for (uint32_t q = 0; q < 4; ++q) {
+                const uint32_t v = v0 + q * kScoreThreads;
+                if (v < vocab) acc4[q] += __expf(__fmul_rn(h, __ldg(rowsum + v)) - M);
+            }
+        }
+        float ws = (acc4[0] + acc4[1]) + (acc4[2] + acc4[3]);
+        for (int o2 = 16; o2 > 0; o2 >>= 1) ws += __shfl_xor_sync(0xffffffffu, ws, o2);
+        if (lane == 0) s_s[warp] = ws;
+        // ---- exact re-scoring: the CTA stages the candidates' rows (chunks of kRowChunk columns), lane r of warp 0
+        //      runs the reference's sequential sum over row r (lstm_predictor.cpp:166-173) ----
+        if (warp == 0 && lane < nc) ci = cl[lane];
+        float acc = 0.0f;
+        for (uint32_t j0 = 0; j0 < hidden; j0 += kRowChunk) {
+            const uint32_t nj = min((uint32_t)kRowChunk, hidden - j0);
+            for (uint32_t idx = tid; idx < nc * nj; idx += kScoreThreads) {
+                const uint32_t r = idx / nj, j = idx - r * nj;
+                s_rows[r][j] = __fmul_rn(h, __ldg(wout + (size_t)cl[r] * hidden + j0 + j));   // h[j] * w, :170
+            }
+            __syncthreads();
+            if (warp == 0 && lane < nc)
+                for (uint32_t j = 0; j < nj; ++j) acc = __fadd_rn(acc, s_rows[lane][j]);       // logits[i] += ..., in j order
+            __syncthreads();
+        }
+        if (warp != 0) return;
+        if (lane < nc) xv = acc;
+        float ss = lane < kScoreWarps ? s_s[lane] : 0.0f;
+        for (int o2 = 16; o2 > 0; o2 >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o2);
+        S = ss;
+    } else {
+        // ---- exact pass over the vocabulary ----
+        float m = -FLT_MAX, se = 0.0f, bv[KC];
+        uint32_t bi[KC];
+#pragma unroll
+        for (int i = 0; i < KC; ++i) {
+            bv[i] = -FLT_MAX;
+            bi[i] = 0xffffffffu;
+        }
+        for (uint32_t v = tid; v < vocab; v += kScoreThreads) {
+            const float* w = wout + (size_t)v * hidden;
+            float x = 0.0f;
+            for (uint32_t j = 0; j < hidden; ++j) x = __fadd_rn(x, __fmul_rn(h, __ldg(w + j)));
+            if (x > m) {
+                se *= __expf(m - x);
+                m = x;
+            }
+            se += __expf(x - m);
+            if (better(x, v, bv[KC - 1], bi[KC - 1])) list_insert<KC>(bv, bi, x, v);
+        }
+        float wm = m;
+        for (int o2 = 16; o2 > 0; o2 >>= 1) wm = fmaxf(wm, __shfl_xor_sync(0xffffffffu, wm, o2));
+        float ws = se * __expf(m - wm);   // a thread without rows has se = 0
+        for (int o2 = 16; o2 > 0; o2 >>= 1) ws += __shfl_xor_sync(0xffffffffu, ws, o2);
+        float wv;
+        uint32_t wi;
+        warp_select<KC>(bv, bi, lane, wv, wi);
+        if (lane == 0) {
+            s_m[warp] = wm;
+            s_s[warp] = ws;
+        }
+        if (lane < KC) {
+            s_v[warp][lane] = wv;
+            s_i[warp][lane] = wi;
+        }
+        __syncthreads();
+        if (warp != 0) return;
+        float mm = lane < kScoreWarps ? s_m[lane] : -FLT_MAX;
+        for (int o2 = 16; o2 > 0; o2 >>= 1) mm = fmaxf(mm, __shfl_xor_sync(0xffffffffu, mm, o2));
+        float ss = lane < kScoreWarps ? s_s[lane] * __expf(s_m[lane] - mm) : 0.0f;
+        for (int o2 = 16; o2 > 0; o2 >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o2);
+        float lv[KC];
+        uint32_t li[KC];
+#pragma unroll
+        for (int i = 0; i < KC; ++i) {
+            lv[i] = lane < kScoreWarps ? s_v[lane][i] : -FLT_MAX;
+            li[i] = lane < kScoreWarps ? s_i[lane][i] : 0xffffffffu;
+        }
+        warp_select<KC>(lv, li, lane, xv, ci);
+        M = mm;
+        S = ss;
+    }
+    // ---- warp 0: rank by the exact order (all candidates are distinct rows) ----
+    uint32_t rank = 0;
+    for (int r = 0; r < KC; ++r) {
+        const float ov = __shfl_sync(0xffffffffu, xv, r);
+        const uint32_t oi = __shfl_sync(0xffffffffu, ci, r);
+        if (lane < KC && (uint32_t)r != lane && better(ov, oi, xv, ci)) ++rank;
+    }
+    // exact maximum = the best candidate; the sum was taken against M
+    float best = lane < KC ? xv : -FLT_MAX;
+    for (int o2 = 16; o2 > 0; o2 >>= 1) best = fmaxf(best, __shfl_xor_sync(0xffffffffu, best, o2));
+    if (lane == 0) {
+        o[0] = best;
+        o[1] = S * __expf(M - best);
+    }
+    if (lane < KC) {
+        if (ci == 0xffffffffu) rank = lane;   // fewer rows than candidates: the empty entries keep their places at the end
+        o[2 + rank] = xv;
+        o[2 + KC + rank] = __uint_as_float(ci);
+    }
+}
+
 // One warp per sequence: merge the P partials, evaluate the k confidences, filter by residency, stage the requests;
 // the last CTA compacts them in sequence order.
 struct MergeArgs {
@@ -499,6 +698,8 @@ score_merge_kernel(const MergeArgs a) {
 void free_predictor() {
     if (g_pred.d_emb) cudaFree(g_pred.d_emb);
     if (g_pred.d_wout) cudaFree(g_pred.d_wout);
+    if (g_pred.d_rowsum) cudaFree(g_pred.d_rowsum);
+    if (g_pred.d_cand) cudaFree(g_pred.d_cand);
     if (g_pred.d_ring) cudaFree(g_pred.d_ring);
     if (g_pred.d_total) cudaFree(g_pred.d_total);
     g_pred = Predictor();
@@ -565,12 +766,19 @@ speckv_status_t score_emit(const uint32_t* d_tokens, uint32_t batch, uint32_t k,
     int dev = -1;
     if (cudaGetDevice(&dev) != cudaSuccess || dev != g_pred.device) return SPECKV_ERR_INVAL;   // weights live on another device
     cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
-    const int KK = k <= 4 ? 4 : (k <= 8 ? 8 : 16);
+    // rank-one scoring (candidates from h * rowsum[v], exact re-scoring) keeps k + 2 or more candidates; the tiled
+    // exact kernel remains for k > 14 and for SPECKV_SCORE_EXACT=2 (=1: the rank-one kernel with exact logits only)
+    const char* ex_env = getenv("SPECKV_SCORE_EXACT");
+    const int ex_mode = ex_env ? atoi(ex_env) : 0;
+    const bool rank1 = g_pred.d_rowsum && k <= 14 && ex_mode != 2;
+    const int KK = rank1 ? (k <= 6 ? 8 : 16) : (k <= 4 ? 4 : (k <= 8 ? 8 : 16));
     const int PW = 2 + 2 * KK;
-    uint32_t n_partials = 0;
-    cudaError_t e = KK == 4 ? launch_partial<4, 8>(batch, nullptr, nullptr, n_partials, 1, st)
-                  : KK == 8 ? launch_partial<8, 4>(batch, nullptr, nullptr, n_partials, 1, st)
-                            : launch_partial<16, 2>(batch, nullptr, nullptr, n_partials, 1, st);
+    uint32_t n_partials = 1;
+    cudaError_t e = cudaSuccess;
+    if (!rank1)
+        e = KK == 4 ? launch_partial<4, 8>(batch, nullptr, nullptr, n_partials, 1, st)
+          : KK == 8 ? launch_partial<8, 4>(batch, nullptr, nullptr, n_partials, 1, st)
+                    : launch_partial<16, 2>(batch, nullptr, nullptr, n_partials, 1, st);
     // per-call scratch from the stream's persistent buffer (two calls on different streams never share it)
     const size_t off_h = 0, off_p = (((size_t)batch * 4) + 255) & ~(size_t)255;
     const size_t off_s = (off_p + (size_t)batch * n_partials * PW * 4 + 255) & ~(size_t)255;
@@ -618,9 +826,19 @@ speckv_status_t score_emit(const uint32_t* d_tokens, uint32_t batch, uint32_t k,
         hidden_kernel<<<(batch + 127) / 128, 128, 0, st>>>(d_tokens, batch, g_pred.hist_len, g_pred.d_emb, g_pred.vocab,
                                                            g_pred.emb_dim, g_pred.hidden, g_pred.layers, d_h,
                                                            reinterpret_cast<unsigned int*>(scratch + off_t));
-    e = KK == 4 ? launch_partial<4, 8>(batch, d_h, d_partials, n_partials, 0, st)
-      : KK == 8 ? launch_partial<8, 4>(batch, d_h, d_partials, n_partials, 0, st)
-                : launch_partial<16, 2>(batch, d_h, d_partials, n_partials, 0, st);
+    if (rank1) {
+        if (KK == 8)
+            score_rank1_kernel<8><<<batch, kScoreThreads, 0, st>>>(g_pred.d_wout, g_pred.d_rowsum, g_pred.d_cand, g_pred.vocab, g_pred.hidden, d_h,
+                                                                  batch, k, g_pred.row_abs_max, ex_mode == 1, d_partials);
+        else
+            score_rank1_kernel<16><<<batch, kScoreThreads, 0, st>>>(g_pred.d_wout, g_pred.d_rowsum, g_pred.d_cand, g_pred.vocab, g_pred.hidden, d_h,
+                                                                   batch, k, g_pred.row_abs_max, ex_mode == 1, d_partials);
+        e = cudaGetLastError();
+    } else {
+        e = KK == 4 ? launch_partial<4, 8>(batch, d_h, d_partials, n_partials, 0, st)
+          : KK == 8 ? launch_partial<8, 4>(batch, d_h, d_partials, n_partials, 0, st)
+                    : launch_partial<16, 2>(batch, d_h, d_partials, n_partials, 0, st);
+    }
     if (e != cudaSuccess) return status_of(e);
     MergeArgs m;
     m.partials = d_partials;
@@ -677,6 +895,38 @@ speckv_status_t speckv_ext_predictor_load(const float* h_embedding, const float*
     if (e == cudaSuccess) e = cudaMemset(g_pred.d_total, 0, sizeof(unsigned long long));
     if (e == cudaSuccess) e = cudaMemcpy(g_pred.d_emb, h_embedding, (size_t)vocab * emb_dim * sizeof(float), cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemcpy(g_pred.d_wout, h_output, (size_t)vocab * hidden * sizeof(float), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+        // rank-one form of the logits: row sums (fp64, rounded once) and the largest absolute row sum for its error bound
+        std::vector<float> rs(vocab);
+        double amax = 0.0;
+        for (uint32_t v = 0; v < vocab; ++v) {
+            const float* w = h_output + (size_t)v * hidden;
+            double sum = 0.0, asum = 0.0;
+            for (uint32_t j = 0; j < hidden; ++j) {
+                sum += (double)w[j];
+                asum += fabs((double)w[j]);
+            }
+            rs[v] = (float)sum;
+            if (!(asum <= amax)) amax = asum;   // a NaN row makes the bound NaN: every sequence then takes the exact pass
+        }
+        g_pred.row_abs_max = nextafterf((float)amax, INFINITY);
+        e = cudaMalloc((void**)&g_pred.d_rowsum, (size_t)vocab * sizeof(float));
+        if (e == cudaSuccess) e = cudaMemcpy(g_pred.d_rowsum, rs.data(), (size_t)vocab * sizeof(float), cudaMemcpyHostToDevice);
+        // candidate orders (ties by the lower id in both, as the final ranking does); NaN sums sort last and make the bound NaN
+        std::vector<uint32_t> idx(vocab), cand(2 * 16, 0u);
+        for (uint32_t v = 0; v < vocab; ++v) idx[v] = v;
+        const size_t nc = vocab < 16u ? vocab : 16u;
+        for (int dir = 0; dir < 2; ++dir) {
+            auto key = [&](uint32_t v) { return rs[v] != rs[v] ? -INFINITY : (dir ? -rs[v] : rs[v]); };
+            std::partial_sort(idx.begin(), idx.begin() + nc, idx.end(), [&](uint32_t a, uint32_t b) {
+                const float ka = key(a), kb = key(b);
+                return ka > kb || (ka == kb && a < b);
+            });
+            for (size_t i = 0; i < nc; ++i) cand[16 * dir + i] = idx[i];
+        }
+        if (e == cudaSuccess) e = cudaMalloc((void**)&g_pred.d_cand, cand.size() * sizeof(uint32_t));
+        if (e == cudaSuccess) e = cudaMemcpy(g_pred.d_cand, cand.data(), cand.size() * sizeof(uint32_t), cudaMemcpyHostToDevice);
+    }
     if (e == cudaSuccess && !g_h_counts) {
         e = cudaHostAlloc((void**)&g_h_counts, kEmitCalls * sizeof(unsigned long long), cudaHostAllocMapped | cudaHostAllocPortable);
         if (e == cudaSuccess) e = cudaHostGetDevicePointer((void**)&g_d_counts, g_h_counts, 0);

@@ -84,6 +84,48 @@ def test_predicted_blocks_are_decompressed(weights):
         assert torch.equal(y2.view(torch.int16), codec.decompress(c2)[idx.long()].view(torch.int16))
 
 
+def test_rank_one_scoring_equals_the_exact_kernels(weights, monkeypatch):
+    """The rank-one candidate pass + exact re-scoring (default) against the same kernel with exact logits everywhere
+    (SPECKV_SCORE_EXACT=1) and the tiled exact kernel (=2): identical ids, confidences within the tolerance."""
+    rng = np.random.default_rng(41)
+    for B, k in ((256, 4), (33, 7), (5, 12), (3, 1)):
+        toks = torch.from_numpy(rng.integers(0, 32000, (B, 16)).astype(np.int32)).to(DEV)
+        out = {}
+        for mode in ("0", "1", "2"):
+            monkeypatch.setenv("SPECKV_SCORE_EXACT", mode)
+            ids, conf, _ = prefetch.score(toks, k=k)
+            out[mode] = (ids.cpu().numpy().copy(), conf.cpu().numpy().copy())
+        monkeypatch.delenv("SPECKV_SCORE_EXACT")
+        for mode in ("1", "2"):
+            assert np.array_equal(out["0"][0], out[mode][0]), (B, k, mode)
+            assert np.abs(out["0"][1] - out[mode][1]).max() <= CONF_TOL
+
+
+def test_rank_one_scoring_falls_back_on_wide_ties(weights):
+    """Forty identical best rows (an exact tie wider than the candidate list) and an all-out-of-vocabulary window (h = 0,
+    every logit 0): the candidate pass cannot separate them, the CTA repeats the pass with exact logits -- ids are the
+    lowest row ids, as the oracle's."""
+    emb, wout = weights
+    w2 = wout.copy()
+    big = np.abs(w2[123]) + 0.07
+    rows = np.arange(500, 540)
+    w2[rows] = big
+    try:
+        prefetch.load_predictor(emb, w2, layers=2, history_len=16)
+        rng = np.random.default_rng(43)
+        hists = rng.integers(0, 32000, (6, 16)).astype(np.uint32)
+        hists[2, :] = 50000                                       # embeds to zeros: h = 0
+        ids, conf, _ = prefetch.score(torch.from_numpy(hists.astype(np.int32)).to(DEV), k=4)
+        ids, conf = ids.cpu().numpy(), conf.cpu().numpy()
+        for b in range(6):
+            oi, oc, _ = Port.lstm_predict(emb, w2, hists[b], k=4)
+            assert np.abs(conf[b] - oc).max() <= CONF_TOL
+            assert same_topk(ids[b].tolist(), oi.tolist(), oc.view(np.uint32).tolist()), (b, ids[b], oi)
+        assert ids[2].tolist() == [0, 1, 2, 3]
+    finally:
+        prefetch.load_predictor(emb, wout, layers=2, history_len=16)
+
+
 # ---- SpeculativePrefetcher::prefetch on the device: residency filter, request records, statistics --------------
 def _ref_prefetcher():
     from oracle.oracle import Ref
