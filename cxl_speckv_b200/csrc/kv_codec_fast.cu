@@ -64,6 +64,7 @@ struct FastSmem {
     uint32_t xa[kMaxR];   // region max bits | head count + flags | sum of counts
     uint32_t xb[kMaxR];   // sum of value*count + flags
     uint32_t xc[kMaxR];   // second round of xa (no reuse hazard between rounds)
+    uint32_t stash[kW];   // long-run groups: first | (last + 1) << 12 of the region's natural heads, between the two passes
 };
 
 // ---- PTX helpers ------------------------------------------------------------------
@@ -383,7 +384,7 @@ __device__ __forceinline__ void flush_region(uint32_t sbase, uint8_t* gout, int 
 // and "interior" forced heads (those after its first natural head) itself; the forced heads in the stretch before the
 // first natural head of a region depend on lower regions and are derived by every region for all lower regions from
 // the exchanged words (long_reduce).  The kernel reaches all of this through two calls that are deliberately NOT
-// inlined (long_region_interior, long_path): inlined, the long-run code costs the common path 5 %.
+// inlined (long_first_pass, long_path): inlined, the long-run code costs the common path 5 %.
 __device__ __forceinline__ uint32_t head_mask8(uint32_t nz0, uint32_t nz1) {   // bit j = position j of the chunk starts a run
     const uint32_t lo = (((nz0 >> 7) & 0x01010101u) * 0x01020408u) >> 24;
     const uint32_t hi = (((nz1 >> 7) & 0x01010101u) * 0x01020408u) >> 24;
@@ -406,37 +407,68 @@ __device__ __forceinline__ int forced_head_in(int c, int lead_len, int nb) {
     return pf < c + lead_len ? pf : -1;
 }
 
-// Second look at a region that has a chunk without a head (phase 2a parked {dsh0, dsh1, nz0, nz1} per lane and
-// iteration): counts the interior forced heads and finds the first / last natural head (positions relative to the
-// region; first = 2048 and last = -1 when there is none).
-__device__ __forceinline__ void long_region_scan(const uint8_t* reg, int lane, uint32_t& interior_forced, int& reg_first,
-                                                 int& reg_last) {
-    interior_forced = 0;
-    reg_first = 2048;
-    reg_last = -1;
-    for (int k = 0; k < kIters; ++k) {
-        const uint4 st = lds128(reg + k * 512 + lane * 16);
-        const uint32_t m = head_mask8(st.z, st.w);
-        const int c = k * 256 + lane * 8;
-        const int own_last = m ? c + (31 - __clz((int)m)) : -1;
-        const int incl = warp_scan_max(own_last, lane);
-        const int excl = __shfl_up_sync(kFull, incl, 1);
-        const int nb = lane == 0 ? reg_last : max(reg_last, excl);
-        const int lead_len = m ? __ffs((int)m) - 1 : 8;
-        const bool forced = forced_head_in(c, lead_len, nb) >= 0;
-        interior_forced += (uint32_t)__popc(__ballot_sync(kFull, forced));
-        const int fpos = m ? c + lead_len : 2048;
-        reg_first = min(reg_first, __reduce_min_sync(kFull, fpos));
-        reg_last = max(reg_last, __shfl_sync(kFull, incl, 31));
-    }
-}
+// x / 255 for any 32-bit x
+__device__ __forceinline__ uint32_t div255(uint32_t x) { return __umulhi(x, 0x80808081u) >> 7; }
 
-// the same for the kernel body: results by value (interior forced heads), no locals whose address escapes
-__device__ __noinline__ uint32_t long_region_interior(const uint8_t* reg, int lane) {
-    uint32_t interior;
-    int f, l;
-    long_region_scan(reg, lane, interior, f, l);
-    return interior;
+// Selector table of the head-stationary emission: nibble i of entry m = position of the i-th set bit of m (0 beyond
+// popc(m)), so that two byte permutes bring the values (and the positions) of a chunk's heads to the front.  It lives
+// in global memory (1 KiB, L1-resident): the lanes index it with different masks, which a __constant__ bank would serialise.
+struct HeadSelTable {
+    uint32_t v[256];
+    constexpr HeadSelTable() : v() {
+        for (int m = 0; m < 256; ++m) {
+            uint32_t sel = 0;
+            int n = 0;
+            for (int j = 0; j < 8; ++j)
+                if ((m >> j) & 1) sel |= (uint32_t)j << (4 * n++);
+            v[m] = sel;
+        }
+    }
+};
+__device__ const HeadSelTable kHeadSel = HeadSelTable();
+
+// First pass over a region of a long-run group (phase 2a parked {dsh0, dsh1, nz0, nz1} per lane and iteration).  Per
+// chunk: the head mask m (8 bits) and nb, the last natural head before the chunk INSIDE the region -- "the nearest lower
+// lane with a head" is one ballot + one shuffle, the carry across iterations is warp-uniform.  Both are cached in the
+// chunk's own slot (word 2 = m | (nb_rel + 1) << 8; 0 = none yet in this region) for the emission pass.  Counts the
+// interior forced heads (the 255 cap, positions nb + 255 t inside a chunk's leading stretch) and leaves
+// first | (last + 1) << 12 of the region's natural heads in *stash (first = 2048, last + 1 = 0 when there is none).
+__device__ __forceinline__ uint32_t long_first_pass_body(uint8_t* reg, int lane, uint32_t* stash) {
+    const unsigned lt = (1u << lane) - 1u;
+    uint32_t forced_acc = 0;
+    int reg_last = -1, reg_first = 2048;
+    for (int k = 0; k < kIters; ++k) {
+        uint8_t* slot = reg + k * 512 + lane * 16;
+        const uint2 e = *reinterpret_cast<const uint2*>(slot + 8);
+        const uint32_t m = head_mask8(e.x, e.y);
+        const unsigned bal = __ballot_sync(kFull, m != 0u);
+        const int c = k * 256 + lane * 8;
+        const int own_last = c + 31 - __clz((int)m);
+        const unsigned pl = bal & lt;
+        const int t = __shfl_sync(kFull, own_last, pl ? 31 - __clz((int)pl) : 0);
+        const int nb = pl ? t : reg_last;
+        const int lead_len = m ? __ffs((int)m) - 1 : 8;
+        if (nb >= 0) {
+            const uint32_t d = (uint32_t)(c - nb);   // >= 1
+            forced_acc += div255(d + (uint32_t)lead_len - 1u) - div255(d - 1u);   // multiples of 255 in [d, d + lead_len)
+        }
+        *reinterpret_cast<uint32_t*>(slot + 8) = m | ((uint32_t)(nb + 1) << 8);
+        if (bal) {
+            if (reg_first == 2048) reg_first = __shfl_sync(kFull, c + lead_len, __ffs((int)bal) - 1);
+            reg_last = __shfl_sync(kFull, own_last, 31 - __clz((int)bal));
+        }
+    }
+    if (lane == 0) *stash = (uint32_t)reg_first | ((uint32_t)(reg_last + 1) << 12);
+    return __reduce_add_sync(kFull, forced_acc);
+}
+#ifdef SPECKV_LONG_INLINE
+#define SPECKV_LONG_ATTR __forceinline__
+#else
+#define SPECKV_LONG_ATTR __noinline__
+#endif
+// the kernel body calls it out of line (inlined there, the long-run code costs the common path 5 %)
+__device__ SPECKV_LONG_ATTR uint32_t long_first_pass(uint8_t* reg, int lane, uint32_t* stash) {
+    return long_first_pass_body(reg, lane, stash);
 }
 
 // Round-2 reduce of a group with long runs.  A: interior head count (low 20 bits) per region, B: first | (last + 1) << 12.
@@ -473,42 +505,76 @@ __device__ __forceinline__ void long_reduce(const uint32_t* A, const uint32_t* B
     nb_in = (int)__reduce_max_sync(kFull, (unsigned)(mine + 1)) - 1;
 }
 
-// Phase 2b of a region of a group with long runs: every iteration through the general routine.  Returns the pair
-// index after the region; prev_end = the last emitted head before the end of the region (for the final pair).
+// one 16-bit unit to shared memory under a predicate (stays a predicated STS: no branch)
+__device__ __forceinline__ void sts16_if(uint32_t a, uint32_t v, bool on) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.u32 p, %2, 0;\n"
+        "@p st.shared.b16 [%0], %1;\n"
+        "}" ::"r"(a),
+        "h"((unsigned short)v), "r"((uint32_t)on)
+        : "memory");
+}
+
+// Phase 2b of a region of a group with long runs.  Per chunk (from the slot: dsh0, dsh1 and the first pass's m | nb):
+// the previous emitted head before the chunk is nb + 255 * floor((c - 1 - nb) / 255); a forced head falls into the
+// chunk's leading stretch when the next multiple does; then the chunk's natural heads, head-stationary: the selector
+// table compacts their values and positions, the counts are the byte-wise differences of the positions (the first one
+// reaches back to the previous emitted head).  Iterations without any head are skipped after the vote.
+//
+// The body has NO lane-divergent branch: every store is predicated.  A first version stored the units through an
+// if / else ladder on (alignment, count) inside "if (m)"; on the B200 the lanes that skipped the block were then seen
+// to run on without the others (the shuffle that fetches lane 31's running count returned the reader's own value, the
+// loop's uniform counter was stepped by both halves) although the block ends in the compiler's reconvergence point --
+// bit-exact with printf in the loop, wrong without.  With at most the warp-uniform "continue" left, there is nothing
+// to reconverge.
+// Returns the pair index after the region; prev_end = the last emitted head before the end of the region.
 __device__ __forceinline__ int long_emit(const uint8_t* reg, uint32_t sbase, int lane, int rstart, int pidx, int nb_in,
                                          int& prev_end) {
-    int ln = nb_in;   // last natural head before the current iteration (group position)
-    int prev31 = 0;
+    int last_emitted = 0;
     for (int k = 0; k < kIters; ++k) {
         const uint4 st = lds128(reg + k * 512 + lane * 16);
         __syncwarp();   // every lane has read its slot before any pair of this iteration lands on it
-        const uint32_t m = head_mask8(st.z, st.w);
         const int c = rstart + k * 256 + lane * 8;
-        const int own_last = m ? c + (31 - __clz((int)m)) : -1;
-        const int incl = warp_scan_max(own_last, lane);
-        const int excl = __shfl_up_sync(kFull, incl, 1);
-        const int nb = lane == 0 ? ln : max(ln, excl);
+        const uint32_t m = st.z & 0xffu, nbr1 = st.z >> 8;
+        const int nb = nbr1 ? rstart + (int)nbr1 - 1 : nb_in;   // group position of the last natural head before the chunk
         const int lead_len = m ? __ffs((int)m) - 1 : 8;
-        const int pf = forced_head_in(c, lead_len, nb);
-        const int n = __popc(m) + (pf >= 0 ? 1 : 0);
-        const int inc = (int)warp_scan_inclusive((uint32_t)n);
-        int idx = pidx + inc - n;
-        int prev = nb >= 0 ? nb + 255 * ((c - 1 - nb) / 255) : 0;   // previous emitted head
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const uint32_t v = (j < 4 ? st.x >> (8 * j) : st.y >> (8 * (j - 4))) & 0xffu;   // delta[c + j - 1]
-            const int p = c + j;
-            if (((m >> j) & 1u) || p == pf) {
-                sts16(sbase + 2u * (uint32_t)idx, v | ((uint32_t)((p - prev) & 0xff) << 8));
-                ++idx;
-                prev = p;
-            }
+        int prev = 0, pf = 0x7fffffff;
+        if (nb >= 0) {
+            prev = nb + 255 * (int)div255((uint32_t)(c - 1 - nb));   // previous emitted head (natural or forced), <= c - 1
+            pf = prev + 255;                                        // the next forced head, >= c
         }
+        const bool forced = pf < c + lead_len;
+        const int nn = __popc(m), n = nn + (forced ? 1 : 0);
+        last_emitted = m ? c + 31 - __clz((int)m) : (forced ? pf : prev);
+        if (!__any_sync(kFull, n != 0)) continue;
+        const int inc = (int)warp_scan_inclusive((uint32_t)n);
+        const int idx = pidx + inc - n;
+        // the forced pair closes 255 positions of the run whose delta is delta[pf - 1] (byte pf - c of the shifted deltas)
+        const uint32_t fj = (uint32_t)(pf - c);   // 0 .. 7 when forced
+        sts16_if(sbase + 2u * (uint32_t)idx, ((((fj & 4u) ? st.y : st.x) >> (8u * (fj & 3u))) & 0xffu) | 0xff00u, forced);
+        if (forced) prev = pf;
+        const uint32_t a = sbase + 2u * (uint32_t)(idx + (forced ? 1 : 0));
+        const uint32_t sel = __ldg(&kHeadSel.v[m]);
+        const uint32_t v0 = __byte_perm(st.x, st.y, sel & 0xffffu), v1 = __byte_perm(st.x, st.y, sel >> 16);
+        const uint32_t p0 = __byte_perm(0x03020100u, 0x07060504u, sel & 0xffffu);
+        const uint32_t p1 = __byte_perm(0x03020100u, 0x07060504u, sel >> 16);
+        // counts: position differences; bytes beyond the last head are garbage (borrows only travel upwards)
+        const uint32_t c0 = p0 - (p0 << 8) + (uint32_t)(c - prev), c1 = p1 - __funnelshift_l(p0, p1, 8);
+        const uint32_t w0 = __byte_perm(v0, c0, 0x5140), w1 = __byte_perm(v0, c0, 0x7362);
+        const uint32_t w2 = __byte_perm(v1, c1, 0x5140), w3 = __byte_perm(v1, c1, 0x7362);
+        sts16_if(a, w0, nn > 0);
+        sts16_if(a + 2, w0 >> 16, nn > 1);
+        sts16_if(a + 4, w1, nn > 2);
+        sts16_if(a + 6, w1 >> 16, nn > 3);
+        sts16_if(a + 8, w2, nn > 4);
+        sts16_if(a + 10, w2 >> 16, nn > 5);
+        sts16_if(a + 12, w3, nn > 6);
+        sts16_if(a + 14, w3 >> 16, nn > 7);
         pidx += __shfl_sync(kFull, inc, 31);
-        ln = max(ln, __shfl_sync(kFull, incl, 31));
-        prev31 = __shfl_sync(kFull, prev, 31);
     }
-    prev_end = prev31;
+    prev_end = __shfl_sync(kFull, last_emitted, 31);
     return pidx;
 }
 
@@ -516,22 +582,14 @@ __device__ __forceinline__ int long_emit(const uint8_t* reg, uint32_t sbase, int
 // register allocation): a third exchange (first / last natural head per region), offsets from long_reduce, every
 // iteration through the general routine, the final pair, the flush.
 template <int R>
-__device__ __noinline__ void long_path(FastSmem& sm, uint8_t* reg, uint32_t reg_s, int warp, int lane, int ridx, bool longr,
+__device__ SPECKV_LONG_ATTR void long_path(FastSmem& sm, uint8_t* reg, uint32_t reg_s, int warp, int lane, int ridx, bool longr,
                                        uint32_t carry_d1, float s, uint8_t* gout, float* scale_out, uint32_t* comp_out) {
     constexpr uint32_t G = (uint32_t)R * kRegion;
-    int reg_first, reg_last;
-    if (longr) {
-        uint32_t unused;
-        long_region_scan(reg, lane, unused, reg_first, reg_last);
-    } else {   // without a head-less chunk they sit in the first and the last lane chunk
-        uint2 e = make_uint2(0u, 0u);   // lane 0 and lane 31 read the flags they parked themselves
-        if (lane == 0) e = *reinterpret_cast<const uint2*>(reg + 8);
-        else if (lane == 31) e = *reinterpret_cast<const uint2*>(reg + (kIters - 1) * 512 + 31 * 16 + 8);
-        const uint32_t m = head_mask8(e.x, e.y);
-        reg_first = __shfl_sync(kFull, __ffs((int)m) - 1, 0);
-        reg_last = __shfl_sync(kFull, (kIters - 1) * 256 + 31 * 8 + 31 - __clz((int)m), 31);
-    }
-    group_publish<R>(sm, sm.xb, 2, warp, lane, ridx, (uint32_t)reg_first | ((uint32_t)(reg_last + 1) << 12));
+    // regions with a head-less chunk ran the first pass in phase 2a (their interior forced heads went into round 2);
+    // the others run it now (no forced head can fall inside them): every slot then carries m | nb for the emission
+    if (!longr) long_first_pass_body(reg, lane, &sm.stash[warp]);
+    __syncwarp();
+    group_publish<R>(sm, sm.xb, 2, warp, lane, ridx, sm.stash[warp]);
     group_sync_own<R>(sm, 2, warp);
     uint32_t hb;
     int nb_in;
@@ -692,7 +750,7 @@ compress_fast_kernel(const T* __restrict__ in, uint32_t n_groups, uint8_t* __res
         heads = __reduce_add_sync(kFull, heads);
     }
     longr = __any_sync(kFull, longr);
-    if (longr && active && fast) heads += long_region_interior(reg, lane);   // forced heads behind the region's first natural head
+    if (longr && active && fast) heads += long_first_pass(reg, lane, &sm.stash[warp]);   // forced heads behind the region's first natural head
     // one word per region: head count (natural + interior forced, <= 2056) in the low 20 bits, "has long runs" counted
     // above.  "Needs the generic kernel" (a scale outside the fast quantiser's domain) follows from the group max,
     // which every region already has: no exchange needed.
@@ -1426,3 +1484,4 @@ cudaError_t launch_decompress_fast(int R, const CodecArgs& a, const DecodeScratc
 }
 
 }  // namespace speckv
+

@@ -31,8 +31,18 @@ for name, mk in (("runs300", lambda n: torch.randn((n * G + 299) // 300, device=
             p, s, cb = Port.compress_batch(raw, G, threads=8, scheme=scheme)
             want, wn = Port.decompress_batch(p, s, cb, G, 0, threads=8, scheme=scheme)
             ok = np.array_equal(y[:k].view(torch.int16).cpu().numpy().view(np.uint16), want.view(np.uint16)) and (oel == G).all().item()
+            # the compressed side: sizes, scales and payload bytes against the oracle
+            gcb = c.comp_bytes[:k].cpu().numpy()
+            okc = np.array_equal(gcb, cb) and np.array_equal(c.scales[:k].cpu().numpy().view(np.uint32), np.asarray(s).view(np.uint32))
+            gp = c.payload[:k].cpu().numpy()
+            pp = np.asarray(p).reshape(k, -1)
+            for i in range(k):
+                okc = okc and np.array_equal(gp[i, : int(cb[i])], pp[i, : int(cb[i])])
+            ok = ok and okc
             td = t(lambda: codec.decompress(c, out=y))
+            tc = t(lambda: codec.compress(x, G, scheme=scheme, out=c))
             cbs = float(c.comp_bytes.to(torch.int64).sum())
             print(f"{name:8s} n={n:4d} scheme {scheme}: {'ok ' if ok else 'BAD'} ratio {n*G*2/cbs:7.2f} decompress {td*1e3:8.1f} us "
-                  f"{n*G*2/td/1e6:7.0f} KV GB/s  alg {(n*G*2+cbs)/td/1e6/6553:5.3f} of peak", flush=True)
+                  f"{n*G*2/td/1e6:7.0f} KV GB/s  alg {(n*G*2+cbs)/td/1e6/6553:5.3f} of peak | compress {tc*1e3:8.1f} us "
+                  f"alg {(n*G*2+cbs)/tc/1e6/6553:5.3f} of peak", flush=True)
 print(codec.stats())

@@ -61,6 +61,8 @@ def main(seconds=120.0, seed=0):
         else:
             raw = bf16_from_f32(x)
             xd = torch.from_numpy(raw.astype(np.int16)).cuda().view(torch.bfloat16)
+        if os.environ.get("FUZZ_VERBOSE"):
+            print(f"case {cases}: G={G} n={n_groups} dtype={dtype}", file=sys.stderr, flush=True)
         c = codec.compress(xd, G)
         oel = torch.zeros(n_groups, dtype=torch.int32, device="cuda")
         y = codec.decompress(c, out_elems=oel)

@@ -633,6 +633,46 @@ def test_infinite_group_decodes_to_the_oracles_nan_bits(tdt):
     assert (got[1] == (0xFE00 if tdt == F16 else 0xFFC0)).any()
 
 
+@pytest.mark.parametrize("G", [2048, 16384, 32768, 131072])
+@pytest.mark.parametrize("tdt", [F16, BF16])
+def test_long_runs_then_dense_heads(G, tdt):
+    """Regions that start inside a long constant stretch (only forced heads: the 255 cap of cache_engine.cpp:223) and
+    turn into noise at an arbitrary position -- every lane chunk then holds a different number of run boundaries.
+    The first head-stationary emission of the long-run path lost all pairs after such a turn (fuzz seed 13, case 840:
+    the lanes without a boundary ran on without the others behind a lane-divergent store ladder); sizes, scales and
+    every payload byte against the oracle."""
+    rng = np.random.default_rng(840 + G)
+    n_groups = max(4, min(64, (2 << 20) // G))
+    x = rng.standard_normal(n_groups * G).astype(np.float32)
+    for g in range(n_groups):
+        pos = g * G + int(rng.integers(0, 8))
+        end = (g + 1) * G
+        while pos < end:
+            run = int(rng.choice([300, 700, 2048 + 3, 4904, 1016, 255, 256, 8 * int(rng.integers(1, 600)) + int(rng.integers(0, 8))]))
+            x[pos:min(end, pos + run)] = x[pos] if rng.random() < 0.5 else 0.0
+            pos += run
+            dense = int(rng.choice([1, 7, 9, 130, 1144, 2500])) + int(rng.integers(0, 16))
+            if rng.random() < 0.5:      # sparse boundaries: short runs of 1 .. 12
+                q = pos
+                while q < min(end, pos + dense):
+                    r = int(rng.integers(1, 13))
+                    x[q:min(end, q + r)] = x[q]
+                    q += r
+            pos += dense
+    raw = x.astype(np.float16) if tdt == F16 else bf16_from_f32(x)
+    xd = torch.from_numpy(raw).to(DEV) if tdt == F16 else torch.from_numpy(raw.astype(np.int16)).to(DEV).view(torch.bfloat16)
+    c = codec.compress(xd, G)
+    payload, scales, comp = Port.compress_batch(raw, G, dtype=tdt, threads=8)
+    assert np.array_equal(f32_bits(c.scales.cpu().numpy()), f32_bits(scales))
+    assert np.array_equal(c.comp_bytes.cpu().numpy().view(np.uint32), comp)
+    gp = c.payload.cpu().numpy()
+    for g in range(n_groups):
+        assert np.array_equal(gp[g, :comp[g]], payload[g, :comp[g]]), (g, comp[g])
+    y = codec.decompress(c)
+    want, _ = Port.decompress_batch(payload, scales, comp, G, tdt, threads=8)
+    assert np.array_equal(out_bits(y).reshape(-1), want.view(np.uint16).reshape(-1))
+
+
 def test_randomised_differential_run():
     """tests/fuzz_codec.py for a few seconds: random geometries, dtypes and value structures against the oracle."""
     from tests import fuzz_codec
