@@ -94,6 +94,17 @@ static speckv_status_t fetch_pages_locked(Runtime& rt, uint64_t handle, KvAlloca
 Runtime* runtime_locked() { return g_rt.get(); }
 std::mutex& runtime_mutex() { return g_mutex; }
 
+// A tier that is going away must not stay reachable through the pools bound to it (speckv_free, speckv_access and
+// speckv_prefetch dereference PoolBinding::tier): speckv_ext_tier_destroy calls this first.  Pages whose only copy
+// lived in that tier are gone with it; their flags keep saying "compressed, not resident", so a later access
+// reports SPECKV_ERR_INVAL (no tier) instead of touching freed memory.
+void runtime_unbind_tier(speckv_tier_t* tier) {
+    std::lock_guard<std::mutex> lock(g_mutex);
+    if (!g_rt) return;
+    for (auto& kv : g_rt->pools)
+        if (kv.second.tier == tier) kv.second.tier = nullptr;
+}
+
 }  // namespace speckv
 
 using namespace speckv;

@@ -50,16 +50,17 @@ struct GroupIter {
     __device__ GroupIter(const uint32_t* f, uint32_t n_groups, uint32_t* sm)
         : flags(f), n(n_groups), t0(0), word(kWarps), mask(0), smask(sm) {}
     __device__ bool next(uint32_t& g) {
-        if (!flags) {
-            g = blockIdx.x + t0 * gridDim.x;
+        if (!flags) {   // 64-bit index: n_groups may be close to 2^32, where blockIdx.x + t0 * gridDim.x wraps
+            const uint64_t gi = (uint64_t)blockIdx.x + (uint64_t)t0 * gridDim.x;
             ++t0;
-            return g < n;
+            g = (uint32_t)gi;
+            return gi < n;
         }
         for (;;) {
             if (mask) {
                 const uint32_t j = (uint32_t)__ffs((int)mask) - 1u;
                 mask &= mask - 1u;
-                g = blockIdx.x + (t0 - kThreads + (word - 1u) * 32u + j) * gridDim.x;
+                g = (uint32_t)((uint64_t)blockIdx.x + (uint64_t)(t0 - kThreads + (word - 1u) * 32u + j) * gridDim.x);   // < n: its flag was read
                 return true;
             }
             if (word == kWarps) {   // flags of the CTA's next kThreads groups

@@ -24,6 +24,8 @@
 
 namespace speckv {
 
+void runtime_unbind_tier(speckv_tier_t* tier);   // c_api.cu
+
 namespace {
 
 constexpr int kPackThreads = 256;
@@ -322,6 +324,7 @@ speckv_status_t speckv_ext_tier_create(size_t pool_bytes, speckv_tier_t** out_ti
 
 void speckv_ext_tier_destroy(speckv_tier_t* tier) {
     if (!tier) return;
+    speckv::runtime_unbind_tier(tier);   // pools bound to this tier (speckv_ext_bind_pool) forget it before it is freed
     Tier& t = tier->t;
     t.release_staging();
     for (int b = 0; b < Tier::kBuf; ++b) {
