@@ -79,7 +79,11 @@ static speckv_status_t fetch_pages_locked(Runtime& rt, uint64_t handle, KvAlloca
     for (uint64_t p = p0; p < p1; ++p) {
         KvPage& pg = a.pages[p];
         const bool resident = (pg.flags & (kFlagL1 | kFlagL2)) != 0;
-        if (!resident && (pg.flags & kFlagCompressed) && pb.tier) {
+        if (!resident && (pg.flags & kFlagCompressed)) {
+            if (!pb.tier) {   // its only copy went with a tier that was destroyed (runtime_unbind_tier): nothing to serve
+                flush();
+                return SPECKV_ERR_INVAL;
+            }
             if (ids.empty()) run_start = p;
             ids.push_back(pg.virt_page_id);
         } else {

@@ -22,6 +22,13 @@ struct CodecArgs {
                                              // decompress writes `out` there) instead of block i
     const uint32_t* n_groups_dev = nullptr;  // decompress, optional: device word holding the number of valid requests
                                              // (<= n_groups, which then is the capacity the grid is sized for)
+    // compress, optional -- packed emission: the payloads go back to back (16 B aligned) into `payload` instead of
+    // one slot per group; pack_offsets[g] receives the byte offset of group g, *pack_total the length of the stream.
+    // Offsets follow from a look-back over per-CTA status words inside the compress kernel (no pack pass); a group
+    // left to the generic kernel keeps a whole slot (its size is not known in the first pass).  Covered geometries:
+    // compress_packed_supported().
+    uint64_t* pack_offsets = nullptr;
+    uint64_t* pack_total = nullptr;
     size_t slot_bytes = 0;
     uint32_t group_elems = 0;
     uint32_t n_groups = 0;
@@ -59,7 +66,13 @@ cudaError_t launch_decompress_generic(const CodecArgs& a, cudaStream_t st, const
 // returns R when they cover the call, else 0; they set flags[g] = 1 for every group they leave
 // to the generic kernel.
 int fast_regions(const CodecArgs& a, bool decompress);
-cudaError_t launch_compress_fast(int R, const CodecArgs& a, uint32_t* flags, cudaStream_t st);
+bool compress_packed_supported(const CodecArgs& a);   // packed emission: fp16 / bf16 groups of 2048 elements (4 KiB pages), RLE schemes
+struct PackOut {                                      // kernel-side view of the packed emission (all null = one slot per group)
+    uint64_t* offsets = nullptr;
+    uint64_t* total = nullptr;
+    unsigned long long* status = nullptr;             // one word per CTA, zero before the launch
+};
+cudaError_t launch_compress_fast(int R, const CodecArgs& a, uint32_t* flags, cudaStream_t st, unsigned long long* pack_status = nullptr);
 cudaError_t launch_decompress_fast(int R, const CodecArgs& a, const DecodeScratch& scratch, cudaStream_t st);
 
 // dispatch: tuned kernels for the common geometries, generic otherwise (kv_codec_dispatch.cu)

@@ -19,8 +19,25 @@ static bool force_generic() {
     return v;
 }
 
+bool compress_packed_supported(const CodecArgs& a) {
+    return !force_generic() && scheme_is_rle(a.scheme) && fast_regions(a, false) == 1;
+}
+
 cudaError_t launch_compress(const CodecArgs& a, cudaStream_t st) {
     const int R = force_generic() ? 0 : fast_regions(a, false);
+    if (a.pack_offsets) {
+        // packed emission: one status word per CTA of the tuned kernel (16 page groups each), cleared for every launch
+        if (!a.pack_total || !compress_packed_supported(a)) return cudaErrorInvalidValue;
+        uint32_t* flags = nullptr;
+        unsigned long long* status = nullptr;
+        const size_t n_ctas = ((size_t)a.n_groups + 15) / 16;
+        cudaError_t e = scratch_persistent(reinterpret_cast<void**>(&flags), (size_t)a.n_groups * sizeof(uint32_t), st);
+        if (e == cudaSuccess) e = scratch_persistent(reinterpret_cast<void**>(&status), n_ctas * sizeof(unsigned long long), st, 2);
+        if (e == cudaSuccess) e = cudaMemsetAsync(status, 0, n_ctas * sizeof(unsigned long long), st);
+        if (e == cudaSuccess) e = launch_compress_fast(R, a, flags, st, status);
+        if (e == cudaSuccess) e = launch_compress_generic(a, st, flags);   // writes at pack_offsets[g] (a whole slot was reserved)
+        return e;
+    }
     if (R == 0) return launch_compress_generic(a, st, nullptr);
     // the per-group flag words live in a buffer that belongs to the stream and stays allocated: no allocation on
     // the call path, and the two launches can be captured into a CUDA graph

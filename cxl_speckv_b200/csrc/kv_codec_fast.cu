@@ -612,13 +612,75 @@ __device__ SPECKV_LONG_ATTR void long_path(FastSmem& sm, uint8_t* reg, uint32_t 
 }
 
 // ===================================================================================
+// compress: packed emission (page groups, R = 1)
+// ===================================================================================
+// The tier's offload wants the payloads back to back (what crosses PCIe), not one worst-case slot per group.  A
+// group's size is known once its run heads are counted (2 bytes per head), i.e. before any pair is staged, so the
+// compress kernel can place the groups itself: the 16 groups of a CTA are scanned in shared memory, the CTAs chain
+// through one status word each (decoupled look-back: [2-bit state | 62-bit bytes], state 1 = this CTA's total,
+// 2 = inclusive prefix; warp 0 polls 32 predecessors per step).  CTAs start in blockIdx order and a CTA waits only
+// for lower ones, so the chain always advances.  A group left to the generic kernel reserves a whole slot.
+enum : unsigned long long { kPackAgg = 1ull << 62, kPackIncl = 2ull << 62, kPackVal = (1ull << 62) - 1 };
+
+__device__ __forceinline__ unsigned long long warp_sum_u64(unsigned long long v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+    return v;
+}
+
+// byte offset of this warp's group in the packed stream; called by ALL warps of the CTA (two block barriers)
+__device__ __noinline__ unsigned long long pack_place(FastSmem& sm, const PackOut& pk, uint32_t my_bytes, int warp, int lane) {
+    if (lane == 0) sm.xb[warp] = my_bytes;
+    __syncthreads();
+    const uint32_t v = lane < kW ? sm.xb[lane] : 0u;
+    const uint32_t incl = warp_scan_inclusive(v);
+    const uint32_t before = __shfl_sync(kFull, incl - v, warp);
+    const uint32_t cta_total = __shfl_sync(kFull, incl, kW - 1);
+    if (warp == 0) {
+        unsigned long long prefix = 0;
+        volatile unsigned long long* status = pk.status;
+        const uint32_t b = blockIdx.x;
+        if (b != 0) {
+            if (lane == 0) status[b] = kPackAgg | cta_total;
+            long long base = (long long)b - 1;
+            for (;;) {
+                const long long idx = base - lane;
+                unsigned long long w;
+                do {
+                    w = idx >= 0 ? status[idx] : kPackIncl;   // in front of CTA 0: prefix 0
+                } while (__any_sync(kFull, (w >> 62) == 0ull));
+                const unsigned incl_mask = __ballot_sync(kFull, (w >> 62) == 2ull);
+                const unsigned long long val = w & kPackVal;
+                if (incl_mask) {   // the nearest predecessor that knows its prefix: everything behind it is included
+                    const int first = __ffs((int)incl_mask) - 1;
+                    prefix += warp_sum_u64(lane <= first ? val : 0ull);
+                    break;
+                }
+                prefix += warp_sum_u64(val);
+                base -= 32;
+            }
+        }
+        if (lane == 0) {
+            status[b] = kPackIncl | (prefix + cta_total);
+            sm.xc[kW] = (uint32_t)prefix;
+            sm.xc[kW + 1] = (uint32_t)(prefix >> 32);
+            if (b == gridDim.x - 1) *pk.total = prefix + cta_total;
+        }
+    }
+    __syncthreads();
+    return ((unsigned long long)sm.xc[kW] | ((unsigned long long)sm.xc[kW + 1] << 32)) + before;
+}
+
+// ===================================================================================
 // compress
 // ===================================================================================
-template <typename T, int R>
+template <typename T, int R, bool PACKED = false>
 __global__ void __launch_bounds__(kThreadsF, kCtasPerSm)
 compress_fast_kernel(const T* __restrict__ in, uint32_t n_groups, uint8_t* __restrict__ payload, size_t slot_bytes,
                      float* __restrict__ scales, uint32_t* __restrict__ comp_bytes,
-                     uint32_t* __restrict__ needs_generic, const uint32_t* __restrict__ elem_index, uint32_t max_scale) {
+                     uint32_t* __restrict__ needs_generic, const uint32_t* __restrict__ elem_index, uint32_t max_scale,
+                     const PackOut pk) {
+    static_assert(!PACKED || R == 1, "packed emission is built for page groups");
     extern __shared__ __align__(128) uint8_t smem_raw[];
     FastSmem& sm = *reinterpret_cast<FastSmem*>(smem_raw);
     constexpr int C = R > kW ? R / kW : 1;        // CTAs per group (cluster size)
@@ -761,6 +823,16 @@ compress_fast_kernel(const T* __restrict__ in, uint32_t n_groups, uint8_t* __res
     const bool any_cplx = cplx;
     const bool any_long = (h_total >> 20) != 0;
     h_before &= 0xfffffu;
+    size_t out_off = (size_t)g * slot_bytes;
+    if constexpr (PACKED) {
+        // bytes of this group: 2 per run head (the head at position 0 emits nothing, the open run at the end one pair),
+        // the closed form of a zero group, a whole slot for a group the generic kernel will encode
+        constexpr uint32_t zfull = G / 255u, zrem = G % 255u, znp = zfull + (zrem ? 1u : 0u);
+        uint32_t my = 0;
+        if (active) my = cplx ? (uint32_t)slot_bytes : (zero_group ? 2u * znp : 2u * (h_total & 0xfffffu));
+        out_off = (size_t)pack_place(sm, pk, (my + 15u) & ~15u, warp, lane);
+        if (active && lane == 0) pk.offsets[g] = out_off;
+    }
     if (!active) return;
     if (ridx == 0 && lane == 0) {
         needs_generic[g] = any_cplx ? 1u : 0u;
@@ -770,7 +842,7 @@ compress_fast_kernel(const T* __restrict__ in, uint32_t n_groups, uint8_t* __res
     if (zero_group) {
         if (ridx == 0) {
             constexpr uint32_t full = G / 255u, rem = G % 255u, npairs = full + (rem ? 1u : 0u);
-            uint16_t* go = reinterpret_cast<uint16_t*>(payload + (size_t)g * slot_bytes);
+            uint16_t* go = reinterpret_cast<uint16_t*>(payload + out_off);
             for (uint32_t i = lane; i < npairs; i += 32u) go[i] = i < full ? (uint16_t)0xff00u : (uint16_t)(rem << 8);
             if (lane == 0) {
                 scales[g] = s;   // 1.0f
@@ -780,7 +852,7 @@ compress_fast_kernel(const T* __restrict__ in, uint32_t n_groups, uint8_t* __res
         return;
     }
 
-    uint8_t* gout = payload + (size_t)g * slot_bytes;
+    uint8_t* gout = payload + out_off;
     if (any_long) {   // groups with long runs: everything else happens in long_path (not inlined)
         long_path<R>(sm, reg, reg_s, warp, lane, ridx, longr, carry_d1, s, gout, scales + g, comp_bytes + g);
         return;
@@ -1396,7 +1468,7 @@ cudaError_t launch_clustered(K kernel, int R, uint32_t n_groups, cudaStream_t st
 }
 
 template <typename T>
-cudaError_t compress_fast_t(int R, const CodecArgs& a, uint32_t* flags, cudaStream_t st) {
+cudaError_t compress_fast_t(int R, const CodecArgs& a, uint32_t* flags, cudaStream_t st, unsigned long long* pack_status) {
     const T* in = static_cast<const T*>(a.in);
     uint32_t n = a.n_groups;
     uint8_t* pay = static_cast<uint8_t*>(a.payload);
@@ -1405,7 +1477,15 @@ cudaError_t compress_fast_t(int R, const CodecArgs& a, uint32_t* flags, cudaStre
     uint32_t* cb = a.comp_bytes;
     const uint32_t* ei = a.elem_index;
     uint32_t ms = scheme_max_scale(a.scheme) ? 1u : 0u;
-    void* args[] = {&in, &n, &pay, &sb, &sc, &cb, &flags, &ei, &ms};
+    PackOut pko;
+    pko.offsets = a.pack_offsets;
+    pko.total = a.pack_total;
+    pko.status = pack_status;
+    void* args[] = {&in, &n, &pay, &sb, &sc, &cb, &flags, &ei, &ms, &pko};   // the codes-only kernels take the first nine
+    if (pack_status) {
+        if (R != 1 || scheme_is_codes(a.scheme) || !a.pack_offsets || !a.pack_total) return cudaErrorInvalidValue;
+        return launch_clustered(compress_fast_kernel<T, 1, true>, 1, n, st, args);
+    }
     if (scheme_is_codes(a.scheme)) {
         switch (R) {
 #define SPECKV_CASE(RR) case RR: return launch_clustered(compress_codes_fast_kernel<T, RR>, RR, n, st, args);
@@ -1474,8 +1554,9 @@ int fast_regions(const CodecArgs& a, bool decompress) {
     return (int)R;
 }
 
-cudaError_t launch_compress_fast(int R, const CodecArgs& a, uint32_t* flags, cudaStream_t st) {
-    return a.dtype == DT_F16 ? compress_fast_t<__half>(R, a, flags, st) : compress_fast_t<__nv_bfloat16>(R, a, flags, st);
+cudaError_t launch_compress_fast(int R, const CodecArgs& a, uint32_t* flags, cudaStream_t st, unsigned long long* pack_status) {
+    return a.dtype == DT_F16 ? compress_fast_t<__half>(R, a, flags, st, pack_status)
+                             : compress_fast_t<__nv_bfloat16>(R, a, flags, st, pack_status);
 }
 
 cudaError_t launch_decompress_fast(int R, const CodecArgs& a, const DecodeScratch& scratch, cudaStream_t st) {

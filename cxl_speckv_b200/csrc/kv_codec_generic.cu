@@ -186,7 +186,7 @@ compress_rle_generic_kernel(const T* __restrict__ in, uint32_t G, uint32_t n_gro
                             uint8_t* __restrict__ payload, size_t slot_bytes,
                             float* __restrict__ scales, uint32_t* __restrict__ comp_bytes,
                             const uint32_t* __restrict__ only_flagged, const uint32_t* __restrict__ elem_index,
-                            bool max_scale) {
+                            bool max_scale, const uint64_t* __restrict__ slot_offsets) {
     __shared__ __align__(16) uint16_t stage[kTile + 16];
     __shared__ int wbuf[kWarps];
     __shared__ float fbuf[kWarps];
@@ -198,7 +198,7 @@ compress_rle_generic_kernel(const T* __restrict__ in, uint32_t G, uint32_t n_gro
     GroupIter it(only_flagged, n_groups, smask);
     for (uint32_t g; it.next(g);) {
         const T* gin = in + (size_t)(elem_index ? elem_index[g] : g) * G;
-        uint8_t* gout = payload + (size_t)g * slot_bytes;
+        uint8_t* gout = payload + (slot_offsets ? (size_t)slot_offsets[g] : (size_t)g * slot_bytes);   // packed emission: the slot reserved by the tuned kernel
         const bool vec_ok = (reinterpret_cast<uintptr_t>(gin) & 15) == 0;
 
         // second pass behind the tuned kernel: that kernel already took the group max and left its bits in
@@ -792,7 +792,7 @@ static cudaError_t launch_compress_t(const CodecArgs& a, cudaStream_t st, const 
     if (scheme_is_rle(a.scheme)) {
         compress_rle_generic_kernel<T><<<grid, kThreads, 0, st>>>(in, a.group_elems, a.n_groups, pay, a.slot_bytes,
                                                                   a.scales, a.comp_bytes, only_flagged, a.elem_index,
-                                                                  scheme_max_scale(a.scheme));
+                                                                  scheme_max_scale(a.scheme), a.pack_offsets);
     } else {
         compress_int8_generic_kernel<T><<<grid, kThreads, 0, st>>>(in, a.group_elems, a.n_groups, pay, a.slot_bytes,
                                                                    a.scales, a.comp_bytes, only_flagged, a.elem_index,

@@ -414,11 +414,22 @@ static speckv_status_t tier_offload_impl(speckv_tier_t* tier, const void* d_in, 
         a.dtype = dtype;
         a.scheme = scheme;
         a.sm_count = current_sm_count();
-        if ((e = launch_compress(a, st)) != cudaSuccess) { rc = status_of(e); break; }
-        pack_offsets_kernel<<<1, 1024, 0, st>>>(t.d_comp[b], (uint32_t)ng, t.d_offsets[b], t.d_total[b]);
-        const int grid = (int)std::min<size_t>((ng + 7) / 8, (size_t)current_sm_count() * 8);
-        pack_kernel<<<grid, kPackThreads, 0, st>>>(t.d_slots[b], slot, t.d_comp[b], t.d_offsets[b], (uint32_t)ng, t.d_packed[b]);
-        count_launch(2);
+        if (compress_packed_supported(a)) {
+            // 4 KiB page groups: the compress kernel places the payloads itself (look-back over per-CTA totals), the
+            // packed stream is written once.  A group the generic kernel encodes keeps a whole slot inside the
+            // stream; the bytes behind its payload stay allocated in the pool until the tier is dropped (rare:
+            // non-finite or out-of-range scales).
+            a.payload = t.d_packed[b];
+            a.pack_offsets = t.d_offsets[b];
+            a.pack_total = t.d_total[b];
+            if ((e = launch_compress(a, st)) != cudaSuccess) { rc = status_of(e); break; }
+        } else {
+            if ((e = launch_compress(a, st)) != cudaSuccess) { rc = status_of(e); break; }
+            pack_offsets_kernel<<<1, 1024, 0, st>>>(t.d_comp[b], (uint32_t)ng, t.d_offsets[b], t.d_total[b]);
+            const int grid = (int)std::min<size_t>((ng + 7) / 8, (size_t)current_sm_count() * 8);
+            pack_kernel<<<grid, kPackThreads, 0, st>>>(t.d_slots[b], slot, t.d_comp[b], t.d_offsets[b], (uint32_t)ng, t.d_packed[b]);
+            count_launch(2);
+        }
         cudaEventRecord(t.ev_kernel[b], st);
         cudaStreamWaitEvent(t.copy_st[b], t.ev_kernel[b], 0);
         cudaMemcpyAsync(t.h_total[b], t.d_total[b], 8, cudaMemcpyDeviceToHost, t.copy_st[b]);

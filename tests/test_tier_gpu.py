@@ -58,6 +58,49 @@ def test_offload_restore_roundtrip(G, n_groups):
         tier.close()
 
 
+@pytest.mark.parametrize("tdt", [torch.float16, torch.bfloat16])
+def test_offload_page_groups_packed_emission(tdt):
+    """4 KiB page groups: the compress kernel places the payloads in the packed stream itself (look-back over per-CTA
+    totals, no pack pass).  Pages of every kind the kernel sizes differently -- noise, zero pages (closed form), constant
+    and long-run pages (long path), pages with +-inf / tiny magnitudes (left to the generic kernel: they keep a whole
+    slot inside the stream) -- over enough pages for look-back chains of hundreds of CTAs; every restored page must be
+    what the device codec gives, and the stored bytes must be the 16 B-rounded payloads plus those slots' slack."""
+    G, n_groups = 2048, 40000 + 7
+    g = torch.Generator(device=DEV)
+    g.manual_seed(99)
+    x = torch.randn(n_groups, G, device=DEV, generator=g)
+    kind = torch.randint(0, 10, (n_groups,), device=DEV, generator=g)
+    x[kind == 1] = 0.0
+    x[kind == 2] = 0.75
+    runs = (kind == 3).nonzero().flatten()
+    x[runs] = x[runs][:, ::300].repeat_interleave(300, dim=1)[:, :G]
+    half = (kind == 4).nonzero().flatten()
+    x[half, : G // 2 + 5] = 0.0
+    x = x.to(tdt)
+    special = (kind == 5).nonzero().flatten()
+    x[special[0::2], 17] = float("inf")
+    if tdt == torch.bfloat16:
+        x[special[1::2]] = (x[special[1::2]].float() * 1e-38).to(tdt)      # scales outside the short quantiser's domain
+    x = x.contiguous().view(-1)
+    tier = HostTier(pool_bytes=int(n_groups * G * 2 * 1.3) + (1 << 20))
+    try:
+        ids = np.arange(n_groups, dtype=np.uint64) + np.uint64(1000)
+        tier.offload(x, G, ids)
+        c = codec.compress(x, G)
+        want = codec.decompress(c)
+        y = tier.restore(ids, G, tdt)
+        assert torch.equal(y.view(torch.int16), want.view(torch.int16))
+        comp = c.comp_bytes.cpu().numpy().view(np.uint32).astype(np.int64)
+        rounded = int(((comp + 15) // 16 * 16).sum())
+        st = tier.stats()
+        assert rounded <= st["bytes_offloaded_stored"] <= rounded + int(special.numel()) * 4096
+        sel = np.random.default_rng(3).permutation(n_groups)[:513]
+        y2 = tier.restore(ids[sel], G, tdt)
+        assert torch.equal(y2.view(torch.int16), want[torch.from_numpy(sel).to(DEV)].view(torch.int16))
+    finally:
+        tier.close()
+
+
 def test_pool_exhaustion_is_reported():
     G, n_groups = 2048, 4096
     x = torch.randn(n_groups * G, device=DEV).half()
@@ -67,6 +110,38 @@ def test_pool_exhaustion_is_reported():
             tier.offload(x, G, np.arange(n_groups, dtype=np.uint64))
         assert ei.value.status == -3                       # SPECKV_ERR_NOMEM
     finally:
+        tier.close()
+
+
+def test_tier_destroyed_before_the_pool_handle():
+    """A tier closed while pools are still bound to it must leave no dangling pointer behind: access to a page whose
+    only copy went with the tier reports an error, resident pages keep working, speckv_free does not touch the
+    freed tier (advisor finding, c_api.cu PoolBinding::tier)."""
+    import ctypes as C
+
+    import cxl_speckv_b200 as pkg
+    from cxl_speckv_b200 import CxlSpeckvKVAllocator
+
+    alloc = CxlSpeckvKVAllocator(pkg.lib_path(), "cuda:0")
+    L = pkg.lib()
+    tier = HostTier(8 << 20)
+    try:
+        tokens, layers, heads, hd = 64, 1, 8, 128
+        h = alloc.allocate(tokens, layers, heads, hd, 2)
+        total = tokens * layers * heads * hd * 2 * 2
+        n_pages = total // 4096
+        pool = torch.randn(total // 2, device=DEV).half()
+        alloc.bind_pool(pool, tier)
+        alloc.offload_pages(0, n_pages // 2)             # the first half lives only in the tier now
+        tier.close()                                     # ... and the tier goes away first
+        ptr = C.c_void_p()
+        assert L.speckv_access(h, (n_pages - 1) * 4096, 16, C.byref(ptr)) == 0      # resident page: served
+        assert ptr.value == pool.data_ptr() + (n_pages - 1) * 4096
+        assert L.speckv_access(h, 0, 16, C.byref(ptr)) != 0                          # its copy is gone: an error, not a crash
+        alloc.prefetch_step(req_id=0, layer=0, cur_pos=1, recent_tokens=list(range(8)), depth_k=2)   # status discarded
+        assert L.speckv_free(h) == 0
+    finally:
+        alloc._speckv.finalize()
         tier.close()
 
 
