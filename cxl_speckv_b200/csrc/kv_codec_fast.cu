@@ -18,12 +18,14 @@
 // smem, max-abs and quantisation both read the smem tile), each output byte is
 // written once: the staged region leaves shared memory with one bulk-TMA store.
 //
-// The tuned kernels assume what holds for KV activations: no run of equal deltas
-// spans a whole 8-element lane chunk (compress) / ordinary payloads (decompress).
-// Groups that violate it (constant blocks, zeros, +-inf, tiny bf16 scales) are
-// flagged in `needs_generic` and re-done by the generic kernel
-// (kv_codec_generic.cu) in the same stream, so results are bit-exact for every
-// input.
+// The common path is built for what holds for KV activations: no run of equal deltas
+// spans a whole 8-element lane chunk (compress) / counts of 1 and 2 (decompress).
+// Groups with longer runs take the long-run routines of this file (compress) or the
+// run-expansion path of the second launch (decompress); zero groups are written in
+// closed form.  What remains -- +-inf, tiny or huge bf16 scales, malformed payloads --
+// is flagged in `needs_generic` and re-done by the generic kernel
+// (kv_codec_generic.cu) in the same stream, so results are bit-exact for every input.
+// Page groups (R = 1) can emit straight into a packed stream (pack_place).
 #include <cooperative_groups.h>
 
 #include <cstdlib>
@@ -399,14 +401,6 @@ __device__ __forceinline__ int warp_scan_max(int v, int lane) {
     }
     return v;
 }
-// the forced head of a chunk [c, c + lead_len) whose last natural head before it is nb (nb < c): position or -1
-__device__ __forceinline__ int forced_head_in(int c, int lead_len, int nb) {
-    if (nb < 0 || lead_len <= 0) return -1;
-    const int r = (c - nb) % 255;
-    const int pf = r == 0 ? c : c + 255 - r;
-    return pf < c + lead_len ? pf : -1;
-}
-
 // x / 255 for any 32-bit x
 __device__ __forceinline__ uint32_t div255(uint32_t x) { return __umulhi(x, 0x80808081u) >> 7; }
 
