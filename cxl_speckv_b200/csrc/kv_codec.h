@@ -28,7 +28,7 @@ struct CodecArgs {
     // left to the generic kernel keeps a whole slot (its size is not known in the first pass).  Covered geometries:
     // compress_packed_supported().
     uint64_t* pack_offsets = nullptr;
-    uint64_t* pack_total = nullptr;
+    uint64_t* pack_total = nullptr;          // receives the stream length, or ~0 when the placement failed (look-back timeout)
     size_t slot_bytes = 0;
     uint32_t group_elems = 0;
     uint32_t n_groups = 0;

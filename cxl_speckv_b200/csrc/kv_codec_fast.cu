@@ -614,7 +614,7 @@ __device__ SPECKV_LONG_ATTR void long_path(FastSmem& sm, uint8_t* reg, uint32_t 
 // through one status word each (decoupled look-back: [2-bit state | 62-bit bytes], state 1 = this CTA's total,
 // 2 = inclusive prefix; warp 0 polls 32 predecessors per step).  CTAs start in blockIdx order and a CTA waits only
 // for lower ones, so the chain always advances.  A group left to the generic kernel reserves a whole slot.
-enum : unsigned long long { kPackAgg = 1ull << 62, kPackIncl = 2ull << 62, kPackVal = (1ull << 62) - 1 };
+enum : unsigned long long { kPackAgg = 1ull << 62, kPackIncl = 2ull << 62, kPackErr = 1ull << 61, kPackVal = (1ull << 61) - 1 };
 
 __device__ __forceinline__ unsigned long long warp_sum_u64(unsigned long long v) {
 #pragma unroll
@@ -622,7 +622,10 @@ __device__ __forceinline__ unsigned long long warp_sum_u64(unsigned long long v)
     return v;
 }
 
-// byte offset of this warp's group in the packed stream; called by ALL warps of the CTA (two block barriers)
+// byte offset of this warp's group in the packed stream; called by ALL warps of the CTA (two block barriers).
+// A predecessor that never shows up (it cannot happen while CTAs start in blockIdx order) must not hang the device:
+// a poll gives up after ~10 s and marks its word; the mark travels down the chain and the stream's total becomes
+// ~0, which the host treats as a failed launch.
 __device__ __noinline__ unsigned long long pack_place(FastSmem& sm, const PackOut& pk, uint32_t my_bytes, int warp, int lane) {
     if (lane == 0) sm.xb[warp] = my_bytes;
     __syncthreads();
@@ -632,6 +635,7 @@ __device__ __noinline__ unsigned long long pack_place(FastSmem& sm, const PackOu
     const uint32_t cta_total = __shfl_sync(kFull, incl, kW - 1);
     if (warp == 0) {
         unsigned long long prefix = 0;
+        bool err = false;
         volatile unsigned long long* status = pk.status;
         const uint32_t b = blockIdx.x;
         if (b != 0) {
@@ -640,25 +644,25 @@ __device__ __noinline__ unsigned long long pack_place(FastSmem& sm, const PackOu
             for (;;) {
                 const long long idx = base - lane;
                 unsigned long long w;
+                uint32_t polls = 0;
                 do {
                     w = idx >= 0 ? status[idx] : kPackIncl;   // in front of CTA 0: prefix 0
+                    if (++polls == (1u << 23)) w = kPackIncl | kPackErr;   // ~1 us per poll
                 } while (__any_sync(kFull, (w >> 62) == 0ull));
                 const unsigned incl_mask = __ballot_sync(kFull, (w >> 62) == 2ull);
                 const unsigned long long val = w & kPackVal;
-                if (incl_mask) {   // the nearest predecessor that knows its prefix: everything behind it is included
-                    const int first = __ffs((int)incl_mask) - 1;
-                    prefix += warp_sum_u64(lane <= first ? val : 0ull);
-                    break;
-                }
-                prefix += warp_sum_u64(val);
+                const int first = incl_mask ? __ffs((int)incl_mask) - 1 : 31;   // the nearest predecessor that knows its prefix
+                err |= __any_sync(kFull, lane <= first && (w & kPackErr) != 0ull);
+                prefix += warp_sum_u64(lane <= first ? val : 0ull);
+                if (incl_mask) break;   // everything behind it is included
                 base -= 32;
             }
         }
         if (lane == 0) {
-            status[b] = kPackIncl | (prefix + cta_total);
+            status[b] = kPackIncl | (err ? kPackErr : 0ull) | ((prefix + cta_total) & kPackVal);
             sm.xc[kW] = (uint32_t)prefix;
             sm.xc[kW + 1] = (uint32_t)(prefix >> 32);
-            if (b == gridDim.x - 1) *pk.total = prefix + cta_total;
+            if (b == gridDim.x - 1) *pk.total = err ? ~0ull : prefix + cta_total;
         }
     }
     __syncthreads();

@@ -366,6 +366,7 @@ static speckv_status_t tier_offload_impl(speckv_tier_t* tier, const void* d_in, 
         cudaError_t e2 = cudaStreamSynchronize(t.copy_st[b]);   // metadata (offsets, sizes, scales, total) on the host
         if (e2 != cudaSuccess) return status_of(e2);
         const uint64_t total = *t.h_total[b];
+        if (total == ~0ull) return SPECKV_ERR_DRIVER;            // the packed emission's look-back gave up (kv_codec_fast.cu, pack_place)
         const size_t off = t.alloc_pool(total);
         if (off == SIZE_MAX) return SPECKV_ERR_NOMEM;
         e2 = cudaMemcpyAsync(t.pool + off, t.d_packed[b], total, cudaMemcpyDeviceToHost, t.copy_st[b]);
