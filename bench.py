@@ -722,6 +722,7 @@ def aux_ratios(env, n_groups=4096, reps=8):
         "normal_bf16": (base.to(torch.bfloat16), 2),
         "zeros_fp16": (torch.zeros_like(base), 2),
         "runs300_fp16": (base[: (n_groups * G + 299) // 300].repeat_interleave(300)[: n_groups * G].contiguous(), 2),
+        "zero_tail60_fp16": (torch.where((torch.arange(G, device=dev) < int(G * 0.4)).repeat(n_groups), base, torch.zeros_like(base)), 2),
         "smooth_fp16": ((torch.cumsum(base.float().view(n_groups, G) * 0.01, 1)).to(torch.float16).view(-1), 2),
         "normal_fp16_int8": (base, 1),
         "normal_fp16_fp16": (base, 0),

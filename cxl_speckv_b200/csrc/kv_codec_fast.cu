@@ -542,7 +542,16 @@ __device__ __forceinline__ int long_emit(const uint8_t* reg, uint32_t sbase, int
         const bool forced = pf < c + lead_len;
         const int nn = __popc(m), n = nn + (forced ? 1 : 0);
         last_emitted = m ? c + 31 - __clz((int)m) : (forced ? pf : prev);
-        if (!__any_sync(kFull, n != 0)) continue;
+        if (__ballot_sync(kFull, m != 0u) == 0u) {
+            // no natural head in the whole iteration (inside a long run): only the cap's forced heads, at most two lanes
+            const unsigned fb = __ballot_sync(kFull, forced);
+            if (fb == 0u) continue;
+            const uint32_t fj0 = (uint32_t)(pf - c);
+            sts16_if(sbase + 2u * (uint32_t)(pidx + __popc(fb & ((1u << lane) - 1u))),
+                     ((((fj0 & 4u) ? st.y : st.x) >> (8u * (fj0 & 3u))) & 0xffu) | 0xff00u, forced);
+            pidx += __popc(fb);
+            continue;
+        }
         const int inc = (int)warp_scan_inclusive((uint32_t)n);
         const int idx = pidx + inc - n;
         // the forced pair closes 255 positions of the run whose delta is delta[pf - 1] (byte pf - c of the shifted deltas)
@@ -729,6 +738,7 @@ compress_fast_kernel(const T* __restrict__ in, uint32_t n_groups, uint8_t* __res
         // non-negative floats order like their bit patterns: one integer warp reduction
         m = __uint_as_float(__reduce_max_sync(kFull, __float_as_uint(pack_max_to_float(pm))));
     }
+    const bool zero_region = active && __float_as_uint(m) == 0u;   // only +-0 and NaN in this region
     if (C > 1) cluster_wait();   // all CTAs of the cluster are running: their shared memory may be written
     group_publish<R>(sm, sm.xa, 0, warp, lane, ridx, __float_as_uint(m));   // non-negative floats order like their bits
     group_sync<R>(sm, 0);
@@ -774,6 +784,16 @@ compress_fast_kernel(const T* __restrict__ in, uint32_t n_groups, uint8_t* __res
         asm volatile("" : "+r"(half_k));   // keep it in a register: LOP3 takes only one immediate
 #pragma unroll
         for (int k = 0; k < kIters; ++k) {
+            if (k == 1 && zero_region) {
+                // A region of zeros (and NaNs: code 0 as well) inside a non-zero group -- the unused tail of a
+                // partially filled block.  Its codes are all 0, so behind the first chunks (iteration 0 settles the
+                // hand-over from the previous region) every delta, shifted delta and boundary flag is 0: the slots
+                // are written without quantising anything.  The carries keep iteration 0's values (0 as well).
+#pragma unroll
+                for (int kk = 1; kk < kIters; ++kk) *reinterpret_cast<uint4*>(reg + kk * 512 + lane * 16) = make_uint4(0u, 0u, 0u, 0u);
+                longr = true;   // head-less chunks
+                break;
+            }
             uint8_t* slot = reg + k * 512 + lane * 16;
             const uint4 raw = lds128(slot);
             float x[8];
@@ -821,7 +841,7 @@ compress_fast_kernel(const T* __restrict__ in, uint32_t n_groups, uint8_t* __res
     const bool any_cplx = cplx;
     const bool any_long = (h_total >> 20) != 0;
     h_before &= 0xfffffu;
-    size_t out_off = (size_t)g * slot_bytes;
+    size_t out_off = 0;   // packed emission only; the slot form derives its address where it is used (no live range across the exchange)
     if constexpr (PACKED) {
         // bytes of this group: 2 per run head (the head at position 0 emits nothing, the open run at the end one pair),
         // the closed form of a zero group, a whole slot for a group the generic kernel will encode
@@ -840,7 +860,7 @@ compress_fast_kernel(const T* __restrict__ in, uint32_t n_groups, uint8_t* __res
     if (zero_group) {
         if (ridx == 0) {
             constexpr uint32_t full = G / 255u, rem = G % 255u, npairs = full + (rem ? 1u : 0u);
-            uint16_t* go = reinterpret_cast<uint16_t*>(payload + out_off);
+            uint16_t* go = reinterpret_cast<uint16_t*>(payload + (PACKED ? out_off : (size_t)g * slot_bytes));
             for (uint32_t i = lane; i < npairs; i += 32u) go[i] = i < full ? (uint16_t)0xff00u : (uint16_t)(rem << 8);
             if (lane == 0) {
                 scales[g] = s;   // 1.0f
@@ -850,7 +870,7 @@ compress_fast_kernel(const T* __restrict__ in, uint32_t n_groups, uint8_t* __res
         return;
     }
 
-    uint8_t* gout = payload + out_off;
+    uint8_t* gout = payload + (PACKED ? out_off : (size_t)g * slot_bytes);
     if (any_long) {   // groups with long runs: everything else happens in long_path (not inlined)
         long_path<R>(sm, reg, reg_s, warp, lane, ridx, longr, carry_d1, s, gout, scales + g, comp_bytes + g);
         return;

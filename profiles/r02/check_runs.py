@@ -18,6 +18,7 @@ def t(fn, n=10):
 for name, mk in (("runs300", lambda n: torch.randn((n * G + 299) // 300, device=dev).half().repeat_interleave(300)[: n * G].contiguous()),
                  ("smooth", lambda n: torch.cumsum(torch.randn(n, G, device=dev) * 0.01, 1).half().view(-1)),
                  ("mixed", lambda n: torch.where(torch.rand(n * G, device=dev) < 0.5, torch.randn(n * G, device=dev), torch.zeros(n * G, device=dev)).half()),
+                 ("tail60", lambda n: torch.where((torch.arange(G, device=dev) < int(G * 0.4)).repeat(n), torch.randn(n * G, device=dev), torch.zeros(n * G, device=dev)).half()),
                  ("one700", lambda n: torch.randn(n * G, device=dev).half().index_fill_(0, torch.arange(G // 2, G // 2 + 700, device=dev), 0.5))):
     for n in (4, 512):
         x = mk(n)
