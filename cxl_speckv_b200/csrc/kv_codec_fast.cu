@@ -970,6 +970,47 @@ compress_fast_kernel(const T* __restrict__ in, uint32_t n_groups, uint8_t* __res
 // ===================================================================================
 // decompress
 // ===================================================================================
+// Rare-path helpers of phase A, out of line (the kernel keeps its registers): the index of the first pair of the
+// region's zero-valued tail (0 = every value is zero; pairs past the payload were blanked before), and the element
+// count of that tail while its pairs are blanked in the tile (count 0 emits nothing in the expansion).
+__device__ __noinline__ uint32_t zero_tail_start(const uint8_t* reg, int lane) {
+    int last_nz = -1;
+#pragma unroll
+    for (int k = 0; k < kIters; ++k) {
+        const uint4 w = lds128(reg + k * 512 + lane * 16);
+        const uint32_t va = __byte_perm(w.x, w.y, 0x6420), vb = __byte_perm(w.z, w.w, 0x6420);
+        const uint32_t za = (((va & 0x7f7f7f7fu) + 0x7f7f7f7fu) | va) & 0x80808080u;
+        const uint32_t zb = (((vb & 0x7f7f7f7fu) + 0x7f7f7f7fu) | vb) & 0x80808080u;
+        const int pbase = k * 256 + lane * 8;
+        if (zb) last_nz = pbase + 4 + ((31 - __clz((int)zb)) >> 3);
+        else if (za) last_nz = pbase + ((31 - __clz((int)za)) >> 3);
+    }
+    return __reduce_max_sync(kFull, (unsigned)(last_nz + 1));
+}
+__device__ __noinline__ uint32_t zero_tail_blank(uint8_t* reg, int lane, uint32_t np, uint32_t t_first) {
+    uint32_t tsum = 0;
+    for (int k = 0; k < kIters; ++k) {
+        const int pbase = k * 256 + lane * 8;
+        if (pbase + 8 > (int)t_first && pbase < (int)np) {
+            uint32_t* slot = reinterpret_cast<uint32_t*>(reg + k * 512 + lane * 16);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                uint32_t w = slot[i];
+                if (pbase + 2 * i >= (int)t_first) {
+                    tsum += (w >> 8) & 0xffu;
+                    w &= 0xffff0000u;
+                }
+                if (pbase + 2 * i + 1 >= (int)t_first) {
+                    tsum += w >> 24;
+                    w &= 0x0000ffffu;
+                }
+                slot[i] = w;
+            }
+        }
+    }
+    return __reduce_add_sync(kFull, tsum);
+}
+
 template <typename T, int R>
 __global__ void __launch_bounds__(kThreadsF, kCtasPerSm)
 decompress_fast_kernel(const uint8_t* __restrict__ payload, size_t slot_bytes, const float* __restrict__ scales,
@@ -1177,6 +1218,7 @@ decompress_fast_kernel(const uint8_t* __restrict__ payload, size_t slot_bytes, c
     uint32_t csum = 0, ssum = 0, nnz = 0;
     bool fill = false;   // region decoded as a constant fill (all pair values zero) instead of through the staging area
     bool runs = false;   // region expands beyond what in-place staging holds: the group goes to the run-expansion path
+    uint32_t tail_elems = 0, np_front = 0;   // split region: np_front pairs expanded in place, then tail_elems elements of fill
     if (np > 0) {
         mbar_wait(mb, 0);
 #pragma unroll
@@ -1215,14 +1257,21 @@ decompress_fast_kernel(const uint8_t* __restrict__ payload, size_t slot_bytes, c
         // expands further is still decoded here when all its pair values are zero (zero blocks, long constant
         // stretches): every element then repeats the code the region starts with, and nothing is staged.
         if (csum - nnz > (uint32_t)(kPadBytes / 2 - 8)) {
-            uint32_t vor = 0;
-#pragma unroll
-            for (int k = 0; k < kIters; ++k) {
-                const uint4 w = lds128(reg + k * 512 + lane * 16);
-                vor |= (w.x | w.y | w.z | w.w) & 0x00ff00ffu;
+            // where the region's last pair with a non-zero value sits: none -> constant fill; otherwise the pairs behind
+            // it (value 0: the code stays) are the zero tail of a partially filled block or the end of a long constant
+            // stretch -- if the pairs in front of them fit the staging area, they are expanded in place and the tail
+            // is written as a fill behind them (split), and the group stays off the run-expansion path
+            const uint32_t t_first = zero_tail_start(reg, lane);   // first pair of the zero-valued tail
+            fill = t_first == 0u;
+            if (!fill) {
+                const uint32_t tsum = zero_tail_blank(reg, lane, np, t_first);
+                if ((csum - tsum) - t_first <= (uint32_t)(kPadBytes / 2 - 8) && nnz == np) {
+                    tail_elems = tsum;
+                    np_front = t_first;
+                } else {
+                    runs = true;
+                }
             }
-            fill = __reduce_or_sync(kFull, vor) == 0u;
-            if (!fill) runs = true;
         }
         // a pair with count 0 (never written by the encoder) emits nothing: such payloads keep to the generic kernel,
         // whose tables allow several pairs at one output position
@@ -1267,26 +1316,31 @@ decompress_fast_kernel(const uint8_t* __restrict__ payload, size_t slot_bytes, c
     // ---- C. expand in place: element e of run j carries code q_before + ... + v_j * (e - start_j + 1) ----
     uint8_t* gout = reinterpret_cast<uint8_t*>(out + (size_t)(elem_index ? elem_index[g] : g) * G);   // paged scatter
     const uint32_t e0 = e_before;
-    if (fill) {
-        // constant fill: elements [e0, e0 + csum) all carry code q_before (zero blocks, long runs of one value)
-        const uint32_t e1 = e0 + csum;
-        const uint32_t hb = out_bits<T>(dequantize(q_before & 0xffu, s));
+    // constant fill: elements [ea, ea + n) all carry `code` (zero blocks, long runs of one value, zero tails)
+    auto fill_const = [&](uint32_t ea, uint32_t n, uint32_t code) {
+        const uint32_t e1 = ea + n;
+        const uint32_t hb = out_bits<T>(dequantize(code & 0xffu, s));
         const uint32_t w2 = hb | (hb << 16);
-        const uint32_t a0 = min((e0 + 7u) & ~7u, e1), a1 = max(e1 & ~7u, a0);
+        const uint32_t a0 = min((ea + 7u) & ~7u, e1), a1 = max(e1 & ~7u, a0);
         uint16_t* go16 = reinterpret_cast<uint16_t*>(gout);
-        if (e0 + lane < a0) go16[e0 + lane] = (uint16_t)hb;
+        if (ea + lane < a0) go16[ea + lane] = (uint16_t)hb;
         if (a1 + lane < e1) go16[a1 + lane] = (uint16_t)hb;
         const uint4 v4 = make_uint4(w2, w2, w2, w2);
         for (uint32_t e = a0 + 8u * lane; e < a1; e += 256u) *reinterpret_cast<uint4*>(go16 + e) = v4;
+    };
+    if (fill) {
+        fill_const(e0, csum, q_before);
         return;
     }
     ecur = e0;
     qcur = q_before & 0xffu;
     sbase = reg_s - (uint32_t)kPadBytes - 2u * (e0 & ~7u);
+    if (tail_elems) np = np_front;   // split region: the pairs of the zero-valued tail were blanked in phase A
     if (kTryShort && short_deq) expand(std::integral_constant<bool, kTryShort>{}, std::false_type{});
     else expand(std::false_type{}, std::false_type{});
     __syncwarp();
     flush_region(sbase, gout, (int)e0, (int)ecur, lane);   // (an early partial flush, as in compress, measured slower here)
+    if (tail_elems) fill_const(ecur, tail_elems, qcur);     // the tail repeats the code the expansion ended on
 }
 
 // ===================================================================================

@@ -673,6 +673,43 @@ def test_long_runs_then_dense_heads(G, tdt):
     assert np.array_equal(out_bits(y).reshape(-1), want.view(np.uint16).reshape(-1))
 
 
+@pytest.mark.parametrize("G", [8192, 32768, 131072])
+@pytest.mark.parametrize("tdt", [F16, BF16])
+def test_partially_filled_blocks(G, tdt):
+    """KV blocks filled up to an arbitrary token and zero (or constant, or NaN-sprinkled zero) behind it: compress skips
+    the quantiser for all-zero regions of a non-zero group, decompress expands the dense front of the boundary region in
+    place and writes the tail as a fill (the group stays off the run-expansion path).  Sizes, scales, payload bytes and
+    decoded bits against the oracle; fill levels around region and iteration edges."""
+    rng = np.random.default_rng(7 * G + (1 if tdt == BF16 else 0))
+    levels = [1, 9, 255, 256, 2047, 2048, 2049, 2048 + 1016, 5000, G // 2 - 1, G // 2, G - 2048 - 3, G - 300, G - 9, G - 1]
+    n_groups = len(levels) * 3
+    x = rng.standard_normal(n_groups * G).astype(np.float32)
+    for i in range(n_groups):
+        lvl = levels[i % len(levels)]
+        tail = x[i * G + lvl:(i + 1) * G]
+        kind = i // len(levels)
+        tail[:] = 0.0 if kind != 1 else 0.625
+        if kind == 2 and tail.size > 40:
+            tail[rng.integers(0, tail.size, 3)] = np.nan          # NaN quantises to code 0 like the zeros around it
+    raw = x.astype(np.float16) if tdt == F16 else bf16_from_f32(x)
+    xd = torch.from_numpy(raw).to(DEV) if tdt == F16 else torch.from_numpy(raw.astype(np.int16)).to(DEV).view(torch.bfloat16)
+    c = codec.compress(xd, G)
+    payload, scales, comp = Port.compress_batch(raw, G, dtype=tdt, threads=8)
+    assert np.array_equal(f32_bits(c.scales.cpu().numpy()), f32_bits(scales))
+    assert np.array_equal(c.comp_bytes.cpu().numpy().view(np.uint32), comp)
+    gp = c.payload.cpu().numpy()
+    for g in range(n_groups):
+        assert np.array_equal(gp[g, :comp[g]], payload[g, :comp[g]]), (g, levels[g % len(levels)], comp[g])
+    oel = torch.zeros(n_groups, dtype=torch.int32, device=DEV)
+    y = codec.decompress(c, out_elems=oel)
+    want, want_n = Port.decompress_batch(payload, scales, comp, G, tdt, threads=8)
+    assert np.array_equal(oel.cpu().numpy().view(np.uint32), want_n)
+    got = out_bits(y).reshape(n_groups, G)
+    wantb = want.view(np.uint16).reshape(n_groups, G)
+    bad = np.argwhere(got != wantb)
+    assert bad.size == 0, (bad[:3], levels[int(bad[0][0]) % len(levels)])
+
+
 def test_randomised_differential_run():
     """tests/fuzz_codec.py for a few seconds: random geometries, dtypes and value structures against the oracle."""
     from tests import fuzz_codec
