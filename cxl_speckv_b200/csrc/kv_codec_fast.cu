@@ -581,22 +581,139 @@ __device__ __forceinline__ int long_emit(const uint8_t* reg, uint32_t sbase, int
     return pidx;
 }
 
+// ===================================================================================
+// compress: phase 2b, the common emission (every run shorter than 9: no chunk without a head)
+// ===================================================================================
+template <int R>
+__device__ __forceinline__ void emit_common(uint8_t* reg, uint32_t reg_s, int lane, unsigned lt_mask, int ridx, uint32_t h_before,
+                                            uint32_t halo_tail, uint32_t carry_d1, float s, uint8_t* gout, float* scale_out,
+                                            uint32_t* comp_out) {
+    // ---- 2b. emit: a head at position p closes the previous run -> pair (delta[p-1], p - previous head).
+    //          Pairs are staged IN PLACE (behind the slots still to be read) at the alignment they
+    //          will have in global memory, then the region goes out with one bulk-TMA store.
+    // Region 0 starts at pair index -1: the head at position 0 closes nothing, so its "pair" is
+    // staged in the pad in front of the tile and never flushed.
+    int pidx = (int)h_before - 1;
+    const int p0 = max(pidx, 0);                         // first real pair index of this region
+    const uint32_t sbase = reg_s - 16u - 2u * (uint32_t)(p0 & ~7);   // pair i is staged at sbase + 2*i
+    // tail = distance from the end of a lane chunk back to its last head; the next chunk's first
+    // pair closes a run of that length (+ its own offset)
+    uint32_t carry_tail = halo_tail;
+    const int src_lane = (lane + 31) & 31;
+#ifndef SPECKV_UNROLL_2B
+#define SPECKV_UNROLL_2B 8
+#endif
+    int done = 0;   // units below this index already left with an early bulk store
+    constexpr int kUnroll2b = SPECKV_UNROLL_2B;   // full unrolling measured 2.4 % faster than 2; fetching slot k + 1 early: slower
+#pragma unroll kUnroll2b
+    for (int k = 0; k < kIters; ++k) {
+        const uint4 st = lds128(reg + k * 512 + lane * 16);
+        __syncwarp();   // every lane has read its slot before any pair of this iteration lands on it
+        const uint32_t dsh0 = st.x, dsh1 = st.y;
+        const uint32_t nz0 = st.z, nz1 = st.w;
+        const uint32_t hw0 = ~nz0 & 0x80808080u, hw1 = ~nz1 & 0x80808080u;   // "holes": positions that continue a run
+        const int nhole = __popc(hw0) + __popc(hw1);
+        if (!__any_sync(kFull, nhole > 1)) {
+            // ---- common case: every lane emits 8 pairs, or 7 (one position continues a run) ----
+            // with at most one hole the run open at the end of the chunk is 1 or 2 positions long
+            const uint32_t rt = __shfl_sync(kFull, 1u + (hw1 >> 31), src_lane);
+            const uint32_t lf = lane == 0 ? carry_tail : rt;   // distance back to the previous head
+            carry_tail = rt;
+            const unsigned bal = __ballot_sync(kFull, nhole != 0);
+            const int idx = pidx + 8 * lane - __popc(bal & lt_mask);
+            // Branch-free hole deletion.  u = 1 << (8 * hole byte) in its word, 0 without a hole.
+            // counts: lf for the first unit, 1 elsewhere; once the hole unit is gone the unit that
+            // takes its index has absorbed the hole's position: +1 at that index (lf + 1 at index 0).
+            const uint32_t u0 = hw0 >> 7, u1 = hw1 >> 7;
+            const uint32_t c0 = (0x01010100u | lf) + u0, c1 = 0x01010101u + u1;
+            // values: bytes below the hole stay, bytes from the hole on move down by one
+            const uint32_t keep0 = u0 - 1u;                    // all ones when the hole is not in word 0
+            const uint32_t keep1 = u0 ? 0u : u1 - 1u;
+            const uint32_t sh0 = __funnelshift_r(dsh0, dsh1, 8), sh1 = dsh1 >> 8;
+            const uint32_t v0 = (dsh0 & keep0) | (sh0 & ~keep0), v1 = (dsh1 & keep1) | (sh1 & ~keep1);
+            const uint32_t w0 = __byte_perm(v0, c0, 0x5140), w1 = __byte_perm(v0, c0, 0x7362);
+            const uint32_t w2 = __byte_perm(v1, c1, 0x5140), w3 = __byte_perm(v1, c1, 0x7362);
+            store_units8(sbase + 2u * (uint32_t)idx, w0, w1, w2, w3, 8 - nhole);
+            pidx += 256 - __popc(bal);
+        } else {
+            // ---- some lane has two or more continuing positions: scan + one store per head ----
+            const uint32_t tail = nz1 ? ((uint32_t)__clz((int)nz1) >> 3) + 1u : ((uint32_t)__clz((int)nz0) >> 3) + 5u;
+            const uint32_t rt = __shfl_sync(kFull, tail, src_lane);
+            const uint32_t lf = lane == 0 ? carry_tail : rt;
+            carry_tail = rt;
+            const int n = 8 - nhole;
+            const int inc = (int)warp_scan_inclusive((uint32_t)n);
+            int idx = pidx + inc - n;
+            uint32_t run = lf;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const uint32_t v = (j < 4 ? dsh0 >> (8 * j) : dsh1 >> (8 * (j - 4))) & 0xffu;
+                const uint32_t isz = (j < 4 ? nz0 >> (8 * j) : nz1 >> (8 * (j - 4))) & 0x80u;
+                if (isz) {
+                    sts16(sbase + 2u * (uint32_t)idx, v | (run << 8));
+                    ++idx;
+                    run = 1;
+                } else {
+                    ++run;
+                }
+            }
+            pidx += __shfl_sync(kFull, inc, 31);
+        }
+        if (k == kEarlyFlushIter) {
+            // the pairs staged so far are final: the whole vectors among them leave now, overlapping the rest
+            done = max(pidx & ~7, (p0 + 7) & ~7);
+            flush_bulk(sbase, gout, (p0 + 7) & ~7, done, lane);
+        }
+    }
+    if (ridx == R - 1) {
+        // the run still open at the end of the group (cache_engine.cpp:235-236)
+        if (lane == 0) {
+            const uint32_t cnt = carry_tail;
+            sts16(sbase + 2u * (uint32_t)pidx, (carry_d1 >> 24) | (cnt << 8));
+            *scale_out = s;
+            *comp_out = 2u * (uint32_t)(pidx + 1);
+        }
+        ++pidx;
+    }
+    __syncwarp();
+    flush_region(sbase, gout, p0, pidx, lane, done);
+}
+
 // Phase 2b of a group with long runs, as ONE routine outside the kernel body (the common path keeps its code and
 // register allocation): a third exchange (first / last natural head per region), offsets from long_reduce, every
 // iteration through the general routine, the final pair, the flush.
 template <int R>
 __device__ SPECKV_LONG_ATTR void long_path(FastSmem& sm, uint8_t* reg, uint32_t reg_s, int warp, int lane, int ridx, bool longr,
-                                       uint32_t carry_d1, float s, uint8_t* gout, float* scale_out, uint32_t* comp_out) {
+                                       uint32_t carry_d1, uint32_t halo_tail, float s, uint8_t* gout, float* scale_out,
+                                       uint32_t* comp_out) {
     constexpr uint32_t G = (uint32_t)R * kRegion;
-    // regions with a head-less chunk ran the first pass in phase 2a (their interior forced heads went into round 2);
-    // the others run it now (no forced head can fall inside them): every slot then carries m | nb for the emission
-    if (!longr) long_first_pass_body(reg, lane, &sm.stash[warp]);
-    __syncwarp();
-    group_publish<R>(sm, sm.xb, 2, warp, lane, ridx, sm.stash[warp]);
+    // regions with a head-less chunk ran the first pass in phase 2a (their interior forced heads went into round 2 and
+    // first | last natural head into the stash); in the others these two sit in the first and the last lane chunk
+    uint32_t stash_w;
+    if (!longr) {
+        uint2 e = make_uint2(0u, 0u);   // lane 0 and lane 31 read the flags they parked themselves
+        if (lane == 0) e = *reinterpret_cast<const uint2*>(reg + 8);
+        else if (lane == 31) e = *reinterpret_cast<const uint2*>(reg + (kIters - 1) * 512 + 31 * 16 + 8);
+        const uint32_t m = head_mask8(e.x, e.y);
+        const int reg_first = __shfl_sync(kFull, __ffs((int)m) - 1, 0);
+        const int reg_last = __shfl_sync(kFull, (kIters - 1) * 256 + 31 * 8 + 31 - __clz((int)m), 31);
+        stash_w = (uint32_t)reg_first | ((uint32_t)(reg_last + 1) << 12);
+    } else {
+        __syncwarp();
+        stash_w = sm.stash[warp];
+    }
+    group_publish<R>(sm, sm.xb, 2, warp, lane, ridx, stash_w);
     group_sync_own<R>(sm, 2, warp);
     uint32_t hb;
     int nb_in;
     long_reduce<R>(sm.xc, sm.xb, warp, lane, ridx, hb, nb_in);
+    if (!longr) {
+        // A region WITHOUT a head-less chunk and with a head among the 8 positions in front of it: no run of 16 or more
+        // touches it, so no forced head falls into it -- the common emission, behind the pairs of the lower regions
+        // (dense regions of a partially filled block, the noise around one constant stretch).
+        emit_common<R>(reg, reg_s, lane, (1u << lane) - 1u, ridx, hb, halo_tail, carry_d1, s, gout, scale_out, comp_out);
+        return;
+    }
     int pl = (int)hb - 1;
     const int pl0 = max(pl, 0);
     const uint32_t sb = reg_s - 16u - 2u * (uint32_t)(pl0 & ~7);
@@ -872,99 +989,11 @@ compress_fast_kernel(const T* __restrict__ in, uint32_t n_groups, uint8_t* __res
 
     uint8_t* gout = payload + (PACKED ? out_off : (size_t)g * slot_bytes);
     if (any_long) {   // groups with long runs: everything else happens in long_path (not inlined)
-        long_path<R>(sm, reg, reg_s, warp, lane, ridx, longr, carry_d1, s, gout, scales + g, comp_bytes + g);
+        long_path<R>(sm, reg, reg_s, warp, lane, ridx, longr, carry_d1, halo_tail, s, gout, scales + g, comp_bytes + g);
         return;
     }
 
-    // ---- 2b. emit: a head at position p closes the previous run -> pair (delta[p-1], p - previous head).
-    //          Pairs are staged IN PLACE (behind the slots still to be read) at the alignment they
-    //          will have in global memory, then the region goes out with one bulk-TMA store.
-    // Region 0 starts at pair index -1: the head at position 0 closes nothing, so its "pair" is
-    // staged in the pad in front of the tile and never flushed.
-    int pidx = (int)h_before - 1;
-    const int p0 = max(pidx, 0);                         // first real pair index of this region
-    const uint32_t sbase = reg_s - 16u - 2u * (uint32_t)(p0 & ~7);   // pair i is staged at sbase + 2*i
-    // tail = distance from the end of a lane chunk back to its last head; the next chunk's first
-    // pair closes a run of that length (+ its own offset)
-    uint32_t carry_tail = halo_tail;
-    const int src_lane = (lane + 31) & 31;
-#ifndef SPECKV_UNROLL_2B
-#define SPECKV_UNROLL_2B 8
-#endif
-    int done = 0;   // units below this index already left with an early bulk store
-    constexpr int kUnroll2b = SPECKV_UNROLL_2B;   // full unrolling measured 2.4 % faster than 2; fetching slot k + 1 early: slower
-#pragma unroll kUnroll2b
-    for (int k = 0; k < kIters; ++k) {
-        const uint4 st = lds128(reg + k * 512 + lane * 16);
-        __syncwarp();   // every lane has read its slot before any pair of this iteration lands on it
-        const uint32_t dsh0 = st.x, dsh1 = st.y;
-        const uint32_t nz0 = st.z, nz1 = st.w;
-        const uint32_t hw0 = ~nz0 & 0x80808080u, hw1 = ~nz1 & 0x80808080u;   // "holes": positions that continue a run
-        const int nhole = __popc(hw0) + __popc(hw1);
-        if (!__any_sync(kFull, nhole > 1)) {
-            // ---- common case: every lane emits 8 pairs, or 7 (one position continues a run) ----
-            // with at most one hole the run open at the end of the chunk is 1 or 2 positions long
-            const uint32_t rt = __shfl_sync(kFull, 1u + (hw1 >> 31), src_lane);
-            const uint32_t lf = lane == 0 ? carry_tail : rt;   // distance back to the previous head
-            carry_tail = rt;
-            const unsigned bal = __ballot_sync(kFull, nhole != 0);
-            const int idx = pidx + 8 * lane - __popc(bal & lt_mask);
-            // Branch-free hole deletion.  u = 1 << (8 * hole byte) in its word, 0 without a hole.
-            // counts: lf for the first unit, 1 elsewhere; once the hole unit is gone the unit that
-            // takes its index has absorbed the hole's position: +1 at that index (lf + 1 at index 0).
-            const uint32_t u0 = hw0 >> 7, u1 = hw1 >> 7;
-            const uint32_t c0 = (0x01010100u | lf) + u0, c1 = 0x01010101u + u1;
-            // values: bytes below the hole stay, bytes from the hole on move down by one
-            const uint32_t keep0 = u0 - 1u;                    // all ones when the hole is not in word 0
-            const uint32_t keep1 = u0 ? 0u : u1 - 1u;
-            const uint32_t sh0 = __funnelshift_r(dsh0, dsh1, 8), sh1 = dsh1 >> 8;
-            const uint32_t v0 = (dsh0 & keep0) | (sh0 & ~keep0), v1 = (dsh1 & keep1) | (sh1 & ~keep1);
-            const uint32_t w0 = __byte_perm(v0, c0, 0x5140), w1 = __byte_perm(v0, c0, 0x7362);
-            const uint32_t w2 = __byte_perm(v1, c1, 0x5140), w3 = __byte_perm(v1, c1, 0x7362);
-            store_units8(sbase + 2u * (uint32_t)idx, w0, w1, w2, w3, 8 - nhole);
-            pidx += 256 - __popc(bal);
-        } else {
-            // ---- some lane has two or more continuing positions: scan + one store per head ----
-            const uint32_t tail = nz1 ? ((uint32_t)__clz((int)nz1) >> 3) + 1u : ((uint32_t)__clz((int)nz0) >> 3) + 5u;
-            const uint32_t rt = __shfl_sync(kFull, tail, src_lane);
-            const uint32_t lf = lane == 0 ? carry_tail : rt;
-            carry_tail = rt;
-            const int n = 8 - nhole;
-            const int inc = (int)warp_scan_inclusive((uint32_t)n);
-            int idx = pidx + inc - n;
-            uint32_t run = lf;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const uint32_t v = (j < 4 ? dsh0 >> (8 * j) : dsh1 >> (8 * (j - 4))) & 0xffu;
-                const uint32_t isz = (j < 4 ? nz0 >> (8 * j) : nz1 >> (8 * (j - 4))) & 0x80u;
-                if (isz) {
-                    sts16(sbase + 2u * (uint32_t)idx, v | (run << 8));
-                    ++idx;
-                    run = 1;
-                } else {
-                    ++run;
-                }
-            }
-            pidx += __shfl_sync(kFull, inc, 31);
-        }
-        if (k == kEarlyFlushIter) {
-            // the pairs staged so far are final: the whole vectors among them leave now, overlapping the rest
-            done = max(pidx & ~7, (p0 + 7) & ~7);
-            flush_bulk(sbase, gout, (p0 + 7) & ~7, done, lane);
-        }
-    }
-    if (ridx == R - 1) {
-        // the run still open at the end of the group (cache_engine.cpp:235-236)
-        if (lane == 0) {
-            const uint32_t cnt = carry_tail;
-            sts16(sbase + 2u * (uint32_t)pidx, (carry_d1 >> 24) | (cnt << 8));
-            scales[g] = s;
-            comp_bytes[g] = 2u * (uint32_t)(pidx + 1);
-        }
-        ++pidx;
-    }
-    __syncwarp();
-    flush_region(sbase, gout, p0, pidx, lane, done);
+    emit_common<R>(reg, reg_s, lane, lt_mask, ridx, h_before, halo_tail, carry_d1, s, gout, scales + g, comp_bytes + g);
 }
 
 // ===================================================================================
