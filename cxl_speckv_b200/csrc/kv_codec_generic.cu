@@ -551,14 +551,16 @@ decompress_rle_generic_kernel(const uint8_t* __restrict__ payload, size_t slot_b
                 decode_runs_region<T>(rs, wid, lane, gp, npairs, scales[gi], runs_prefix + (size_t)g * (runs_R + 1), runs_R, o,
                                       out + (size_t)(elem_index ? elem_index[g] : g) * G);
             }
-        }
-        // the last CTA to get here clears the list for the next call (every CTA has read the count by then)
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            __threadfence();
-            if (atomicAdd(runs_counters + 1, 1u) == gridDim.x - 1) {
-                runs_counters[0] = 0u;
-                runs_counters[1] = 0u;
+            // the last CTA to get here clears the list for the next call (every CTA has read the count by then).  Only
+            // when there was a list: with n_runs == 0 both counters are zero already, and one atomic per CTA on the same
+            // word made the (usual) empty second pass twice as long as it needs to be.
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                __threadfence();
+                if (atomicAdd(runs_counters + 1, 1u) == gridDim.x - 1) {
+                    runs_counters[0] = 0u;
+                    runs_counters[1] = 0u;
+                }
             }
         }
     }
