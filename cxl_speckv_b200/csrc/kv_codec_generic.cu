@@ -779,6 +779,10 @@ passthrough_out_kernel(const uint8_t* __restrict__ payload, size_t slot_bytes,
     }
 }
 
+#ifndef SPECKV_SECOND_PASS_PER_SM
+#define SPECKV_SECOND_PASS_PER_SM 3
+#endif
+constexpr int kSecondPassPerSm = SPECKV_SECOND_PASS_PER_SM;
 inline int grid_for(uint32_t n_groups, int sm_count, int per_sm) {
     const long long cap = (long long)sm_count * per_sm;
     return (int)((long long)n_groups < cap ? (n_groups ? n_groups : 1) : cap);
@@ -790,7 +794,9 @@ template <typename T>
 static cudaError_t launch_compress_t(const CodecArgs& a, cudaStream_t st, const uint32_t* only_flagged) {
     const T* in = static_cast<const T*>(a.in);
     uint8_t* pay = static_cast<uint8_t*>(a.payload);
-    const int grid = grid_for(a.n_groups, a.sm_count, 8);
+    // as the second pass behind a tuned kernel almost nothing is flagged: a smaller grid (its launch and drain are
+    // what an empty pass costs) still spreads the few flagged groups over every SM
+    const int grid = grid_for(a.n_groups, a.sm_count, only_flagged ? kSecondPassPerSm : 8);
     if (scheme_is_rle(a.scheme)) {
         compress_rle_generic_kernel<T><<<grid, kThreads, 0, st>>>(in, a.group_elems, a.n_groups, pay, a.slot_bytes,
                                                                   a.scales, a.comp_bytes, only_flagged, a.elem_index,
@@ -808,7 +814,7 @@ template <typename T>
 static cudaError_t launch_decompress_t(const CodecArgs& a, cudaStream_t st, const uint32_t* only_flagged, const DecodeScratch* runs) {
     T* out = static_cast<T*>(a.out);
     const uint8_t* pay = static_cast<const uint8_t*>(a.payload);
-    int grid = grid_for(a.n_groups, a.sm_count, 8);
+    int grid = grid_for(a.n_groups, a.sm_count, only_flagged ? kSecondPassPerSm : 8);
     if (runs) {   // a few flagged groups still spread over the device: one warp per output region, up to 2 CTAs per SM
         const long long want = ((long long)a.n_groups * runs->regions + kWarps - 1) / kWarps;
         const long long cap = (long long)a.sm_count * 2;
