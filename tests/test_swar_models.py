@@ -136,3 +136,62 @@ def test_count_classification_mask():
         ta = (ca - 0x01010101) & M32
         small = (ta & 0xFEFEFEFE) == 0
         assert small == all(x in (1, 2) for x in c), c
+
+
+# ---- head-stationary emission of the long-run path (kv_codec_fast.cu, long_emit / HeadSelTable) ----------------------
+def head_sel_table():
+    """HeadSelTable: nibble i of entry m = position of the i-th set bit of m (0 beyond popc(m))."""
+    tab = []
+    for m in range(256):
+        sel, n = 0, 0
+        for j in range(8):
+            if (m >> j) & 1:
+                sel |= j << (4 * n)
+                n += 1
+        tab.append(sel)
+    return tab
+
+
+def long_emit_units(m, dsh, c_minus_prev):
+    """The 16-bit units long_emit stages for a chunk with head mask m, shifted deltas dsh[0..7] and c - prev
+    (distance from the chunk's first position back to the previous emitted head; <= 0 after a forced head)."""
+    sel = head_sel_table()[m]
+    stx, sty = pack(dsh[:4]), pack(dsh[4:])
+    v0, v1 = byte_perm(stx, sty, sel & 0xFFFF), byte_perm(stx, sty, sel >> 16)
+    p0, p1 = byte_perm(0x03020100, 0x07060504, sel & 0xFFFF), byte_perm(0x03020100, 0x07060504, sel >> 16)
+    c0 = (p0 - ((p0 << 8) & M32) + (c_minus_prev & M32)) & M32
+    c1 = (p1 - funnelshift_l(p0, p1, 8)) & M32
+    w = [byte_perm(v0, c0, 0x5140), byte_perm(v0, c0, 0x7362), byte_perm(v1, c1, 0x5140), byte_perm(v1, c1, 0x7362)]
+    units = []
+    for x in w:
+        units += [x & 0xFFFF, x >> 16]
+    return units[:bin(m).count("1")]
+
+
+def test_long_emit_selector_table_and_counts():
+    """Every head mask, with and without a forced head in the leading stretch: values are the shifted deltas at the
+    head positions, counts the distances between heads (the first one reaching back to the previous emitted head)."""
+    rng = random.Random(5)
+    for m in range(1, 256):
+        pos = [j for j in range(8) if (m >> j) & 1]
+        for trial in range(40):
+            dsh = [rng.randrange(256) for _ in range(8)]
+            if pos[0] > 0 and trial % 3 == 0:
+                cmp_ = -rng.randrange(0, pos[0])             # a forced head at chunk position -cmp_ (< first natural head)
+            else:
+                cmp_ = rng.randrange(1, 256 - pos[0])         # (c + first head) - prev <= 255: no forced head in between
+            want = [dsh[p] | (((p + cmp_) if i == 0 else (p - pos[i - 1])) << 8) for i, p in enumerate(pos)]
+            assert long_emit_units(m, dsh, cmp_) == want, (m, cmp_)
+
+
+def test_div255_and_forced_head_closed_forms():
+    """div255 (umulhi by 0x80808081, >> 7) for the ranges the kernel feeds it, and the count of forced heads in a
+    chunk's leading stretch: multiples of 255 in [d, d + lead) = div255(d + lead - 1) - div255(d - 1)."""
+    def div255(x):
+        return ((x * 0x80808081) >> 32) >> 7
+    for x in list(range(0, 70000)) + [2 ** 31 - 1, 2 ** 32 - 1, 255 * 1234567, 255 * 1234567 - 1]:
+        assert div255(x) == x // 255, x
+    for d in range(1, 1200):
+        for lead in range(0, 9):
+            want = sum(1 for t in range(d, d + lead) if t % 255 == 0)
+            assert div255(d + lead - 1) - div255(d - 1) == want, (d, lead)
