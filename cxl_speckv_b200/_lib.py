@@ -157,6 +157,7 @@ def lib() -> C.CDLL:
     L.speckv_ext_submit_dma_batch.argtypes = [vp, vp, C.c_uint32, vp]; L.speckv_ext_submit_dma_batch.restype = C.c_int
     L.speckv_ext_poll_complete.argtypes = []; L.speckv_ext_poll_complete.restype = C.c_uint32
     L.speckv_ext_set_param.argtypes = [C.c_uint32, C.c_uint32]; L.speckv_ext_set_param.restype = C.c_int
+    L.speckv_ext_submit_prefetch.argtypes = [C.c_void_p]; L.speckv_ext_submit_prefetch.restype = C.c_int
     L.speckv_ext_policy_create.argtypes = [C.c_uint64] * 4 + [C.POINTER(vp)]; L.speckv_ext_policy_create.restype = C.c_int
     L.speckv_ext_policy_destroy.argtypes = [vp]; L.speckv_ext_policy_destroy.restype = None
     L.speckv_ext_policy_place.argtypes = [vp, vp, sz, C.c_int, vp]; L.speckv_ext_policy_place.restype = C.c_int

@@ -287,6 +287,14 @@ speckv_status_t speckv_ext_prefetch_feedback(int was_correct, uint32_t* out_dept
     return SPECKV_OK;
 }
 
+// SPECKV_IOCTL_PREFETCH (driver/uapi/speckv_ioctl.h:25-33,47; handle_prefetch speckv_kernel_module.c:116-167):
+// the ioctl client's request record, served by the frozen entry point
+speckv_status_t speckv_ext_submit_prefetch(const speckv_prefetch_req_t* req) {
+    if (!req || !req->tokens_user_ptr || req->history_len == 0) return SPECKV_ERR_INVAL;
+    return speckv_prefetch(req->req_id, req->layer, req->cur_pos, req->depth_k,
+                           reinterpret_cast<const int32_t*>(static_cast<uintptr_t>(req->tokens_user_ptr)), req->history_len);
+}
+
 // SPECKV_IOCTL_SET_PARAM (driver/uapi/speckv_ioctl.h:36-43, handle_set_param
 // speckv_kernel_module.c:169-191): key 1 = prefetch depth, key 2 = compression scheme, anything
 // else is rejected (-EINVAL there, SPECKV_ERR_INVAL here; tests/test_params.c:68-84).

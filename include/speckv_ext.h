@@ -293,6 +293,20 @@ SPECKV_API speckv_status_t speckv_ext_submit_dma_batch(speckv_tier_t* tier, cons
                                                        uint32_t count, void* cuda_stream);
 /* SpeckvDriver::poll_complete (speckv_driver.cpp:65-72): descriptors completed since the last poll. */
 SPECKV_API uint32_t speckv_ext_poll_complete(void);
+/* SPECKV_IOCTL_PREFETCH with the request record of driver/uapi/speckv_ioctl.h:25-33 (the call tests/test_prefetch.c
+ * makes; SpeckvDriver::prefetch, speckv_driver.cpp:49-55): same effect as speckv_prefetch(req_id, layer, cur_pos,
+ * depth_k, tokens, history_len).  A NULL record, a NULL token pointer or history_len == 0 -> SPECKV_ERR_INVAL (the
+ * kernel module answers -EFAULT for pointers it cannot read, speckv_kernel_module.c:116-132). */
+typedef struct {
+    uint32_t req_id;
+    uint16_t layer;
+    uint16_t reserved0;
+    uint32_t cur_pos;
+    uint32_t depth_k;
+    uint32_t history_len;
+    uint64_t tokens_user_ptr;   /* const int32_t[history_len] in the caller's address space */
+} speckv_prefetch_req_t;
+SPECKV_API speckv_status_t speckv_ext_submit_prefetch(const speckv_prefetch_req_t* req);
 /* SPECKV_IOCTL_SET_PARAM: key 1 = prefetch depth, key 2 = compression scheme; any other key is
  * rejected with SPECKV_ERR_INVAL (speckv_kernel_module.c:179-188, tests/test_params.c:68-84). */
 SPECKV_API speckv_status_t speckv_ext_set_param(uint32_t key, uint32_t value);

@@ -208,6 +208,36 @@ def _build_c_program(tmp_path, with_cuda: bool) -> str:
     return exe
 
 
+def test_prefetch_ioctl_record_like_the_reference_test(L):
+    """tests/test_prefetch.c through the record of SPECKV_IOCTL_PREFETCH (driver/uapi/speckv_ioctl.h:25-33): one
+    request, the same for five layers, a batch of ten requests -- all accepted; records the kernel module could not
+    read are rejected.  Host logic: no GPU needed (the requests are logged; no pool is bound)."""
+    import ctypes as C
+
+    class Req(C.Structure):
+        _fields_ = [("req_id", C.c_uint32), ("layer", C.c_uint16), ("reserved0", C.c_uint16), ("cur_pos", C.c_uint32),
+                    ("depth_k", C.c_uint32), ("history_len", C.c_uint32), ("tokens_user_ptr", C.c_uint64)]
+
+    assert C.sizeof(Req) == 32
+    assert L.speckv_init(b"/dev/null") == 0
+    try:
+        tokens = (C.c_int32 * 16)(*range(101, 117))
+        req = Req(1, 0, 0, 100, 4, 16, C.addressof(tokens))
+        assert L.speckv_ext_submit_prefetch(C.byref(req)) == 0
+        for layer in range(5):
+            req.layer, req.cur_pos = layer, 100 + layer
+            assert L.speckv_ext_submit_prefetch(C.byref(req)) == 0
+        tokens2 = (C.c_int32 * 16)(*range(1, 17))
+        for rid in range(1, 11):
+            r = Req(rid, 0, 0, rid * 10, 4, 16, C.addressof(tokens2))
+            assert L.speckv_ext_submit_prefetch(C.byref(r)) == 0
+        assert L.speckv_ext_submit_prefetch(None) == pkg.SPECKV_ERR_INVAL
+        assert L.speckv_ext_submit_prefetch(C.byref(Req(1, 0, 0, 1, 4, 0, C.addressof(tokens)))) == pkg.SPECKV_ERR_INVAL
+        assert L.speckv_ext_submit_prefetch(C.byref(Req(1, 0, 0, 1, 4, 16, 0))) == pkg.SPECKV_ERR_INVAL
+    finally:
+        L.speckv_finalize()
+
+
 def test_plain_c_host_program(tmp_path):
     """include/*.h are valid C99 and a C program reproduces the reference's call scenarios and error
     conventions through the frozen ABI (tests/c/frozen_abi.c; no C++, Python or torch in between)."""
