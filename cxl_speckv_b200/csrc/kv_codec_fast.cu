@@ -386,7 +386,9 @@ __device__ __forceinline__ void flush_region(uint32_t sbase, uint8_t* gout, int 
 // and "interior" forced heads (those after its first natural head) itself; the forced heads in the stretch before the
 // first natural head of a region depend on lower regions and are derived by every region for all lower regions from
 // the exchanged words (long_reduce).  The kernel reaches all of this through two calls that are deliberately NOT
-// inlined (long_first_pass, long_path): inlined, the long-run code costs the common path 5 %.
+// inlined (long_first_pass, long_path): inlined, the long-run code costs the common path 1 - 5 % (round 1: 5 %, the
+// round-2 routines: 1 %).  Regions of such a group that hold no long run themselves take the common emission
+// (emit_common) from inside long_path, with the pair offset the exchange gives them.
 __device__ __forceinline__ uint32_t head_mask8(uint32_t nz0, uint32_t nz1) {   // bit j = position j of the chunk starts a run
     const uint32_t lo = (((nz0 >> 7) & 0x01010101u) * 0x01020408u) >> 24;
     const uint32_t hi = (((nz1 >> 7) & 0x01010101u) * 0x01020408u) >> 24;
