@@ -675,11 +675,13 @@ def test_long_runs_then_dense_heads(G, tdt):
 
 @pytest.mark.parametrize("G", [8192, 32768, 131072])
 @pytest.mark.parametrize("tdt", [F16, BF16])
-def test_partially_filled_blocks(G, tdt):
+@pytest.mark.parametrize("scheme", [2, 3])
+def test_partially_filled_blocks(G, tdt, scheme):
     """KV blocks filled up to an arbitrary token and zero (or constant, or NaN-sprinkled zero) behind it: compress skips
     the quantiser for all-zero regions of a non-zero group, decompress expands the dense front of the boundary region in
     place and writes the tail as a fill (the group stays off the run-expansion path).  Sizes, scales, payload bytes and
-    decoded bits against the oracle; fill levels around region and iteration edges."""
+    decoded bits against the oracle; fill levels around region and iteration edges; the reference's scheme and the
+    clamped extension (NaN codes as 0 in both)."""
     rng = np.random.default_rng(7 * G + (1 if tdt == BF16 else 0))
     levels = [1, 9, 255, 256, 2047, 2048, 2049, 2048 + 1016, 5000, G // 2 - 1, G // 2, G - 2048 - 3, G - 300, G - 9, G - 1]
     n_groups = len(levels) * 3
@@ -693,8 +695,8 @@ def test_partially_filled_blocks(G, tdt):
             tail[rng.integers(0, tail.size, 3)] = np.nan          # NaN quantises to code 0 like the zeros around it
     raw = x.astype(np.float16) if tdt == F16 else bf16_from_f32(x)
     xd = torch.from_numpy(raw).to(DEV) if tdt == F16 else torch.from_numpy(raw.astype(np.int16)).to(DEV).view(torch.bfloat16)
-    c = codec.compress(xd, G)
-    payload, scales, comp = Port.compress_batch(raw, G, dtype=tdt, threads=8)
+    c = codec.compress(xd, G, scheme=scheme)
+    payload, scales, comp = Port.compress_batch(raw, G, dtype=tdt, threads=8, scheme=scheme)
     assert np.array_equal(f32_bits(c.scales.cpu().numpy()), f32_bits(scales))
     assert np.array_equal(c.comp_bytes.cpu().numpy().view(np.uint32), comp)
     gp = c.payload.cpu().numpy()
@@ -702,7 +704,7 @@ def test_partially_filled_blocks(G, tdt):
         assert np.array_equal(gp[g, :comp[g]], payload[g, :comp[g]]), (g, levels[g % len(levels)], comp[g])
     oel = torch.zeros(n_groups, dtype=torch.int32, device=DEV)
     y = codec.decompress(c, out_elems=oel)
-    want, want_n = Port.decompress_batch(payload, scales, comp, G, tdt, threads=8)
+    want, want_n = Port.decompress_batch(payload, scales, comp, G, tdt, threads=8, scheme=scheme)
     assert np.array_equal(oel.cpu().numpy().view(np.uint32), want_n)
     got = out_bits(y).reshape(n_groups, G)
     wantb = want.view(np.uint16).reshape(n_groups, G)
