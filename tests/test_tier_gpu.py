@@ -59,7 +59,8 @@ def test_offload_restore_roundtrip(G, n_groups):
 
 
 @pytest.mark.parametrize("tdt", [torch.float16, torch.bfloat16])
-def test_offload_page_groups_packed_emission(tdt):
+@pytest.mark.parametrize("scheme", [2, 3])
+def test_offload_page_groups_packed_emission(tdt, scheme):
     """4 KiB page groups: the compress kernel places the payloads in the packed stream itself (look-back over per-CTA
     totals, no pack pass).  Pages of every kind the kernel sizes differently -- noise, zero pages (closed form), constant
     and long-run pages (long path), pages with +-inf / tiny magnitudes (left to the generic kernel: they keep a whole
@@ -85,8 +86,9 @@ def test_offload_page_groups_packed_emission(tdt):
     tier = HostTier(pool_bytes=int(n_groups * G * 2 * 1.3) + (1 << 20))
     try:
         ids = np.arange(n_groups, dtype=np.uint64) + np.uint64(1000)
+        tier.set_scheme(scheme)
         tier.offload(x, G, ids)
-        c = codec.compress(x, G)
+        c = codec.compress(x, G, scheme=scheme)
         want = codec.decompress(c)
         y = tier.restore(ids, G, tdt)
         assert torch.equal(y.view(torch.int16), want.view(torch.int16))
