@@ -429,11 +429,21 @@ __device__ const HeadSelTable kHeadSel = HeadSelTable();
 // chunk's own slot (word 2 = m | (nb_rel + 1) << 8; 0 = none yet in this region) for the emission pass.  Counts the
 // interior forced heads (the 255 cap, positions nb + 255 t inside a chunk's leading stretch) and leaves
 // first | (last + 1) << 12 of the region's natural heads in *stash (first = 2048, last + 1 = 0 when there is none).
-__device__ __forceinline__ uint32_t long_first_pass_body(uint8_t* reg, int lane, uint32_t* stash) {
+__device__ __forceinline__ uint32_t long_first_pass_body(uint8_t* reg, int lane, uint32_t* stash, bool zero_tail) {
     const unsigned lt = (1u << lane) - 1u;
     uint32_t forced_acc = 0;
     int reg_last = -1, reg_first = 2048;
     for (int k = 0; k < kIters; ++k) {
+        if (k == 1 && zero_tail) {
+            // a zero region (phase 2a wrote its slots behind iteration 0 as zeros): every chunk from here on is head-less
+            // with the same nb, and the forced heads among positions [256, 2048) are the multiples of 255 in
+            // [256 - nb, 2048 - nb) -- closed form instead of seven more iterations
+            const uint32_t w2 = (uint32_t)(reg_last + 1) << 8;
+#pragma unroll
+            for (int kk = 1; kk < kIters; ++kk) *reinterpret_cast<uint32_t*>(reg + kk * 512 + lane * 16 + 8) = w2;
+            if (reg_last >= 0 && lane == 0) forced_acc += div255(2047u - (uint32_t)reg_last) - div255(255u - (uint32_t)reg_last);
+            break;
+        }
         uint8_t* slot = reg + k * 512 + lane * 16;
         const uint2 e = *reinterpret_cast<const uint2*>(slot + 8);
         const uint32_t m = head_mask8(e.x, e.y);
@@ -463,8 +473,8 @@ __device__ __forceinline__ uint32_t long_first_pass_body(uint8_t* reg, int lane,
 #define SPECKV_LONG_ATTR __noinline__
 #endif
 // the kernel body calls it out of line (inlined there, the long-run code costs the common path 5 %)
-__device__ SPECKV_LONG_ATTR uint32_t long_first_pass(uint8_t* reg, int lane, uint32_t* stash) {
-    return long_first_pass_body(reg, lane, stash);
+__device__ SPECKV_LONG_ATTR uint32_t long_first_pass(uint8_t* reg, int lane, uint32_t* stash, bool zero_tail) {
+    return long_first_pass_body(reg, lane, stash, zero_tail);
 }
 
 // Round-2 reduce of a group with long runs.  A: interior head count (low 20 bits) per region, B: first | (last + 1) << 12.
@@ -949,7 +959,7 @@ compress_fast_kernel(const T* __restrict__ in, uint32_t n_groups, uint8_t* __res
         heads = __reduce_add_sync(kFull, heads);
     }
     longr = __any_sync(kFull, longr);
-    if (longr && active && fast) heads += long_first_pass(reg, lane, &sm.stash[warp]);   // forced heads behind the region's first natural head
+    if (longr && active && fast) heads += long_first_pass(reg, lane, &sm.stash[warp], zero_region);   // forced heads behind the region's first natural head
     // one word per region: head count (natural + interior forced, <= 2056) in the low 20 bits, "has long runs" counted
     // above.  "Needs the generic kernel" (a scale outside the fast quantiser's domain) follows from the group max,
     // which every region already has: no exchange needed.
